@@ -1,0 +1,123 @@
+// Shared device/host helpers for libbacs_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "bacs_b200.h"
+
+#define BACS_VERSION 100
+
+namespace bacs {
+
+void set_error(const char* fmt, ...);
+
+#define BACS_REQUIRE(cond, ...)      \
+  do {                               \
+    if (!(cond)) {                   \
+      bacs::set_error(__VA_ARGS__);  \
+      return BACS_ERR_INVALID;       \
+    }                                \
+  } while (0)
+
+#define BACS_CHECK_LAUNCH(name)                                               \
+  do {                                                                        \
+    cudaError_t e__ = cudaGetLastError();                                     \
+    if (e__ != cudaSuccess) {                                                 \
+      bacs::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return BACS_ERR_CUDA;                                                   \
+    }                                                                         \
+  } while (0)
+
+int sm_count();
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- storage dtype <-> float ---------------------------------------------------------
+template <typename T> struct DT;
+template <> struct DT<float> {
+  static constexpr int id = BACS_F32;
+  __device__ static __forceinline__ float to_f(float v) { return v; }
+  __device__ static __forceinline__ float from_f(float v) { return v; }
+};
+template <> struct DT<__nv_bfloat16> {
+  static constexpr int id = BACS_BF16;
+  __device__ static __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __device__ static __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+template <> struct DT<__half> {
+  static constexpr int id = BACS_F16;
+  __device__ static __forceinline__ float to_f(__half v) { return __half2float(v); }
+  __device__ static __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+};
+
+static inline size_t dtype_size(int dtype) { return dtype == BACS_F32 ? 4 : 2; }
+
+#define BACS_DISPATCH_DTYPE(dtype, T, ...)                    \
+  switch (dtype) {                                            \
+    case BACS_F32: { using T = float; __VA_ARGS__; } break;   \
+    case BACS_BF16: { using T = __nv_bfloat16; __VA_ARGS__; } break; \
+    case BACS_F16: { using T = __half; __VA_ARGS__; } break;  \
+    default: bacs::set_error("unknown dtype %d", dtype); return BACS_ERR_INVALID; \
+  }
+
+// ---- warp / block reductions ---------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the block; result valid in thread 0.  `scratch` holds >= 32 T's.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  T r = (threadIdx.x < nw) ? scratch[threadIdx.x] : T(0);
+  if (wid == 0) r = warp_sum(r);
+  return r;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// accurate sigmoid (used where a threshold decision depends on it)
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Source index / weight of torch's bilinear kernels (fp32 arithmetic, matching
+// area_pixel_compute_source_index in ATen/native/UpSample.h).
+struct Lerp {
+  int i0, i1;
+  float w1;  // weight of i1; weight of i0 is 1 - w1
+};
+// Explicitly rounded (no FMA contraction) so the indices match an op-by-op evaluation.
+__device__ __forceinline__ Lerp lerp_align_corners(int dst, int in_size, float scale) {
+  // scale = (in-1)/(out-1)
+  const float src = __fmul_rn(scale, (float)dst);
+  Lerp l;
+  l.i0 = min((int)src, in_size - 1);
+  l.i1 = l.i0 + (l.i0 < in_size - 1 ? 1 : 0);
+  l.w1 = __fsub_rn(src, (float)l.i0);
+  return l;
+}
+__device__ __forceinline__ Lerp lerp_half_pixel(int dst, int in_size, float scale) {
+  // scale = in/out ; src = scale*(dst+0.5)-0.5 clamped at 0
+  float src = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+  src = src < 0.f ? 0.f : src;
+  Lerp l;
+  l.i0 = min((int)src, in_size - 1);
+  l.i1 = l.i0 + (l.i0 < in_size - 1 ? 1 : 0);
+  l.w1 = __fsub_rn(src, (float)l.i0);
+  return l;
+}
+static inline float ac_scale(int in_size, int out_size) {
+  return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+}
+static inline float hp_scale(int in_size, int out_size) { return (float)in_size / (float)out_size; }
+
+}  // namespace bacs

@@ -1,0 +1,351 @@
+// DER logit MSE, confusion matrix + metrics, device-side scalar helpers, state packing.
+#include "common.cuh"
+
+namespace bacs {
+
+// -------------------------------------------------------------------------------------
+// Dark-experience-replay logit MSE with transplant (loss/bacs_loss.py:387-431)
+// -------------------------------------------------------------------------------------
+template <typename T, typename M>
+__global__ void __launch_bounds__(256) der_mse_kernel(const T* __restrict__ sem, const M* __restrict__ mem,
+                                                      int truncate, const int32_t* __restrict__ cut, int ignore_rep_bg,
+                                                      int K, int hw, int64_t total, float grad_coef,
+                                                      T* __restrict__ dsem, double* __restrict__ partials) {
+  __shared__ float scratch[32];
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t jk = i / hw;
+    const int k = (int)(jk % K);
+    const int j = (int)(jk / K);
+    const float s = DT<T>::to_f(sem[i]);
+    float m;
+    if (k >= cut[j] || (ignore_rep_bg && k == 0)) {
+      m = s;  // transplanted from the live logits
+    } else {
+      m = (float)mem[i];
+      if (truncate) m = truncf(m);  // preprocess_batch's .long() (base_loss.py:274-278)
+    }
+    const float d = s - m;
+    acc = fmaf(d, d, acc);
+    if (dsem) dsem[i] = DT<T>::from_f(2.f * grad_coef * d);
+  }
+  const float r = block_sum(acc, scratch);
+  if (threadIdx.x == 0) partials[blockIdx.x] = (double)r;
+}
+
+__global__ void __launch_bounds__(1024) sum_partials2_kernel(const double* __restrict__ partials, int n,
+                                                             double* __restrict__ out) {
+  __shared__ double scratch[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += partials[i];
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
+static int der_blocks(int64_t total) {
+  int64_t b = (total + 256 * 4 - 1) / (256 * 4);
+  const int64_t cap = (int64_t)sm_count() * 4;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// -------------------------------------------------------------------------------------
+// Confusion matrix: block-private K*K histogram in shared memory, run-length aggregated
+// per thread, flushed with 64-bit global atomics.
+//   reference: training/metrics.py:38-50 + torchmetrics 0.6.0 _confusion_matrix_update
+// -------------------------------------------------------------------------------------
+template <typename P, bool SMEM>
+__global__ void __launch_bounds__(256) confmat_kernel(const P* __restrict__ preds, const int64_t* __restrict__ target,
+                                                      int64_t n, int K, unsigned long long* __restrict__ confmat,
+                                                      unsigned long long* __restrict__ oob) {
+  extern __shared__ unsigned int sh[];
+  const int KK = K * K;
+  if (SMEM) {
+    for (int i = threadIdx.x; i < KK; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+  }
+  unsigned int n_oob = 0;
+  const int64_t nchunk = (n + 7) >> 3;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nchunk; c += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t base = c << 3;
+    const int cnt = (int)min((int64_t)8, n - base);
+    int cur = -1;
+    unsigned int run = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < cnt) {
+        // metrics.py:45-46 casts both to int32 before the range test
+        const int t = (int)target[base + k];
+        const int p = (int)preds[base + k];
+        int bin = -1;
+        if (t >= 0 && t < K) {
+          if (p >= 0 && p < K) bin = t * K + p;
+          else ++n_oob;
+        }
+        if (bin == cur) {
+          ++run;
+        } else {
+          if (run && cur >= 0) {
+            if (SMEM) atomicAdd(&sh[cur], run);
+            else atomicAdd(&confmat[cur], (unsigned long long)run);
+          }
+          cur = bin;
+          run = 1;
+        }
+      }
+    }
+    if (run && cur >= 0) {
+      if (SMEM) atomicAdd(&sh[cur], run);
+      else atomicAdd(&confmat[cur], (unsigned long long)run);
+    }
+  }
+  if (n_oob && oob) atomicAdd(oob, (unsigned long long)n_oob);
+  if (SMEM) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < KK; i += blockDim.x)
+      if (sh[i]) atomicAdd(&confmat[i], (unsigned long long)sh[i]);
+  }
+}
+
+// metrics.py:52-88 (the reference's fp/fn naming is kept: "fn" = column sum - tp,
+// "fp" = row sum - tp) + torchmetrics' IoU from the matrix (absent -> 0, reduction none).
+__global__ void __launch_bounds__(256) confmat_metrics_kernel(const int64_t* __restrict__ cm, int K,
+                                                              float* __restrict__ out) {
+  __shared__ float scratch[32];
+  __shared__ long long s_total;
+  __shared__ float s_miou;
+  if (threadIdx.x == 0) s_total = 0;
+  __syncthreads();
+  long long part = 0;
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x) part += cm[i];
+  // exact integer block sum
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd((unsigned long long*)&s_total, (unsigned long long)part);
+  __syncthreads();
+  const long long total = s_total;
+  float iou_sum = 0.f;
+  for (int c = threadIdx.x; c < K; c += blockDim.x) {
+    long long row = 0, col = 0;
+    for (int k = 0; k < K; ++k) {
+      row += cm[c * K + k];
+      col += cm[k * K + c];
+    }
+    const long long tp = cm[c * K + c];
+    const long long fn = col - tp, fp = row - tp;
+    const long long tn = total - (tp + fn + fp);
+    auto div = [](long long a, long long b) {
+      const float r = (float)a / (float)b;
+      return isnan(r) ? 0.f : r;
+    };
+    const long long uni = row + col - tp;
+    const float iou = uni == 0 ? 0.f : (float)tp / (float)uni;
+    out[0 * K + c] = iou;
+    out[1 * K + c] = div(tp + tn, tp + fp + fn + tn);
+    out[2 * K + c] = div(tp, tp + fp);
+    out[3 * K + c] = div(tp, tp + fn);
+    out[4 * K + c] = div(tn, tn + fp);
+    iou_sum += iou;
+  }
+  const float s = block_sum(iou_sum, scratch);
+  if (threadIdx.x == 0) s_miou = s / (float)K;
+  __syncthreads();
+  for (int c = threadIdx.x; c < K; c += blockDim.x) out[5 * K + c] = s_miou;
+}
+
+// -------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) scale_inplace_kernel(T* __restrict__ x, int64_t n, const float* __restrict__ g) {
+  const float s = *g;
+  if (s == 1.f) return;  // uniform early exit: the common (bf16, no grad scaler) case costs nothing
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = DT<T>::from_f(DT<T>::to_f(x[i]) * s);
+}
+
+__global__ void pack_state_kernel(const double* __restrict__ sums, const double* __restrict__ counts, int TD, int T,
+                                  const int64_t* __restrict__ confmat, int KK, double* __restrict__ packed) {
+  const int n = TD + T + KK;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double v;
+    if (i < TD) v = sums[i];
+    else if (i < TD + T) v = counts[i - TD];
+    else v = (double)confmat[i - TD - T];
+    packed[i] = v;
+  }
+}
+__global__ void unpack_state_kernel(const double* __restrict__ packed, int TD, int T, double* __restrict__ sums,
+                                    double* __restrict__ counts, int64_t* __restrict__ confmat, int KK) {
+  const int n = TD + T + KK;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double v = packed[i];
+    if (i < TD) sums[i] = v;
+    else if (i < TD + T) counts[i - TD] = v;
+    else confmat[i - TD - T] = (int64_t)llrint(v);
+  }
+}
+
+// loss = sum_i coef[i] * src_i[idx_i] * (gate ? [*gate != 0] : 1) / (den_i ? den_i[didx_i] : 1)
+struct CombineTerm {
+  const double* src;
+  int idx;
+  const double* den;
+  int didx;
+  float coef;
+};
+struct CombineArgs {
+  CombineTerm t[8];
+  int n;
+};
+__global__ void combine_kernel(CombineArgs a, float* __restrict__ out) {
+  double s = 0.0;
+  for (int i = 0; i < a.n; ++i) {
+    double v = a.t[i].src[a.t[i].idx] * (double)a.t[i].coef;
+    if (a.t[i].den) {
+      v = v / a.t[i].den[a.t[i].didx];  // IEEE: 0/0 -> NaN exactly like torch's mean over nothing
+    }
+    s += v;
+  }
+  out[0] = (float)s;
+}
+
+}  // namespace bacs
+
+using namespace bacs;
+
+extern "C" {
+
+size_t bacs_der_workspace_bytes(int Br, int K, int hw) {
+  return align_up(sizeof(double) * (size_t)der_blocks((int64_t)Br * K * hw), 256);
+}
+
+int bacs_der_mse(const void* sem_logits, int dtype, const void* memory_logits, int memory_is_int64, int truncate,
+                 const int32_t* cut, int ignore_rep_bg, int Br, int K, int hw, float grad_coef, double* loss_sum,
+                 void* dsem, void* workspace, size_t workspace_bytes, bacs_stream_t stream) {
+  BACS_REQUIRE(sem_logits && memory_logits && cut && loss_sum && workspace, "bacs_der_mse: null pointer");
+  BACS_REQUIRE(Br > 0 && K > 0 && hw > 0, "bacs_der_mse: bad shape");
+  const int64_t total = (int64_t)Br * K * hw;
+  const int blocks = der_blocks(total);
+  if (workspace_bytes < sizeof(double) * (size_t)blocks) {
+    set_error("bacs_der_mse: workspace too small");
+    return BACS_ERR_WORKSPACE;
+  }
+  double* partials = reinterpret_cast<double*>(workspace);
+  cudaStream_t s = (cudaStream_t)stream;
+  BACS_DISPATCH_DTYPE(dtype, TT, {
+    if (memory_is_int64)
+      der_mse_kernel<TT, int64_t><<<blocks, 256, 0, s>>>(reinterpret_cast<const TT*>(sem_logits),
+                                                         reinterpret_cast<const int64_t*>(memory_logits), 0, cut,
+                                                         ignore_rep_bg, K, hw, total, grad_coef,
+                                                         reinterpret_cast<TT*>(dsem), partials);
+    else
+      der_mse_kernel<TT, float><<<blocks, 256, 0, s>>>(reinterpret_cast<const TT*>(sem_logits),
+                                                       reinterpret_cast<const float*>(memory_logits), truncate, cut,
+                                                       ignore_rep_bg, K, hw, total, grad_coef,
+                                                       reinterpret_cast<TT*>(dsem), partials);
+  });
+  BACS_CHECK_LAUNCH("bacs_der_mse");
+  sum_partials2_kernel<<<1, 1024, 0, s>>>(partials, blocks, loss_sum);
+  BACS_CHECK_LAUNCH("bacs_der_mse(reduce)");
+  return BACS_OK;
+}
+
+int bacs_confmat_accumulate(const void* preds, int preds_is_float, const int64_t* target, int64_t n, int K,
+                            int64_t* confmat, int64_t* oob, bacs_stream_t stream) {
+  BACS_REQUIRE(preds && target && confmat, "bacs_confmat_accumulate: null pointer");
+  BACS_REQUIRE(K > 0 && K <= 4096 && n >= 0, "bacs_confmat_accumulate: bad K or n");
+  if (n == 0) return BACS_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t nchunk = (n + 7) >> 3;
+  int64_t blocks = (nchunk + 255) / 256;
+  const size_t smem = sizeof(unsigned int) * (size_t)K * K;
+  const bool use_smem = smem <= 96 * 1024;
+  const int64_t cap = (int64_t)sm_count() * (use_smem && smem > 24 * 1024 ? 2 : 8);
+  if (blocks > cap) blocks = cap;
+  unsigned long long* cm = reinterpret_cast<unsigned long long*>(confmat);
+  unsigned long long* ob = reinterpret_cast<unsigned long long*>(oob);
+#define LAUNCH_CM(PT)                                                                                          \
+  do {                                                                                                         \
+    if (use_smem) {                                                                                            \
+      auto kern = confmat_kernel<PT, true>;                                                                    \
+      if (smem > 48 * 1024) {                                                                                  \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        if (e != cudaSuccess) {                                                                                \
+          set_error("bacs_confmat_accumulate: shared memory opt-in failed: %s", cudaGetErrorString(e));       \
+          return BACS_ERR_CUDA;                                                                                \
+        }                                                                                                      \
+      }                                                                                                        \
+      kern<<<(unsigned)blocks, 256, smem, s>>>(reinterpret_cast<const PT*>(preds), target, n, K, cm, ob);      \
+    } else {                                                                                                   \
+      confmat_kernel<PT, false><<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const PT*>(preds), target, n, K, \
+                                                                 cm, ob);                                      \
+    }                                                                                                          \
+  } while (0)
+  if (preds_is_float) LAUNCH_CM(float);
+  else LAUNCH_CM(int64_t);
+#undef LAUNCH_CM
+  BACS_CHECK_LAUNCH("bacs_confmat_accumulate");
+  return BACS_OK;
+}
+
+int bacs_confmat_metrics(const int64_t* confmat, int K, float* out, bacs_stream_t stream) {
+  BACS_REQUIRE(confmat && out && K > 0, "bacs_confmat_metrics: bad arguments");
+  confmat_metrics_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(confmat, K, out);
+  BACS_CHECK_LAUNCH("bacs_confmat_metrics");
+  return BACS_OK;
+}
+
+int bacs_scale_inplace(void* x, int dtype, int64_t n, const float* g_dev, bacs_stream_t stream) {
+  BACS_REQUIRE(x && g_dev && n >= 0, "bacs_scale_inplace: bad arguments");
+  if (n == 0) return BACS_OK;
+  int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t s = (cudaStream_t)stream;
+  BACS_DISPATCH_DTYPE(dtype, TT,
+                      { scale_inplace_kernel<TT><<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<TT*>(x), n, g_dev); });
+  BACS_CHECK_LAUNCH("bacs_scale_inplace");
+  return BACS_OK;
+}
+
+int bacs_pack_state(const double* sums, const double* counts, int T, int D, const int64_t* confmat, int K,
+                    double* packed, bacs_stream_t stream) {
+  BACS_REQUIRE(packed && (T == 0 || (sums && counts)) && (K == 0 || confmat), "bacs_pack_state: null pointer");
+  const int n = T * D + T + K * K;
+  if (n == 0) return BACS_OK;
+  pack_state_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, counts, T * D, T, confmat, K * K, packed);
+  BACS_CHECK_LAUNCH("bacs_pack_state");
+  return BACS_OK;
+}
+
+int bacs_unpack_state(const double* packed, int T, int D, double* sums, double* counts, int64_t* confmat, int K,
+                      bacs_stream_t stream) {
+  BACS_REQUIRE(packed && (T == 0 || (sums && counts)) && (K == 0 || confmat), "bacs_unpack_state: null pointer");
+  const int n = T * D + T + K * K;
+  if (n == 0) return BACS_OK;
+  unpack_state_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(packed, T * D, T, sums, counts, confmat,
+                                                                        K * K);
+  BACS_CHECK_LAUNCH("bacs_unpack_state");
+  return BACS_OK;
+}
+
+/* out[0] = sum_i coef[i] * src[i][idx[i]] / (den[i] ? den[i][didx[i]] : 1)   (n <= 8 terms)
+ * -- assembles the step's loss scalar on the device from the fp64 accumulators. */
+int bacs_combine_scalars(int n, const double* const* src, const int* idx, const double* const* den, const int* didx,
+                         const float* coef, float* out, bacs_stream_t stream) {
+  BACS_REQUIRE(n > 0 && n <= 8 && src && idx && coef && out, "bacs_combine_scalars: bad arguments");
+  CombineArgs a;
+  a.n = n;
+  for (int i = 0; i < n; ++i) {
+    a.t[i].src = src[i];
+    a.t[i].idx = idx[i];
+    a.t[i].den = den ? den[i] : nullptr;
+    a.t[i].didx = didx ? didx[i] : 0;
+    a.t[i].coef = coef[i];
+    BACS_REQUIRE(src[i], "bacs_combine_scalars: null source %d", i);
+  }
+  combine_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a, out);
+  BACS_CHECK_LAUNCH("bacs_combine_scalars");
+  return BACS_OK;
+}
+
+}  // extern "C"

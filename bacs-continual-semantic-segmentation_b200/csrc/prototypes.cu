@@ -1,0 +1,223 @@
+// Prototype kernels: label-masked segmented reduction of penultimate features into
+// per-task sums (reference-exact row split or per-channel), running-mean update.
+//   reference: loss/prototypes.py:127-163 (update_feats_prototypes), 31-40 (ready)
+#include "common.cuh"
+
+namespace bacs {
+
+// Per (image b, channel c) the masked pixels of task g form one run of n_bg elements in
+// the reference's flattened masked-index tensor, at flat position
+//     base = D * sum_{b'<b} n_b'g + c * n_bg .
+// `.view(D, -1)` cuts that sequence into D rows of N_g elements, so the run spans at most
+// two rows: r0 = base / N_g gets the elements with rank < split, r0 + 1 the rest, where
+// split = (r0 + 1) * N_g - base.  Per-channel mode is the same code with split = n_bg.
+template <typename T, int TMAX>
+__global__ void __launch_bounds__(256) proto_accumulate_kernel(const T* __restrict__ feat, int B, int D, int hw,
+                                                               const int8_t* __restrict__ task,
+                                                               const int32_t* __restrict__ rank,
+                                                               const int32_t* __restrict__ n_bt, int Tn, int mode,
+                                                               float* __restrict__ partial /* [B,D,Tn,2] */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * (blockDim.x >> 5) + wid;
+  if (c >= D) return;
+  // lane g holds the split point of task g
+  int split = 0x7fffffff;
+  if (mode == 0 && lane < Tn) {
+    long long pre = 0, tot = 0;
+    for (int bb = 0; bb < B; ++bb) {
+      const int n = n_bt[bb * Tn + lane];
+      if (bb < b) pre += n;
+      tot += n;
+    }
+    const long long nb = n_bt[b * Tn + lane];
+    if (tot > 0) {
+      const long long base = (long long)D * pre + (long long)c * nb;
+      const long long r0 = base / tot;
+      const long long sp = (r0 + 1) * tot - base;
+      split = sp > 0x7fffffffLL ? 0x7fffffff : (int)sp;
+    }
+  }
+  float lo[TMAX], hi[TMAX];
+#pragma unroll
+  for (int g = 0; g < TMAX; ++g) lo[g] = hi[g] = 0.f;
+  const T* row = feat + ((int64_t)b * D + c) * hw;
+  const int8_t* tk = task + (int64_t)b * hw;
+  const int32_t* rk = rank + (int64_t)b * hw;
+  for (int q0 = 0; q0 < hw; q0 += 32) {
+    const int q = q0 + lane;
+    int t = -1;
+    float v = 0.f;
+    int k = 0;
+    if (q < hw) {
+      t = tk[q];
+      if (t >= 0) {
+        v = DT<T>::to_f(row[q]);
+        k = rk[q];
+      }
+    }
+    const int sp = __shfl_sync(0xffffffffu, split, t < 0 ? 0 : t);
+    const bool low = k < sp;
+#pragma unroll
+    for (int g = 0; g < TMAX; ++g) {
+      const float m = (t == g) ? v : 0.f;
+      lo[g] += low ? m : 0.f;
+      hi[g] += low ? 0.f : m;
+    }
+  }
+  float* out = partial + (((int64_t)b * D + c) * Tn) * 2;
+#pragma unroll
+  for (int g = 0; g < TMAX; ++g) {
+    if (g < Tn) {
+      const float a = warp_sum(lo[g]);
+      const float h2 = warp_sum(hi[g]);
+      if (lane == 0) {
+        out[g * 2 + 0] = a;
+        out[g * 2 + 1] = h2;
+      }
+    }
+  }
+}
+
+// One thread per (task g, output row r): gathers the partial runs that land in row r.
+__global__ void __launch_bounds__(256) proto_finalize_kernel(const float* __restrict__ partial, int B, int D,
+                                                             const int32_t* __restrict__ n_bt, int Tn, int mode,
+                                                             double* __restrict__ sums, double* __restrict__ counts) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Tn * D) return;
+  const int g = idx / D, r = idx - g * D;
+  long long tot = 0;
+  for (int bb = 0; bb < B; ++bb) tot += n_bt[bb * Tn + g];
+  if (r == 0) counts[g] = (double)tot;
+  double acc = 0.0;
+  if (tot > 0) {
+    if (mode != 0) {
+      for (int bb = 0; bb < B; ++bb) acc += (double)partial[(((int64_t)bb * D + r) * Tn + g) * 2];
+    } else {
+      long long pre = 0;
+      for (int bb = 0; bb < B; ++bb) {
+        const long long nb = n_bt[bb * Tn + g];
+        if (nb > 0) {
+          // channels c with r0(c) == r   <=>  r*tot <= D*pre + c*nb < (r+1)*tot
+          const long long off = (long long)D * pre;
+          auto ceil_div = [](long long a, long long d) { return a <= 0 ? 0LL : (a + d - 1) / d; };
+          long long c_lo = ceil_div((long long)r * tot - off, nb);
+          long long c_hi = ceil_div((long long)(r + 1) * tot - off, nb);
+          if (c_hi > D) c_hi = D;
+          for (long long c = c_lo; c < c_hi; ++c) acc += (double)partial[(((int64_t)bb * D + c) * Tn + g) * 2 + 0];
+          // channels with r0(c) == r - 1 contribute their high part
+          if (r > 0) {
+            long long d_lo = ceil_div((long long)(r - 1) * tot - off, nb);
+            long long d_hi = ceil_div((long long)r * tot - off, nb);
+            if (d_hi > D) d_hi = D;
+            for (long long c = d_lo; c < d_hi; ++c)
+              acc += (double)partial[(((int64_t)bb * D + c) * Tn + g) * 2 + 1];
+          }
+        }
+        pre += nb;
+      }
+    }
+  }
+  sums[idx] = acc;
+}
+
+// proto[g] = (S[g] + cnt[g]*proto[g]) / (cnt[g] + N[g]), cnt[g] += N[g]; separate fp32
+// roundings per operation (torch evaluates them as separate kernels).
+__global__ void __launch_bounds__(512) proto_update_kernel(float* __restrict__ proto, void* __restrict__ count,
+                                                           int count_is_int64, const double* __restrict__ sums,
+                                                           const double* __restrict__ counts, int Tn, int D,
+                                                           int32_t* __restrict__ ready) {
+  __shared__ float s_old[64], s_den[64];
+  __shared__ int s_upd[64];
+  __shared__ int s_nonzero;
+  if (threadIdx.x == 0) s_nonzero = 0;
+  __syncthreads();
+  if (threadIdx.x < Tn) {
+    const int g = threadIdx.x;
+    const double n = counts[g];
+    float oldc, den;
+    int nz;
+    if (count_is_int64) {
+      int64_t* c = reinterpret_cast<int64_t*>(count);
+      const int64_t o = c[g];
+      const int64_t nn = o + (int64_t)n;
+      oldc = (float)o;
+      den = (float)nn;
+      if (n > 0) c[g] = nn;
+      nz = (n > 0 ? nn : o) != 0;
+    } else {
+      float* c = reinterpret_cast<float*>(count);
+      const float o = c[g];
+      const float nn = __fadd_rn(o, (float)n);
+      oldc = o;
+      den = nn;
+      if (n > 0) c[g] = nn;
+      nz = (n > 0 ? nn : o) != 0.f;
+    }
+    s_old[g] = oldc;
+    s_den[g] = den;
+    s_upd[g] = n > 0;
+    if (nz) atomicAdd(&s_nonzero, 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Tn * D; i += blockDim.x) {
+    const int g = i / D;
+    if (s_upd[g]) {
+      const float num = __fadd_rn((float)sums[i], __fmul_rn(s_old[g], proto[i]));
+      proto[i] = __fdiv_rn(num, s_den[g]);
+    }
+  }
+  if (threadIdx.x == 0 && ready) *ready = (s_nonzero == Tn) ? 1 : 0;
+}
+
+}  // namespace bacs
+
+using namespace bacs;
+
+extern "C" {
+
+size_t bacs_proto_workspace_bytes(int B, int D, int T) {
+  return align_up((size_t)B * D * T * 2 * sizeof(float), 256);
+}
+
+int bacs_proto_accumulate(const void* features, int dtype, int B, int D, int h, int w, const int8_t* task,
+                          const int32_t* rank, const int32_t* n_bt, int T, int mode, double* sums, double* counts,
+                          void* workspace, size_t workspace_bytes, bacs_stream_t stream) {
+  BACS_REQUIRE(features && task && rank && n_bt && sums && counts && workspace, "bacs_proto_accumulate: null pointer");
+  BACS_REQUIRE(B > 0 && D > 0 && h > 0 && w > 0 && B < 65536, "bacs_proto_accumulate: bad shape");
+  BACS_REQUIRE(T > 0 && T <= 32, "bacs_proto_accumulate: T=%d not in [1,32]", T);
+  BACS_REQUIRE(mode == 0 || mode == 1, "bacs_proto_accumulate: mode must be 0 (exact) or 1 (channel)");
+  if (workspace_bytes < bacs_proto_workspace_bytes(B, D, T)) {
+    set_error("bacs_proto_accumulate: workspace %zu < %zu", workspace_bytes, bacs_proto_workspace_bytes(B, D, T));
+    return BACS_ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  float* partial = reinterpret_cast<float*>(workspace);
+  const int hw = h * w;
+  dim3 grid((D + 7) / 8, B);
+#define LAUNCH_ACC(TT, TM) \
+  proto_accumulate_kernel<TT, TM><<<grid, 256, 0, s>>>(reinterpret_cast<const TT*>(features), B, D, hw, task, rank, \
+                                                       n_bt, T, mode, partial)
+  BACS_DISPATCH_DTYPE(dtype, TT, {
+    if (T <= 4) LAUNCH_ACC(TT, 4);
+    else if (T <= 8) LAUNCH_ACC(TT, 8);
+    else if (T <= 16) LAUNCH_ACC(TT, 16);
+    else LAUNCH_ACC(TT, 32);
+  });
+#undef LAUNCH_ACC
+  BACS_CHECK_LAUNCH("bacs_proto_accumulate");
+  proto_finalize_kernel<<<(T * D + 255) / 256, 256, 0, s>>>(partial, B, D, n_bt, T, mode, sums, counts);
+  BACS_CHECK_LAUNCH("bacs_proto_accumulate(finalize)");
+  return BACS_OK;
+}
+
+int bacs_proto_update(float* proto, void* count, int count_is_int64, const double* sums, const double* counts, int T,
+                      int D, int32_t* ready, bacs_stream_t stream) {
+  BACS_REQUIRE(proto && count && sums && counts, "bacs_proto_update: null pointer");
+  BACS_REQUIRE(T > 0 && T <= 64 && D > 0, "bacs_proto_update: bad shape");
+  proto_update_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(proto, count, count_is_int64, sums, counts, T, D, ready);
+  BACS_CHECK_LAUNCH("bacs_proto_update");
+  return BACS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,380 @@
+"""Tensor-level wrappers over the C ABI: argument validation, output / workspace
+allocation through PyTorch's caching allocator, and stream plumbing.  Every op is
+asynchronous on the current CUDA stream and never synchronises with the host.
+
+PyTorch is plumbing here (device memory, streams); the arithmetic is in csrc/*.cu.
+There is deliberately no CPU implementation: a CPU tensor raises."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import PixelArgs, check
+
+_DTYPES = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16, torch.float16: _cabi.F16}
+
+
+def _lib():
+    return _cabi.load()
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError("bacs_b200: unsupported feature dtype %s (fp32, bf16, fp16 only)" % t.dtype)
+
+
+def _cuda(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("bacs_b200.%s: expected a CUDA tensor (there is no CPU path)" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("bacs_b200.%s: expected dtype %s, got %s" % (name, dtype, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------
+# labels
+# --------------------------------------------------------------------------------------
+def label_hist(labels: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    labels = _cuda(labels, "label_hist", torch.int64)
+    if out is None:
+        out = torch.zeros(257, dtype=torch.int64, device=labels.device)
+    check(_lib().bacs_label_hist(labels.data_ptr(), labels.numel(), out.data_ptr(), _stream()), "bacs_label_hist")
+    return out
+
+
+def label_remap(labels: torch.Tensor, map1: torch.Tensor, masking1: int, map2: Optional[torch.Tensor] = None,
+                masking2: int = 0, lo: int = -1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """labels int64 [N, ...] (remapped per leading-dim image); map1/map2 int32 [n_dom]."""
+    labels = _cuda(labels, "label_remap", torch.int64)
+    map1 = _cuda(map1, "label_remap", torch.int32)
+    if map2 is not None:
+        map2 = _cuda(map2, "label_remap", torch.int32)
+        if map2.numel() != map1.numel():
+            raise ValueError("label_remap: map1 and map2 must cover the same domain")
+    n_images = labels.shape[0] if labels.dim() > 2 else 1
+    ppi = labels.numel() // max(n_images, 1)
+    if out is None:
+        out = torch.empty_like(labels)
+    lib = _lib()
+    ws = _ws(lib.bacs_label_remap_workspace_bytes(n_images), labels.device)
+    check(lib.bacs_label_remap(labels.data_ptr(), out.data_ptr(), n_images, ppi, lo, map1.numel(), map1.data_ptr(),
+                               masking1, _ptr(map2), masking2, ws.data_ptr(), _stream()), "bacs_label_remap")
+    return out
+
+
+def label_downsample_task(labels: torch.Tensor, h: int, w: int, task_lut: torch.Tensor, T: int,
+                          want_labels_down: bool = False):
+    labels = _cuda(labels, "label_downsample_task", torch.int64)
+    task_lut = _cuda(task_lut, "label_downsample_task", torch.int32)
+    B, H, W = labels.shape
+    dev = labels.device
+    task = torch.empty((B, h, w), dtype=torch.int8, device=dev)
+    rank = torch.empty((B, h, w), dtype=torch.int32, device=dev)
+    n_bt = torch.empty((B, T), dtype=torch.int32, device=dev)
+    down = torch.empty((B, h, w), dtype=torch.int64, device=dev) if want_labels_down else None
+    check(_lib().bacs_label_downsample_task(labels.data_ptr(), B, H, W, h, w, task_lut.data_ptr(), T, _ptr(down),
+                                            task.data_ptr(), rank.data_ptr(), n_bt.data_ptr(), _stream()),
+          "bacs_label_downsample_task")
+    return task, rank, n_bt, down
+
+
+# --------------------------------------------------------------------------------------
+# prototypes
+# --------------------------------------------------------------------------------------
+def proto_accumulate(features: torch.Tensor, task: torch.Tensor, rank: torch.Tensor, n_bt: torch.Tensor, T: int,
+                     mode: int = 0, out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns (sums fp64 [T,D], counts fp64 [T]) as two views of ONE packed fp64 buffer
+    [T*D + T] so that a single all-reduce moves both."""
+    features = _cuda(features, "proto_accumulate")
+    B, D, h, w = features.shape
+    dev = features.device
+    packed = out if out is not None else torch.empty(T * D + T, dtype=torch.float64, device=dev)
+    sums, counts = packed[:T * D].view(T, D), packed[T * D:T * D + T]
+    lib = _lib()
+    ws = _ws(lib.bacs_proto_workspace_bytes(B, D, T), dev)
+    check(lib.bacs_proto_accumulate(features.data_ptr(), _dt(features), B, D, h, w, task.data_ptr(), rank.data_ptr(),
+                                    n_bt.data_ptr(), T, mode, sums.data_ptr(), counts.data_ptr(), ws.data_ptr(),
+                                    ws.numel(), _stream()), "bacs_proto_accumulate")
+    return sums, counts
+
+
+def proto_update(proto: torch.Tensor, count: torch.Tensor, sums: torch.Tensor, counts: torch.Tensor,
+                 ready: Optional[torch.Tensor] = None) -> torch.Tensor:
+    proto = _cuda(proto, "proto_update", torch.float32)
+    if not proto.is_contiguous() or not count.is_contiguous():
+        raise ValueError("proto_update works in place: proto and count must be contiguous")
+    if count.dtype not in (torch.int64, torch.float32):
+        raise TypeError("proto_update: count must be int64 or float32 (reference Q3)")
+    T, D = proto.shape
+    if ready is None:
+        ready = torch.empty(1, dtype=torch.int32, device=proto.device)
+    check(_lib().bacs_proto_update(proto.data_ptr(), count.data_ptr(), int(count.dtype == torch.int64),
+                                   sums.data_ptr(), counts.data_ptr(), T, D, ready.data_ptr(), _stream()),
+          "bacs_proto_update")
+    return ready
+
+
+# --------------------------------------------------------------------------------------
+# seen / unseen heads
+# --------------------------------------------------------------------------------------
+def seen_logits(features: torch.Tensor, proto: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    features = _cuda(features, "seen_logits")
+    proto = _cuda(proto.float(), "seen_logits")
+    weight = _cuda(weight.float(), "seen_logits")
+    bias = _cuda(bias.float(), "seen_logits")
+    B, D, h, w = features.shape
+    T = proto.shape[0]
+    z = torch.empty((B, T, h, w), dtype=torch.float32, device=features.device)
+    check(_lib().bacs_seen_logits(features.data_ptr(), _dt(features), B, D, h, w, proto.data_ptr(), weight.data_ptr(),
+                                  bias.data_ptr(), T, z.data_ptr(), _stream()), "bacs_seen_logits")
+    return z
+
+
+def seen_upsample(z: torch.Tensor, scale: int = 16, apply_sigmoid: bool = False) -> torch.Tensor:
+    z = _cuda(z, "seen_upsample", torch.float32)
+    B, T, h, w = z.shape
+    out = torch.empty((B, T, h * scale, w * scale), dtype=torch.float32, device=z.device)
+    check(_lib().bacs_seen_upsample(z.data_ptr(), B, T, h, w, scale, int(apply_sigmoid), out.data_ptr(), _stream()),
+          "bacs_seen_upsample")
+    return out
+
+
+def seen_head_backward(features: torch.Tensor, proto_t: torch.Tensor, weight_t: torch.Tensor, gz: torch.Tensor,
+                       scale_dev: Optional[torch.Tensor], want_dfeatures: bool):
+    features = _cuda(features, "seen_head_backward")
+    B, D, h, w = features.shape
+    dev = features.device
+    dweight = torch.empty(D, dtype=torch.float32, device=dev)
+    dbias = torch.empty(1, dtype=torch.float32, device=dev)
+    dfeat = torch.empty_like(features) if want_dfeatures else None
+    check(_lib().bacs_seen_head_backward(features.data_ptr(), _dt(features), B, D, h, w, proto_t.data_ptr(),
+                                         weight_t.data_ptr(), gz.data_ptr(), _ptr(scale_dev), dweight.data_ptr(),
+                                         dbias.data_ptr(), _ptr(dfeat), _stream()), "bacs_seen_head_backward")
+    return dweight, dbias, dfeat
+
+
+def focal_scale(acc: torch.Tensor, ready: Optional[torch.Tensor], weight: float):
+    dev = acc.device
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    check(_lib().bacs_focal_scale(acc.data_ptr(), _ptr(ready), float(weight), out.data_ptr(),
+                                  out.data_ptr() + 4, _stream()), "bacs_focal_scale")
+    return out[0:1], out[1:2]
+
+
+# --------------------------------------------------------------------------------------
+# fused per-pixel kernel
+# --------------------------------------------------------------------------------------
+def pixel_loss(logits: torch.Tensor, labels: torch.Tensor, mode: int, *, want_grad: bool, want_preds: bool = True,
+               z: Optional[torch.Tensor] = None, want_distill_mask: bool = False, focal_head: int = -1,
+               class_w: Optional[torch.Tensor] = None, hist: Optional[torch.Tensor] = None, old_cl: int = 0,
+               ukd: bool = True, gamma: float = 2.0, threshold: float = 0.5, focal_gamma: float = 2.0,
+               focal_alpha: Optional[float] = None, lkd_threshold: float = 0.5, ignore_index: int = 255,
+               grad_scale: float = 1.0, seen_scale: int = 16, want_score: bool = False) -> dict:
+    logits = _cuda(logits, "pixel_loss")
+    labels = _cuda(labels, "pixel_loss", torch.int64)
+    B, K, H, W = logits.shape
+    if tuple(labels.shape) != (B, H, W):
+        raise ValueError("pixel_loss: labels %s do not match logits %s" % (tuple(labels.shape), tuple(logits.shape)))
+    dev = logits.device
+    a = PixelArgs()
+    out = {}
+    a.logits, a.labels = logits.data_ptr(), labels.data_ptr()
+    out["dlogits"] = torch.empty_like(logits) if want_grad else None
+    out["preds"] = torch.empty((B, H, W), dtype=torch.int64, device=dev) if want_preds else None
+    out["acc"] = torch.empty(_cabi.NACC, dtype=torch.float64, device=dev)
+    out["distill_mask"] = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if want_distill_mask else None
+    out["gz"] = None
+    out["score"] = torch.empty(B, dtype=torch.float64, device=dev) if want_score else None
+    a.T = a.h = a.w = 0
+    if z is not None:
+        z = _cuda(z, "pixel_loss", torch.float32)
+        a.T, a.h, a.w = z.shape[1], z.shape[2], z.shape[3]
+        if focal_head >= 0:
+            out["gz"] = torch.zeros((B, a.h, a.w), dtype=torch.float32, device=dev)
+    if class_w is not None:
+        class_w = _cuda(class_w.float(), "pixel_loss")
+        if class_w.numel() != K:
+            raise ValueError("pixel_loss: class weights must have K=%d entries" % K)
+    need_hist = want_grad and mode in (_cabi.PIX_CE, _cabi.PIX_UNBIASED_CE)
+    if need_hist and hist is None:
+        hist = label_hist(labels)
+    a.dlogits, a.preds, a.z = _ptr(out["dlogits"]), _ptr(out["preds"]), _ptr(z)
+    a.distill_mask, a.gz, a.class_w = _ptr(out["distill_mask"]), _ptr(out["gz"]), _ptr(class_w)
+    a.hist, a.acc, a.score = _ptr(hist), out["acc"].data_ptr(), _ptr(out["score"])
+    a.B, a.K, a.H, a.W = B, K, H, W
+    a.dtype, a.mode = _dt(logits), mode
+    a.old_cl, a.ukd, a.focal_head = int(old_cl), int(bool(ukd)), int(focal_head)
+    a.ignore_index, a.seen_scale = int(ignore_index), int(seen_scale)
+    a.gamma, a.threshold, a.focal_gamma = float(gamma), float(threshold), float(focal_gamma)
+    a.focal_alpha = -1.0 if focal_alpha is None else float(focal_alpha)
+    a.lkd_threshold, a.grad_scale = float(lkd_threshold), float(grad_scale)
+    lib = _lib()
+    nbytes = lib.bacs_pixel_workspace_bytes(C.byref(a))
+    if nbytes == 0:
+        raise _cabi.BacsError("bacs_pixel_loss: no tile plan for K=%d" % K)
+    ws = _ws(nbytes, dev)
+    check(lib.bacs_pixel_loss(C.byref(a), ws.data_ptr(), ws.numel(), _stream()), "bacs_pixel_loss")
+    out["hist"] = hist
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# teacher distillation / DER
+# --------------------------------------------------------------------------------------
+def teacher_distill(old_att: torch.Tensor, new_att: torch.Tensor, mask: Optional[torch.Tensor], out_hw,
+                    grad_coef: float, want_grad: bool):
+    old_att = _cuda(old_att, "teacher_distill")
+    new_att = _cuda(new_att, "teacher_distill")
+    if old_att.dtype != new_att.dtype:
+        old_att = old_att.to(new_att.dtype)
+    if old_att.shape != new_att.shape:
+        raise ValueError("teacher_distill: attention shapes differ")
+    B, A, h, w = new_att.shape
+    H, W = out_hw
+    if mask is not None:
+        mask = _cuda(mask, "teacher_distill", torch.uint8)
+    dev = new_att.device
+    loss_sum = torch.empty(1, dtype=torch.float64, device=dev)
+    dnew = torch.empty_like(new_att) if want_grad else None
+    lib = _lib()
+    ws = _ws(lib.bacs_distill_workspace_bytes(B, A, h, w, H, W), dev)
+    check(lib.bacs_teacher_distill(old_att.data_ptr(), new_att.data_ptr(), _dt(new_att), B, A, h, w, _ptr(mask), H, W,
+                                   float(grad_coef), loss_sum.data_ptr(), _ptr(dnew), ws.data_ptr(), ws.numel(),
+                                   _stream()), "bacs_teacher_distill")
+    return loss_sum, dnew
+
+
+def der_transplant_cut(n_classes, K: int) -> np.ndarray:
+    """Host restatement of the transplant index quirk (loss/bacs_loss.py:415-425): for i, n
+    in enumerate(unique(n_classes)) the sample touched is inverse[i], not the samples whose
+    class count is n.  n_classes is a tiny host array (it comes from the buffer loader)."""
+    n_classes = np.asarray(n_classes).astype(np.int64).reshape(-1)
+    uniq, inv = np.unique(n_classes, return_inverse=True)
+    cut = np.full(n_classes.shape[0], K, dtype=np.int32)
+    for i, n in enumerate(uniq.tolist()):
+        j = int(inv[i])
+        if n < K:
+            cut[j] = min(int(cut[j]), int(n))
+    return cut
+
+
+def der_mse(sem_logits: torch.Tensor, memory_logits: torch.Tensor, cut: torch.Tensor, ignore_rep_bg: bool,
+            truncate: bool, grad_coef: float, want_grad: bool):
+    sem_logits = _cuda(sem_logits, "der_mse")
+    memory_logits = _cuda(memory_logits, "der_mse")
+    is_i64 = memory_logits.dtype == torch.int64
+    if not is_i64 and memory_logits.dtype != torch.float32:
+        memory_logits = memory_logits.float()
+    cut = _cuda(cut, "der_mse", torch.int32)
+    Br, K, h, w = sem_logits.shape
+    if memory_logits.shape != sem_logits.shape:
+        raise ValueError("der_mse: stored logits %s vs live %s (pad with change_data_size first)"
+                         % (tuple(memory_logits.shape), tuple(sem_logits.shape)))
+    dev = sem_logits.device
+    loss_sum = torch.empty(1, dtype=torch.float64, device=dev)
+    dsem = torch.empty_like(sem_logits) if want_grad else None
+    lib = _lib()
+    ws = _ws(lib.bacs_der_workspace_bytes(Br, K, h * w), dev)
+    check(lib.bacs_der_mse(sem_logits.data_ptr(), _dt(sem_logits), memory_logits.data_ptr(), int(is_i64),
+                           int(truncate), cut.data_ptr(), int(ignore_rep_bg), Br, K, h * w, float(grad_coef),
+                           loss_sum.data_ptr(), _ptr(dsem), ws.data_ptr(), ws.numel(), _stream()), "bacs_der_mse")
+    return loss_sum, dsem
+
+
+# --------------------------------------------------------------------------------------
+# confusion matrix
+# --------------------------------------------------------------------------------------
+def confmat_accumulate(preds: torch.Tensor, target: torch.Tensor, K: int, confmat: torch.Tensor,
+                       oob: Optional[torch.Tensor] = None) -> torch.Tensor:
+    target = _cuda(target, "confmat_accumulate", torch.int64)
+    if not preds.is_cuda:
+        raise RuntimeError("bacs_b200.confmat_accumulate: expected CUDA tensors (there is no CPU path)")
+    if preds.dtype == torch.int64:
+        is_float = 0
+    else:
+        preds = preds.float()
+        is_float = 1
+    preds = preds.contiguous()
+    if preds.numel() != target.numel():
+        raise ValueError("confmat_accumulate: preds and target sizes differ")
+    if confmat.dtype != torch.int64 or confmat.numel() != K * K or not confmat.is_contiguous():
+        raise ValueError("confmat_accumulate: confmat must be a contiguous int64 [K,K]")
+    check(_lib().bacs_confmat_accumulate(preds.data_ptr(), is_float, target.data_ptr(), target.numel(), K,
+                                         confmat.data_ptr(), _ptr(oob), _stream()), "bacs_confmat_accumulate")
+    return confmat
+
+
+def confmat_metrics(confmat: torch.Tensor) -> torch.Tensor:
+    confmat = _cuda(confmat, "confmat_metrics", torch.int64)
+    K = confmat.shape[0]
+    out = torch.empty((6, K), dtype=torch.float32, device=confmat.device)
+    check(_lib().bacs_confmat_metrics(confmat.data_ptr(), K, out.data_ptr(), _stream()), "bacs_confmat_metrics")
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# scalar helpers
+# --------------------------------------------------------------------------------------
+def scale_inplace(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """x *= g for a device scalar g (fp32 [1] or 0-d); returns immediately on the device when g == 1."""
+    if g.dtype != torch.float32:
+        g = g.float()
+    check(_lib().bacs_scale_inplace(x.data_ptr(), _dt(x), x.numel(), g.data_ptr(), _stream()), "bacs_scale_inplace")
+    return x
+
+
+def combine_scalars(terms: Sequence[tuple], device) -> torch.Tensor:
+    """terms: (src fp64 tensor, index, coef[, den fp64 tensor, den index]) -> fp32 [1]
+    = sum coef * src[idx] / den[didx]."""
+    n = len(terms)
+    src = (C.c_void_p * n)()
+    den = (C.c_void_p * n)()
+    idx = (C.c_int * n)()
+    didx = (C.c_int * n)()
+    coef = (C.c_float * n)()
+    for i, t in enumerate(terms):
+        src[i], idx[i], coef[i] = t[0].data_ptr(), int(t[1]), float(t[2])
+        if len(t) > 3 and t[3] is not None:
+            den[i], didx[i] = t[3].data_ptr(), int(t[4])
+        else:
+            den[i], didx[i] = None, 0
+    out = torch.empty(1, dtype=torch.float32, device=device)
+    check(_lib().bacs_combine_scalars(n, src, idx, den, didx, coef, out.data_ptr(), _stream()),
+          "bacs_combine_scalars")
+    return out
+
+
+def pack_state(sums: Optional[torch.Tensor], counts: Optional[torch.Tensor], confmat: Optional[torch.Tensor],
+               device) -> torch.Tensor:
+    T, D = (sums.shape if sums is not None else (0, 0))
+    K = confmat.shape[0] if confmat is not None else 0
+    packed = torch.empty(T * D + T + K * K, dtype=torch.float64, device=device)
+    check(_lib().bacs_pack_state(_ptr(sums), _ptr(counts), T, D, _ptr(confmat), K, packed.data_ptr(), _stream()),
+          "bacs_pack_state")
+    return packed
+
+
+def unpack_state(packed: torch.Tensor, sums: Optional[torch.Tensor], counts: Optional[torch.Tensor],
+                 confmat: Optional[torch.Tensor]) -> None:
+    T, D = (sums.shape if sums is not None else (0, 0))
+    K = confmat.shape[0] if confmat is not None else 0
+    check(_lib().bacs_unpack_state(packed.data_ptr(), T, D, _ptr(sums), _ptr(counts), _ptr(confmat), K, _stream()),
+          "bacs_unpack_state")

@@ -1,0 +1,423 @@
+"""GPU parity tests, op by op: every CUDA entry point (through the C ABI) against the CPU
+oracle on the same seeded inputs.  Integer work is bit-exact; floating point is within the
+1e-5 relative tolerance BASELINE.json's north_star states (gradients of 16-bit tensors are
+compared after the oracle's gradient is rounded to the same storage type)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bacs_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from bacs_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from bacs_b200 import synth as _synth
+    return _synth
+
+
+def dev(t):
+    return t.cuda() if isinstance(t, torch.Tensor) else t
+
+
+def close(got, want, rtol=RTOL, atol=None, what=""):
+    got = torch.as_tensor(got).detach().double().cpu()
+    want = torch.as_tensor(want).detach().double().cpu()
+    if atol is None:
+        atol = rtol * max(1e-30, float(want.abs().max()))
+    err = float((got - want).abs().max()) if got.numel() else 0.0
+    assert torch.allclose(got, want, rtol=rtol, atol=atol), "%s max abs err %.3e (atol %.3e)" % (what, err, atol)
+
+
+# --------------------------------------------------------------------------------------
+# labels
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 1000, 512 * 512 * 3 + 5])
+def test_label_hist(ops, n):
+    g = torch.Generator().manual_seed(n)
+    lab = torch.randint(0, 256, (n,), generator=g)
+    if n > 10:
+        lab[3] = -4
+        lab[5] = 300
+    hist = ops.label_hist(lab.cuda()).cpu()
+    inside = lab[(lab >= 0) & (lab < 256)]
+    assert torch.equal(hist[:256], torch.bincount(inside, minlength=256))
+    assert int(hist[256]) == int(((lab < 0) | (lab >= 256)).sum())
+
+
+def test_label_remap_sequential_aliasing(ops):
+    rng = np.random.RandomState(0)
+    for trial in range(12):
+        keys = rng.choice(35, size=14, replace=False) - 1          # raw ids incl. -1
+        d1 = {int(k): int(rng.randint(0, 20)) for k in keys}
+        d2 = {int(k): int(v) for k, v in zip(rng.choice(20, 7, replace=False), rng.randint(0, 9, 7))}
+        d2[255] = 255
+        n_img, H, W = 3, 37, 53
+        lbl = rng.randint(-1, 34, size=(n_img, H, W)).astype(np.int64)
+        if trial % 3 == 0:
+            lbl[0, :4] = 255
+        want = np.stack([O.transform_label(lbl[i], d1, 255, d2, 0) for i in range(n_img)])
+        lo, n_dom = -1, 257
+        m1 = np.full(n_dom, 255, dtype=np.int32)
+        for k, v in d1.items():
+            m1[k - lo] = v
+        m2 = np.full(n_dom, 0, dtype=np.int32)
+        for k, v in d2.items():
+            m2[k - lo] = v
+        got = ops.label_remap(torch.from_numpy(lbl).cuda(), torch.from_numpy(m1).cuda(), 255,
+                              torch.from_numpy(m2).cuda(), 0, lo=lo).cpu().numpy()
+        assert np.array_equal(got, want), trial
+        # single pass
+        want1 = np.stack([O.sequential_remap(lbl[i], d1, 255) for i in range(n_img)])
+        got1 = ops.label_remap(torch.from_numpy(lbl).cuda(), torch.from_numpy(m1).cuda(), 255, lo=lo).cpu().numpy()
+        assert np.array_equal(got1, want1), trial
+
+
+@pytest.mark.parametrize("shape", [(2, 512, 512, 32, 32), (3, 528, 528, 33, 33), (2, 513, 513, 33, 33),
+                                   (2, 64, 96, 4, 6), (1, 100, 75, 7, 5), (2, 512, 1024, 32, 64)])
+def test_label_downsample_task(ops, shape):
+    B, H, W, h, w = shape
+    g = torch.Generator().manual_seed(H + W)
+    lab = torch.randint(0, 22, (B, H, W), generator=g)
+    lab[torch.rand(B, H, W, generator=g) < 0.1] = 255
+    init, inc, T = 16, 1, 6
+    lut = torch.from_numpy(O.class_task_lut(init, inc)).int()
+    lut[lut >= T] = -1
+    task, rank, n_bt, down = ops.label_downsample_task(lab.cuda(), h, w, lut.cuda(), T, want_labels_down=True)
+    want_down = O.downsample_labels(lab, h, w)
+    assert torch.equal(down.cpu(), want_down)
+    want_task = lut[want_down].to(torch.int8)
+    assert torch.equal(task.cpu(), want_task)
+    tk, rk = want_task.view(B, -1), rank.cpu().view(B, -1)
+    for b in range(B):
+        for t in range(T):
+            sel = tk[b] == t
+            assert int(n_bt[b, t]) == int(sel.sum())
+            assert torch.equal(rk[b][sel].long(), torch.arange(int(sel.sum())))
+
+
+# --------------------------------------------------------------------------------------
+# prototypes
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,B,dtype", [("tiny", 1, torch.float32), ("tiny", 2, torch.float32),
+                                          ("small", 3, torch.float32), ("small", 3, torch.bfloat16)])
+def test_proto_accumulate_update(ops, synth, name, B, dtype):
+    cfg = synth.CONFIGS[name]
+    inp = synth.make_step_inputs(cfg, seed=3, dtype=dtype)
+    g = torch.Generator().manual_seed(5)
+    mask = synth.make_labels(cfg, g, classes=list(range(1, cfg.K)), B=B)
+    pen = inp.pen[:B]
+    lut = torch.from_numpy(O.class_task_lut(cfg.initial_classes, cfg.increment)).int()
+    lut[lut >= cfg.T] = -1
+    task, rank, n_bt, _ = ops.label_downsample_task(mask.cuda(), cfg.h, cfg.w, lut.cuda(), cfg.T)
+    for mode, mname in [(0, "exact"), (1, "channel")]:
+        sums, counts = ops.proto_accumulate(pen.cuda(), task, rank, n_bt, cfg.T, mode)
+        want_s, want_n = O.proto_accumulate(pen.float(), mask, cfg.initial_classes, cfg.increment, cfg.T, mode=mname)
+        assert torch.equal(counts.cpu().long(), want_n)
+        close(sums, want_s, atol=2e-5 * float(want_s.abs().max()), what="sums " + mname)
+    # running-mean update with float32 counts (Q3) and with int64 counts (task 0)
+    sums, counts = ops.proto_accumulate(pen.cuda(), task, rank, n_bt, cfg.T, 0)
+    want_s, want_n = O.proto_accumulate(pen.float(), mask, cfg.initial_classes, cfg.increment, cfg.T, mode="exact")
+    for cdtype in (torch.float32, torch.int64):
+        proto = inp.protos.clone()
+        cnt = torch.tensor([0, 1000, 3, 0, 7, 1][:cfg.T] + [5] * max(0, cfg.T - 6)).to(cdtype)
+        p_gpu, c_gpu = proto.cuda(), cnt.cuda()
+        ready = ops.proto_update(p_gpu, c_gpu, sums, counts)
+        wp, wc = O.proto_update(proto, cnt, sums.cpu().float(), want_n)
+        close(p_gpu, wp, what="proto")
+        assert torch.equal(c_gpu.cpu(), wc)
+        assert bool(ready.item()) == O.prototypes_ready(wc)
+
+
+def test_proto_no_foreground_is_noop(ops, synth):
+    cfg = synth.CONFIGS["tiny"]
+    inp = synth.make_step_inputs(cfg, seed=1)
+    mask = torch.zeros(cfg.B, cfg.H, cfg.W, dtype=torch.int64)
+    mask[:, :5] = 255
+    lut = torch.from_numpy(O.class_task_lut(cfg.initial_classes, cfg.increment)).int().cuda()
+    task, rank, n_bt, _ = ops.label_downsample_task(mask.cuda(), cfg.h, cfg.w, lut, cfg.T)
+    sums, counts = ops.proto_accumulate(inp.pen.cuda(), task, rank, n_bt, cfg.T, 0)
+    assert float(counts.abs().sum()) == 0 and float(sums.abs().sum()) == 0
+    proto, cnt = inp.protos.clone().cuda(), torch.zeros(cfg.T).cuda()
+    ready = ops.proto_update(proto, cnt, sums, counts)
+    assert torch.equal(proto.cpu(), inp.protos) and int(ready.item()) == 0
+
+
+# --------------------------------------------------------------------------------------
+# seen heads
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,dtype", [("tiny", torch.float32), ("small", torch.float32), ("small", torch.bfloat16)])
+def test_seen_logits_and_upsample(ops, synth, name, dtype):
+    cfg = synth.CONFIGS[name]
+    inp = synth.make_step_inputs(cfg, seed=1, dtype=dtype)
+    z = ops.seen_logits(inp.pen.cuda(), inp.protos.cuda(), inp.head_w.cuda(), inp.head_b.cuda())
+    want = O.seen_logits_lowres(inp.pen.float(), inp.protos, inp.head_w, inp.head_b)
+    close(z, want, what="z")
+    up = ops.seen_upsample(z, 16, apply_sigmoid=True)
+    close(up, O.seen_probs(inp.pen.float(), inp.protos, inp.head_w, inp.head_b), what="seen probs")
+
+
+def test_seen_head_backward(ops, synth):
+    cfg = synth.CONFIGS["tiny"]
+    inp = synth.make_step_inputs(cfg, seed=4)
+    t = 1
+    pen = inp.pen.clone().requires_grad_(True)
+    w = inp.head_w[t:t + 1].clone().requires_grad_(True)
+    b = inp.head_b[t:t + 1].clone().requires_grad_(True)
+    z = O.seen_logits_lowres(pen, inp.protos[t:t + 1], w, b)
+    gz = torch.randn(cfg.B, cfg.h, cfg.w, generator=torch.Generator().manual_seed(0))
+    (z[:, 0] * gz).sum().backward()
+    scale = torch.tensor([0.37])
+    dw, db, dpen = ops.seen_head_backward(inp.pen.cuda(), inp.protos[t].cuda(), inp.head_w[t].contiguous().cuda(),
+                                          gz.cuda(), scale.cuda(), True)
+    close(dw, 0.37 * w.grad[0], what="dweight")
+    close(db, 0.37 * b.grad, what="dbias")
+    close(dpen, 0.37 * pen.grad, what="dpen")
+
+
+# --------------------------------------------------------------------------------------
+# fused per-pixel kernel
+# --------------------------------------------------------------------------------------
+def _seen_z(inp):
+    return O.seen_logits_lowres(inp.pen.float(), inp.protos, inp.head_w, inp.head_b)
+
+
+@pytest.mark.parametrize("ukd", [True, False])
+@pytest.mark.parametrize("name,dtype", [("tiny", torch.float32), ("small", torch.float32), ("small", torch.bfloat16),
+                                        ("small", torch.float16)])
+def test_pixel_weighted_ce(ops, synth, name, dtype, ukd):
+    from bacs_b200 import _cabi
+    cfg = synth.CONFIGS[name]
+    inp = synth.make_step_inputs(cfg, seed=2, dtype=dtype)
+    g = torch.Generator().manual_seed(9)
+    mask = synth.make_labels(cfg, g, classes=list(range(1, cfg.K)))
+    z = _seen_z(inp)
+    smax = torch.sigmoid(O.bilinear_upsample(z, (cfg.H, cfg.W), True)).max(1)[0]
+    x = inp.logits.float().clone().requires_grad_(True)
+    want = O.weighted_ce(x, mask, smax, cfg.old_cl, 2.0, 0.5, ukd)
+    want.backward()
+    scale = 1024.0 if dtype == torch.float16 else 1.0      # fp16 gradients of a mean need a loss scale
+    out = ops.pixel_loss(inp.logits.cuda(), mask.cuda(), _cabi.PIX_WEIGHTED_CE, want_grad=True, z=z.cuda(),
+                         want_distill_mask=True, old_cl=cfg.old_cl, ukd=ukd, grad_scale=scale)
+    N = cfg.B * cfg.H * cfg.W
+    close(out["acc"][_cabi.ACC_LOSS] / N, want, what="loss")
+    assert torch.equal(out["preds"].cpu(), O.argmax_first(inp.logits.float()))
+    want_g = (x.grad * scale).to(dtype).float()
+    tol = RTOL if dtype == torch.float32 else 2.0 ** (-8 if dtype == torch.bfloat16 else -11)
+    close(out["dlogits"].float(), want_g, atol=tol * float(want_g.abs().max()), what="dlogits")
+    # teacher-distill pixel mask: exact away from the fp32 rounding band of the threshold
+    want_m = (mask == 0) & (smax > 0.5)
+    diff = out["distill_mask"].cpu().bool() != want_m
+    assert int((diff & ((smax - 0.5).abs() > 1e-6)).sum()) == 0
+    assert int(diff.sum()) <= 2
+    acc = out["acc"].cpu()
+    assert int(acc[_cabi.ACC_KEPT]) == int((mask != 255).sum())
+    assert int(acc[_cabi.ACC_BG]) == int((mask == 0).sum())
+    assert int(acc[_cabi.ACC_INVALID]) == 0
+
+
+def test_pixel_focal_term(ops, synth):
+    from bacs_b200 import _cabi
+    cfg = synth.CONFIGS["tiny"]
+    for alpha in (None, 0.25):
+        inp = synth.make_step_inputs(cfg, seed=8)
+        t = 1
+        z = _seen_z(inp).clone().requires_grad_(True)
+        zf = O.bilinear_upsample(z[:, t:t + 1], (cfg.H, cfg.W), True)
+        kept = int((inp.mask != 255).sum())
+        want = O.focal_seen_loss(zf, inp.mask, 2.0, alpha)
+        want.backward()
+        out = ops.pixel_loss(inp.logits.cuda(), inp.mask.cuda(), _cabi.PIX_WEIGHTED_CE, want_grad=False,
+                             z=z.detach().cuda(), focal_head=t, old_cl=cfg.old_cl, focal_alpha=alpha)
+        close(out["acc"][_cabi.ACC_FOCAL] / kept, want, what="focal loss")
+        close(out["gz"] / kept, z.grad[:, t], atol=2e-5 * float(z.grad.abs().max()), what="gz")
+        scale, focal = ops.focal_scale(out["acc"], None, 0.75)
+        close(focal, 0.75 * want, what="focal scaled")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pixel_ce_modes(ops, synth, dtype):
+    from bacs_b200 import _cabi
+    cfg = synth.CONFIGS["small"]
+    inp = synth.make_step_inputs(cfg, seed=4, dtype=dtype)
+    g = torch.Generator().manual_seed(2)
+    mask = synth.make_labels(cfg, g, classes=list(range(1, cfg.K)))
+    w = torch.zeros(cfg.K)
+    w[1:cfg.old_cl] = 1
+    tol = RTOL if dtype == torch.float32 else 2.0 ** -8
+    for weight in (None, w):
+        x = inp.logits.float().clone().requires_grad_(True)
+        want = O.cross_entropy(x, mask, weight)
+        want.backward()
+        out = ops.pixel_loss(inp.logits.cuda(), mask.cuda(), _cabi.PIX_CE, want_grad=True,
+                             class_w=None if weight is None else weight.cuda(), grad_scale=0.2)
+        acc = out["acc"]
+        close(acc[_cabi.ACC_LOSS] / acc[_cabi.ACC_WSUM], want, what="ce")
+        wg = (0.2 * x.grad).to(dtype).float()
+        close(out["dlogits"].float(), wg, atol=tol * float(wg.abs().max()), what="ce grad")
+        assert torch.equal(out["preds"].cpu(), O.argmax_first(inp.logits.float()))
+    # eval: no gradient, no histogram
+    out = ops.pixel_loss(inp.logits.cuda(), mask.cuda(), _cabi.PIX_CE, want_grad=False)
+    close(out["acc"][_cabi.ACC_LOSS] / out["acc"][_cabi.ACC_WSUM], O.cross_entropy(inp.logits.float(), mask))
+    # unbiased CE
+    x = inp.logits.float().clone().requires_grad_(True)
+    want = O.unbiased_ce(x, mask, cfg.old_cl)
+    want.backward()
+    out = ops.pixel_loss(inp.logits.cuda(), mask.cuda(), _cabi.PIX_UNBIASED_CE, want_grad=True, old_cl=cfg.old_cl)
+    close(out["acc"][_cabi.ACC_LOSS] / out["acc"][_cabi.ACC_WSUM], want, what="uce")
+    wg = x.grad.to(dtype).float()
+    close(out["dlogits"].float(), wg, atol=tol * float(wg.abs().max()), what="uce grad")
+    # per-image importance score
+    w2 = torch.ones(cfg.K)
+    w2[0] = 0
+    out = ops.pixel_loss(inp.logits.cuda(), mask.cuda(), _cabi.PIX_SCORE, want_grad=False, class_w=w2.cuda(),
+                         want_score=True, want_preds=False)
+    close(out["score"], O.cross_entropy_per_image_score(inp.logits.float(), mask, w2), what="score")
+
+
+@pytest.mark.parametrize("shape", [(1, 5, 33, 47), (2, 3, 16, 18), (1, 151, 32, 64), (1, 40, 31, 33)])
+def test_pixel_ragged_shapes(ops, shape):
+    """odd sizes / unaligned rows take the non-TMA loader and the 1-pixel-per-thread plan"""
+    from bacs_b200 import _cabi
+    B, K, H, W = shape
+    g = torch.Generator().manual_seed(K)
+    x = torch.randn(B, K, H, W, generator=g)
+    y = torch.randint(0, K, (B, H, W), generator=g)
+    y[torch.rand(B, H, W, generator=g) < 0.2] = 255
+    xr = x.clone().requires_grad_(True)
+    want = O.cross_entropy(xr, y)
+    want.backward()
+    out = ops.pixel_loss(x.cuda(), y.cuda(), _cabi.PIX_CE, want_grad=True)
+    close(out["acc"][_cabi.ACC_LOSS] / out["acc"][_cabi.ACC_WSUM], want)
+    close(out["dlogits"], xr.grad, what="grad")
+    assert torch.equal(out["preds"].cpu(), x.argmax(1))
+
+
+def test_pixel_all_ignored_and_invalid(ops):
+    from bacs_b200 import _cabi
+    x = torch.randn(1, 4, 16, 32)
+    y = torch.full((1, 16, 32), 255)
+    out = ops.pixel_loss(x.cuda(), y.cuda(), _cabi.PIX_CE, want_grad=True)
+    assert float(out["acc"][_cabi.ACC_WSUM]) == 0 and float(out["dlogits"].abs().max()) == 0
+    y[0, 0, :5] = 9            # outside [0,K) and not ignore: counted, treated as ignore
+    out = ops.pixel_loss(x.cuda(), y.cuda(), _cabi.PIX_CE, want_grad=False)
+    assert int(out["acc"][_cabi.ACC_INVALID]) == 5
+
+
+# --------------------------------------------------------------------------------------
+# teacher distill / DER
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,dtype,with_mask", [("tiny", torch.float32, True), ("tiny", torch.float32, False),
+                                                  ("small", torch.float32, True), ("small", torch.bfloat16, True)])
+def test_teacher_distill(ops, synth, name, dtype, with_mask):
+    cfg = synth.CONFIGS[name]
+    inp = synth.make_step_inputs(cfg, seed=6, dtype=dtype)
+    g = torch.Generator().manual_seed(1)
+    m = (inp.mask == 0) & (torch.rand(cfg.B, cfg.H, cfg.W, generator=g) > 0.4) if with_mask else None
+    new = inp.new_att.float().clone().requires_grad_(True)
+    lab = inp.mask if m is None else torch.where(m, torch.zeros_like(inp.mask), torch.ones_like(inp.mask))
+    if m is None:
+        lab = torch.zeros_like(inp.mask)
+    want = O.teacher_distill(inp.old_att.float(), new, lab, None, lkd=0.25)
+    want.backward()
+    coef = 0.25 / (cfg.B * cfg.A * cfg.H)
+    mask_u8 = None if m is None else m.to(torch.uint8).cuda()
+    s, dnew = ops.teacher_distill(inp.old_att.cuda(), inp.new_att.cuda(), mask_u8, (cfg.H, cfg.W), coef, True)
+    close(s * coef, want, what="distill loss")
+    tol = RTOL * 3 if dtype == torch.float32 else 2.0 ** -8
+    wg = new.grad.to(dtype).float()
+    close(dnew.float(), wg, atol=tol * float(wg.abs().max()), what="dnew")
+
+
+def test_teacher_distill_identical_maps_zero(ops, synth):
+    cfg = synth.CONFIGS["tiny"]
+    inp = synth.make_step_inputs(cfg, seed=6)
+    s, dnew = ops.teacher_distill(inp.new_att.cuda(), inp.new_att.cuda(), None, (cfg.H, cfg.W), 1.0, True)
+    assert float(s) == 0.0 and float(dnew.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("ncls", [[6, 6, 8, 7, 9], [9, 9, 9, 9, 9], [5, 6, 7, 8, 9], [8, 5, 5, 8, 6]])
+@pytest.mark.parametrize("ignore_bg", [True, False])
+def test_der_mse(ops, ncls, ignore_bg):
+    K, Br = 9, 5
+    g = torch.Generator().manual_seed(sum(ncls))
+    s = torch.randn(Br, K, 4, 6, generator=g)
+    m = torch.randn(Br, K, 4, 6, generator=g) * 2
+    sr = s.clone().requires_grad_(True)
+    want = O.der_mse(sr, m, np.array(ncls), ignore_rep_bg=ignore_bg)
+    want.backward()
+    cut = torch.from_numpy(ops.der_transplant_cut(ncls, K)).cuda()
+    assert np.array_equal(ops.der_transplant_cut(ncls, K), O.der_transplant_cut(np.array(ncls), K))
+    coef = 0.8 / s.numel()
+    for mem in (m.cuda(), m.long().cuda()):                      # float (truncated in-kernel) or int64 (Q4)
+        tot, ds = ops.der_mse(s.cuda(), mem, cut, ignore_bg, True, coef, True)
+        close(tot / s.numel(), want, what="der")
+        close(ds, 0.8 * sr.grad, atol=1e-6 * float(sr.grad.abs().max()), what="dsem")
+
+
+# --------------------------------------------------------------------------------------
+# confusion matrix
+# --------------------------------------------------------------------------------------
+def test_confmat_known_answer(ops):
+    # the reference's only known-answer vector: training/metrics.py:159-183
+    label = torch.zeros((1, 4, 4), dtype=torch.long)
+    pred = torch.zeros((1, 4, 4), dtype=torch.float32)
+    label[:, :3, :3] = 1
+    pred[:, -3:, -3:] = 1
+    cm = torch.zeros(2, 2, dtype=torch.int64).cuda()
+    ops.confmat_accumulate(pred.cuda(), label.cuda(), 2, cm)
+    assert cm.cpu().tolist() == [[2, 5], [5, 4]]
+    met = ops.confmat_metrics(cm).cpu()
+    assert torch.allclose(met[0], torch.tensor([2.0 / 12, 4.0 / 14]), atol=1e-6)
+
+
+@pytest.mark.parametrize("K,n", [(2, 100), (21, 512 * 512 * 2 + 3), (20, 1024 * 2048), (151, 300000), (256, 50000)])
+def test_confmat_matches_oracle(ops, K, n):
+    g = torch.Generator().manual_seed(K)
+    t = torch.randint(0, K, (n,), generator=g)
+    t[torch.rand(n, generator=g) < 0.1] = 255
+    p = torch.randint(0, K, (n,), generator=g)
+    # long runs like real segmentation maps
+    t = t.view(-1)[torch.arange(n) // 7 * 7 % n]
+    cm = torch.zeros(K, K, dtype=torch.int64).cuda()
+    ops.confmat_accumulate(p.cuda(), t.cuda(), K, cm)
+    ops.confmat_accumulate(p.cuda(), t.cuda(), K, cm)            # accumulates
+    want = O.confusion_matrix(p.numpy(), t.numpy(), K)
+    assert np.array_equal(cm.cpu().numpy(), 2 * want)
+    met = ops.confmat_metrics(cm).cpu().numpy()
+    wm = O.iou_metrics(2 * want)
+    for row, key in enumerate(["iou_per_class", "accuracy", "precision", "recall", "specificity"]):
+        assert np.allclose(met[row], wm[key], rtol=1e-6, atol=1e-7), key
+    assert np.allclose(met[5], wm["miou"], rtol=1e-6)
+
+
+def test_pack_unpack_and_scale(ops):
+    T, D, K = 3, 8, 4
+    sums = torch.randn(T, D, dtype=torch.float64).cuda()
+    counts = torch.tensor([3.0, 0.0, 7.0], dtype=torch.float64).cuda()
+    cm = torch.randint(0, 1 << 40, (K, K)).cuda()
+    packed = ops.pack_state(sums, counts, cm, sums.device)
+    assert packed.numel() == T * D + T + K * K
+    s2, c2, cm2 = torch.empty_like(sums), torch.empty_like(counts), torch.empty_like(cm)
+    ops.unpack_state(packed * 2, s2, c2, cm2)
+    assert torch.equal(s2, sums * 2) and torch.equal(c2, counts * 2) and torch.equal(cm2, cm * 2)
+    x = torch.randn(1000).cuda()
+    y = x.clone()
+    ops.scale_inplace(y, torch.tensor([1.0]).cuda())
+    assert torch.equal(x, y)
+    ops.scale_inplace(y, torch.tensor([0.5]).cuda())
+    assert torch.equal(y, x * 0.5)
+    a = torch.tensor([2.0, 8.0], dtype=torch.float64).cuda()
+    r = ops.combine_scalars([(a, 0, 3.0), (a, 1, 1.0, a, 0)], a.device)
+    assert math.isclose(float(r), 2 * 3 + 8 / 2)
