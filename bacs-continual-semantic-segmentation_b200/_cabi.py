@@ -21,7 +21,7 @@ vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 class PixelArgs(C.Structure):
     """struct bacs_pixel_args"""
     _fields_ = [
-        ("logits", vp), ("labels", vp), ("dlogits", vp), ("preds", vp), ("z", vp), ("distill_mask", vp),
+        ("logits", vp), ("labels", vp), ("dlogits", vp), ("preds", vp), ("z", vp), ("seen_max", vp), ("distill_mask", vp),
         ("gz", vp), ("class_w", vp), ("hist", vp), ("acc", vp), ("score", vp),
         ("B", i32), ("K", i32), ("H", i32), ("W", i32), ("T", i32), ("h", i32), ("w", i32),
         ("dtype", i32), ("mode", i32), ("old_cl", i32), ("ukd", i32), ("focal_head", i32),
@@ -35,6 +35,7 @@ _SIGNATURES = {
     "bacs_version": (i32, []),
     "bacs_last_error_string": (C.c_char_p, []),
     "bacs_device_sm_count": (i32, []),
+    "bacs_launch_count": (C.c_ulonglong, []),
     "bacs_label_hist": (i32, [vp, i64, vp, vp]),
     "bacs_label_remap_workspace_bytes": (sz, [i64]),
     "bacs_label_remap": (i32, [vp, vp, i64, i64, i32, i32, vp, i32, vp, i32, vp, vp]),
@@ -52,6 +53,7 @@ _SIGNATURES = {
     "bacs_teacher_distill": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, f32, vp, vp, vp, sz, vp]),
     "bacs_der_workspace_bytes": (sz, [i32, i32, i32]),
     "bacs_der_mse": (i32, [vp, i32, vp, i32, i32, vp, i32, i32, i32, i32, f32, vp, vp, vp, sz, vp]),
+    "bacs_der_cut": (i32, [vp, i32, i32, vp, vp]),
     "bacs_confmat_accumulate": (i32, [vp, i32, vp, i64, i32, vp, vp, vp]),
     "bacs_confmat_metrics": (i32, [vp, i32, vp, vp]),
     "bacs_scale_inplace": (i32, [vp, i32, i64, vp, vp]),

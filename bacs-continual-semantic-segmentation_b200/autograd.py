@@ -1,0 +1,123 @@
+"""torch.autograd.Function wrappers of the fused forward+backward kernels.
+
+Every Function computes its gradients in the forward launch (one read of the big tensors)
+and keeps them for backward.  backward() multiplies the stored gradients by the upstream
+gradient with a device-predicated in-place kernel that exits immediately when the upstream
+gradient is 1 (the usual case without a GradScaler), so the step never synchronises with
+the host and the [B,K,H,W] tensors are read once and written once.
+
+Losses come back as fp32 tensors of shape [] attached to autograd, like the reference's."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _cabi, ops
+
+
+def _scaled(grad: Optional[torch.Tensor], g: torch.Tensor) -> Optional[torch.Tensor]:
+    if grad is None:
+        return None
+    return ops.scale_inplace(grad, g.reshape(1))
+
+
+class PixelLossFunction(torch.autograd.Function):
+    """Fused per-pixel CE family (+ seen-detector focal term) + arg-max.
+
+    forward(logits, features, head_weight, head_bias, labels, cfg) ->
+        (loss [], preds int64 [B,H,W], distill_mask uint8 [B,H,W] or empty)
+    Gradients: logits; head_weight / head_bias of the focal head; features only when
+    cfg['features_grad'] (first task: stop_gradients is False, base_loss.py:265)."""
+
+    @staticmethod
+    def forward(ctx, logits, features, head_weight, head_bias, labels, cfg: dict):
+        mode = cfg["mode"]
+        z = cfg.get("z")
+        focal_head = cfg.get("focal_head", -1)
+        want_grad = bool(cfg.get("want_grad", True)) and ctx.needs_input_grad[0]
+        has_focal = z is not None and focal_head >= 0
+        out = ops.pixel_loss(
+            logits, labels, mode, want_grad=want_grad, want_preds=True, z=z,
+            want_distill_mask=bool(cfg.get("want_distill_mask", False)), focal_head=focal_head if has_focal else -1,
+            class_w=cfg.get("class_w"), hist=cfg.get("hist"), old_cl=cfg.get("old_cl", 0), ukd=cfg.get("ukd", True),
+            gamma=cfg.get("gamma", 2.0), threshold=cfg.get("threshold", 0.5),
+            focal_gamma=cfg.get("focal_gamma", 2.0), focal_alpha=cfg.get("focal_alpha"),
+            lkd_threshold=cfg.get("lkd_threshold", 0.5), ignore_index=cfg.get("ignore_index", 255),
+            grad_scale=cfg.get("loss_scale", 1.0), seen_scale=cfg.get("seen_scale", 16),
+            seen_max=cfg.get("seen_max"))
+        acc = out["acc"]
+        B, _, H, W = logits.shape
+        scale = cfg.get("loss_scale", 1.0)
+        if mode == _cabi.PIX_WEIGHTED_CE:
+            terms = [(acc, _cabi.ACC_LOSS, scale / float(B * H * W))]           # mean over ALL pixels (Q6)
+        else:
+            terms = [(acc, _cabi.ACC_LOSS, scale, acc, _cabi.ACC_WSUM)]
+        dweight = dbias = dfeat = None
+        if has_focal:
+            fscale, out2 = ops.focal_scale(acc, cfg.get("ready"), cfg.get("focal_weight", 1.0))
+            terms.append((out2, 1, 1.0))
+            if head_weight is not None and (ctx.needs_input_grad[2] or ctx.needs_input_grad[1]):
+                want_df = bool(cfg.get("features_grad", False)) and ctx.needs_input_grad[1]
+                proto_t = cfg["proto"][focal_head]
+                dweight, dbias, dfeat = ops.seen_head_backward(
+                    features, proto_t, head_weight.detach().reshape(-1).float().contiguous(), out["gz"], fscale, want_df)
+        loss = ops.combine_scalars(terms, logits.device).reshape(())
+        ctx.grads = (out["dlogits"], dfeat, dweight, dbias)
+        ctx.shapes = (None if head_weight is None else head_weight.shape, None if head_bias is None else head_bias.shape,
+                      None if head_weight is None else head_weight.dtype)
+        preds = out["preds"]
+        dmask = out["distill_mask"] if out["distill_mask"] is not None else torch.empty(0, dtype=torch.uint8,
+                                                                                        device=logits.device)
+        ctx.mark_non_differentiable(preds, dmask)
+        ctx.aux = {"acc": acc}
+        return loss, preds, dmask
+
+    @staticmethod
+    def backward(ctx, g, _gp, _gm):
+        dlogits, dfeat, dweight, dbias = ctx.grads
+        ctx.grads = None
+        wshape, bshape, wdtype = ctx.shapes
+        dlogits = _scaled(dlogits, g)
+        dfeat = _scaled(dfeat, g)
+        if dweight is not None:
+            dweight = _scaled(dweight, g).reshape(wshape).to(wdtype)
+            dbias = _scaled(dbias, g).reshape(bshape).to(wdtype)
+        return dlogits, dfeat, dweight, dbias, None, None
+
+
+class TeacherDistillFunction(torch.autograd.Function):
+    """lkd * mean_{b,a,y} || m * (U(old)^2 - U(new)^2) ||_2 over x (bacs_loss.py:258-294)."""
+
+    @staticmethod
+    def forward(ctx, new_att, old_att, mask_u8, out_hw, lkd: float):
+        B, A, h, w = new_att.shape
+        H, W = out_hw
+        coef = float(lkd) / float(B * A * H)
+        total, dnew = ops.teacher_distill(old_att.detach(), new_att.detach(), mask_u8, (H, W), coef,
+                                          ctx.needs_input_grad[0])
+        ctx.dnew = dnew
+        return ops.combine_scalars([(total, 0, coef)], new_att.device).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        dnew, ctx.dnew = ctx.dnew, None
+        return _scaled(dnew, g), None, None, None, None
+
+
+class DerMseFunction(torch.autograd.Function):
+    """alpha * MSE(transplanted memory logits, live low-res logits) (bacs_loss.py:387-431)."""
+
+    @staticmethod
+    def forward(ctx, sem_logits, memory_logits, cut, ignore_rep_bg: bool, truncate: bool, alpha: float):
+        n = sem_logits.numel()
+        coef = float(alpha) / float(n)
+        total, dsem = ops.der_mse(sem_logits.detach(), memory_logits, cut, ignore_rep_bg, truncate, coef,
+                                  ctx.needs_input_grad[0])
+        ctx.dsem = dsem
+        return ops.combine_scalars([(total, 0, coef)], sem_logits.device).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        dsem, ctx.dsem = ctx.dsem, None
+        return _scaled(dsem, g), None, None, None, None, None

@@ -22,8 +22,11 @@ void set_error(const char* fmt, ...);
     }                                \
   } while (0)
 
+extern unsigned long long g_launch_count;
+
 #define BACS_CHECK_LAUNCH(name)                                               \
   do {                                                                        \
+    ++bacs::g_launch_count;                                                   \
     cudaError_t e__ = cudaGetLastError();                                     \
     if (e__ != cudaSuccess) {                                                 \
       bacs::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \

@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(32 * kDistillWarps) distill_kernel(const T* __
           d_n[m] = rn1 - rn;
           a_n[m] = rn + 0.5f * d_n[m];
           c0[m] = (a_o - a_n[m]) * (a_o + a_n[m]);
-          c1[m] = 2.f * (a_o * d_o - a_n[m] * d_n[m]);
+          // a_o d_o - a_n d_n written so that identical maps give exactly 0 (no FMA residue)
+          c1[m] = 2.f * ((a_o - a_n[m]) * d_o + a_n[m] * (d_o - d_n[m]));
           c2[m] = (d_o - d_n[m]) * (d_o + d_n[m]);
           M0[m] = on ? mr[j] : 0.f;
           M1[m] = on ? mr[w + j] : 0.f;

@@ -8,6 +8,7 @@
 
 namespace bacs {
 
+unsigned long long g_launch_count = 0;
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -247,11 +248,12 @@ extern "C" {
 int bacs_version(void) { return BACS_VERSION; }
 const char* bacs_last_error_string(void) { return bacs::g_err; }
 int bacs_device_sm_count(void) { return bacs::sm_count(); }
+unsigned long long bacs_launch_count(void) { return bacs::g_launch_count; }
 
 int bacs_label_hist(const int64_t* labels, int64_t n, int64_t* hist, bacs_stream_t stream) {
-  BACS_REQUIRE(labels && hist && n >= 0, "bacs_label_hist: null pointer or negative size");
-  BACS_REQUIRE((reinterpret_cast<uintptr_t>(labels) & 15) == 0, "bacs_label_hist: labels must be 16-byte aligned");
   if (n == 0) return BACS_OK;
+  BACS_REQUIRE(labels && hist && n > 0, "bacs_label_hist: null pointer or negative size");
+  BACS_REQUIRE((reinterpret_cast<uintptr_t>(labels) & 15) == 0, "bacs_label_hist: labels must be 16-byte aligned");
   const int64_t nchunk = (n + 7) >> 3;
   int64_t blocks = (nchunk + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 8;

@@ -42,6 +42,40 @@ __global__ void __launch_bounds__(1024) sum_partials2_kernel(const double* __res
   if (threadIdx.x == 0) out[0] = s;
 }
 
+// Transplant cut per replay sample with the reference's index quirk (bacs_loss.py:415-425):
+//   u, inv = unique(n_classes, return_inverse=True); for i, n in enumerate(u): j = inv[i];
+//   if n < K: memory[j, n:] = live[j, n:]      -- j is ONE sample index (Q5), not a mask.
+// Single block; values are class counts in [0, 1024).
+__global__ void __launch_bounds__(256) der_cut_kernel(const int64_t* __restrict__ n_classes, int Br, int K,
+                                                      int32_t* __restrict__ cut) {
+  __shared__ int present[1024];
+  __shared__ int rank_of[1024];
+  __shared__ int uniq[1024];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) present[i] = 0;
+  __syncthreads();
+  for (int j = threadIdx.x; j < Br; j += blockDim.x) {
+    const int64_t n = n_classes[j];
+    present[n < 0 ? 0 : (n > 1023 ? 1023 : (int)n)] = 1;
+    cut[j] = K;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int r = 0;
+    for (int v = 0; v < 1024; ++v)
+      if (present[v]) {
+        rank_of[v] = r;
+        uniq[r] = v;
+        ++r;
+      }
+    // sequential like the reference's Python loop (later writes win, all are mins of the same slot)
+    for (int i = 0; i < r && i < Br; ++i) {
+      const int64_t nj = n_classes[i];
+      const int j = rank_of[nj < 0 ? 0 : (nj > 1023 ? 1023 : (int)nj)];  // inv[i]
+      if (uniq[i] < K && j < Br) cut[j] = min(cut[j], uniq[i]);
+    }
+  }
+}
+
 static int der_blocks(int64_t total) {
   int64_t b = (total + 256 * 4 - 1) / (256 * 4);
   const int64_t cap = (int64_t)sm_count() * 4;
@@ -246,6 +280,13 @@ int bacs_der_mse(const void* sem_logits, int dtype, const void* memory_logits, i
   BACS_CHECK_LAUNCH("bacs_der_mse");
   sum_partials2_kernel<<<1, 1024, 0, s>>>(partials, blocks, loss_sum);
   BACS_CHECK_LAUNCH("bacs_der_mse(reduce)");
+  return BACS_OK;
+}
+
+int bacs_der_cut(const int64_t* n_classes, int Br, int K, int32_t* cut, bacs_stream_t stream) {
+  BACS_REQUIRE(n_classes && cut && Br > 0 && K > 0, "bacs_der_cut: bad arguments");
+  der_cut_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(n_classes, Br, K, cut);
+  BACS_CHECK_LAUNCH("bacs_der_cut");
   return BACS_OK;
 }
 

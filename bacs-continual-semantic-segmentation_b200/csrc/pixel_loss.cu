@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(256) pixel_loss_kernel(const PixelParams p) {
     if (valid) acc[BACS_ACC_VALID] += 1.f;
     if (valid && y[j] == 0) acc[BACS_ACC_BG] += 1.f;
     float seen = 0.f;
-    if (a.z) seen = sigmoid_acc(zmax[j]);
+    if (a.seen_max) seen = __ldg(a.seen_max + (int64_t)b * HW + p0 + px0 + j);
+    else if (a.z) seen = sigmoid_acc(zmax[j]);
 
     if (a.mode == BACS_PIX_WEIGHTED_CE) {
       if (valid) {
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(256) pixel_loss_kernel(const PixelParams p) {
 
     // teacher-distill pixel mask: background label and confidently "seen"
     if (a.distill_mask) {
-      const bool m = valid && y[j] == 0 && (a.z == nullptr || seen > a.lkd_threshold);
+      const bool m = valid && y[j] == 0 && ((a.z == nullptr && a.seen_max == nullptr) || seen > a.lkd_threshold);
       dmask[j] = m ? 1 : 0;
       if (m) acc[BACS_ACC_DISTILL_PIX] += 1.f;
     }
@@ -591,7 +592,8 @@ int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_
   }
   if (a->gz) BACS_REQUIRE(a->z && a->focal_head >= 0 && a->focal_head < a->T, "bacs_pixel_loss: focal head out of range");
   if (a->mode == BACS_PIX_WEIGHTED_CE)
-    BACS_REQUIRE(a->old_cl >= 1 && a->z, "bacs_pixel_loss: WEIGHTED_CE needs old_cl >= 1 and the seen logits");
+    BACS_REQUIRE(a->old_cl >= 1 && (a->z || a->seen_max),
+                 "bacs_pixel_loss: WEIGHTED_CE needs old_cl >= 1 and the seen logits / probabilities");
   if (a->mode != BACS_PIX_WEIGHTED_CE && a->dlogits)
     BACS_REQUIRE(a->hist, "bacs_pixel_loss: CE-type gradients need the label histogram");
   if (a->mode == BACS_PIX_SCORE) BACS_REQUIRE(a->score && !a->dlogits, "bacs_pixel_loss: SCORE mode needs score and no gradient");

@@ -125,12 +125,15 @@ __global__ void __launch_bounds__(256) seen_head_backward_kernel(const T* __rest
 
 // scale = weight * ready * [#bg > 0] / #kept ; focal = scale * sum(focal terms)
 __global__ void focal_scale_kernel(const double* __restrict__ acc, const int32_t* __restrict__ ready, float weight,
-                                   float* __restrict__ scale_out, float* __restrict__ focal_out) {
+                                   float* __restrict__ scale_out, double* __restrict__ out2) {
   const double kept = acc[BACS_ACC_KEPT];
   const bool on = (ready == nullptr || *ready != 0) && acc[BACS_ACC_BG] > 0.0 && kept > 0.0;
   const double s = on ? (double)weight / kept : 0.0;
   if (scale_out) *scale_out = (float)s;
-  if (focal_out) *focal_out = (float)(s * acc[BACS_ACC_FOCAL]);
+  if (out2) {
+    out2[0] = s;
+    out2[1] = s * acc[BACS_ACC_FOCAL];
+  }
 }
 
 }  // namespace bacs
@@ -199,10 +202,10 @@ int bacs_seen_head_backward(const void* features, int dtype, int B, int D, int h
   return BACS_OK;
 }
 
-int bacs_focal_scale(const double* acc, const int32_t* ready, float weight, float* scale_out, float* focal_out,
+int bacs_focal_scale(const double* acc, const int32_t* ready, float weight, float* scale_out, double* out2,
                      bacs_stream_t stream) {
   BACS_REQUIRE(acc, "bacs_focal_scale: null pointer");
-  focal_scale_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(acc, ready, weight, scale_out, focal_out);
+  focal_scale_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(acc, ready, weight, scale_out, out2);
   BACS_CHECK_LAUNCH("bacs_focal_scale");
   return BACS_OK;
 }

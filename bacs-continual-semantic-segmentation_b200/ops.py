@@ -172,11 +172,13 @@ def seen_head_backward(features: torch.Tensor, proto_t: torch.Tensor, weight_t: 
 
 
 def focal_scale(acc: torch.Tensor, ready: Optional[torch.Tensor], weight: float):
+    """-> (scale fp32 [1], out2 fp64 [2] = {scale, scale * focal sum})"""
     dev = acc.device
-    out = torch.empty(2, dtype=torch.float32, device=dev)
-    check(_lib().bacs_focal_scale(acc.data_ptr(), _ptr(ready), float(weight), out.data_ptr(),
-                                  out.data_ptr() + 4, _stream()), "bacs_focal_scale")
-    return out[0:1], out[1:2]
+    scale = torch.empty(1, dtype=torch.float32, device=dev)
+    out2 = torch.empty(2, dtype=torch.float64, device=dev)
+    check(_lib().bacs_focal_scale(acc.data_ptr(), _ptr(ready), float(weight), scale.data_ptr(), out2.data_ptr(),
+                                  _stream()), "bacs_focal_scale")
+    return scale, out2
 
 
 # --------------------------------------------------------------------------------------
@@ -187,7 +189,8 @@ def pixel_loss(logits: torch.Tensor, labels: torch.Tensor, mode: int, *, want_gr
                class_w: Optional[torch.Tensor] = None, hist: Optional[torch.Tensor] = None, old_cl: int = 0,
                ukd: bool = True, gamma: float = 2.0, threshold: float = 0.5, focal_gamma: float = 2.0,
                focal_alpha: Optional[float] = None, lkd_threshold: float = 0.5, ignore_index: int = 255,
-               grad_scale: float = 1.0, seen_scale: int = 16, want_score: bool = False) -> dict:
+               grad_scale: float = 1.0, seen_scale: int = 16, want_score: bool = False,
+               seen_max: Optional[torch.Tensor] = None) -> dict:
     logits = _cuda(logits, "pixel_loss")
     labels = _cuda(labels, "pixel_loss", torch.int64)
     B, K, H, W = logits.shape
@@ -209,6 +212,11 @@ def pixel_loss(logits: torch.Tensor, labels: torch.Tensor, mode: int, *, want_gr
         a.T, a.h, a.w = z.shape[1], z.shape[2], z.shape[3]
         if focal_head >= 0:
             out["gz"] = torch.zeros((B, a.h, a.w), dtype=torch.float32, device=dev)
+    if seen_max is not None:
+        seen_max = _cuda(seen_max.float(), "pixel_loss")
+        if tuple(seen_max.shape) != (B, H, W):
+            raise ValueError("pixel_loss: seen_max must be [B,H,W]")
+    a.seen_max = _ptr(seen_max)
     if class_w is not None:
         class_w = _cuda(class_w.float(), "pixel_loss")
         if class_w.numel() != K:
@@ -273,6 +281,16 @@ def der_transplant_cut(n_classes, K: int) -> np.ndarray:
         j = int(inv[i])
         if n < K:
             cut[j] = min(int(cut[j]), int(n))
+    return cut
+
+
+def der_cut(n_classes: torch.Tensor, K: int) -> torch.Tensor:
+    """Device version of der_transplant_cut (no host synchronisation)."""
+    if not n_classes.is_cuda:
+        raise RuntimeError("bacs_b200.der_cut: expected a CUDA tensor (there is no CPU path)")
+    n = n_classes.reshape(-1).long().contiguous()
+    cut = torch.empty(n.numel(), dtype=torch.int32, device=n.device)
+    check(_lib().bacs_der_cut(n.data_ptr(), n.numel(), int(K), cut.data_ptr(), _stream()), "bacs_der_cut")
     return cut
 
 

@@ -134,3 +134,127 @@ def make_step_inputs(cfg: StepConfig, seed: int = 0, dtype=torch.float32, device
                                        dtype=torch.int64).to(torch.uint8).to(device),
         }
     return StepInputs(cfg, logits, pen, old_att, new_att, mask, protos, counts, head_w, head_b, replay)
+
+
+# --------------------------------------------------------------------------------------
+# A stand-in network that satisfies the contract the loss relies on by
+# returning fixed tensors, so that only the loss path runs (the DeepLabV3 forward /
+# backward is out of scope for this path).
+# --------------------------------------------------------------------------------------
+class HeadHolder(torch.nn.Module):
+    """Parameter layout of the reference's classification_head: conv.weight [1,D,1,1], conv.bias [1]."""
+
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor):
+        super().__init__()
+        D = weight.numel()
+        self.conv = torch.nn.Conv2d(D, 1, 1)
+        with torch.no_grad():
+            self.conv.weight.copy_(weight.reshape(1, D, 1, 1))
+            self.conv.bias.copy_(bias.reshape(1))
+        self.stop_gradients = False
+
+
+class SeenHeads(torch.nn.Module):
+    def __init__(self, head_w: torch.Tensor, head_b: torch.Tensor):
+        super().__init__()
+        self.inter_channels = head_w.shape[1]
+        self.seen_not_seen_clf = torch.nn.ModuleList([HeadHolder(head_w[t], head_b[t]) for t in range(head_w.shape[0])])
+        self.stop_gradients = False
+
+    def set_stop_gradients(self, stop):
+        self.stop_gradients = stop
+        for h in self.seen_not_seen_clf:
+            h.stop_gradients = stop
+
+
+class FixedOutputNetwork(torch.nn.Module):
+    """model(img, return_penultimate=True, return_attentions=True) -> (logits, pen, [att]);
+    model(img, return_sem_logits=True) -> low-res logits; keyed by the image tensor's id."""
+
+    def __init__(self, seen_fg_network=None):
+        super().__init__()
+        self.seen_fg_network = seen_fg_network
+        self._full, self._sem = {}, {}
+
+    def register(self, img, logits, pen, atts):
+        self._full[id(img)] = (logits, pen, atts)
+
+    def register_sem(self, img, sem):
+        self._sem[id(img)] = sem
+
+    def forward(self, x, return_attentions=False, return_penultimate=False, return_sem_logits=False,
+                only_attentions=False):
+        if return_sem_logits:
+            return self._sem[id(x)]
+        logits, pen, atts = self._full[id(x)]
+        if return_penultimate and return_attentions:
+            return logits, pen, atts
+        if return_penultimate:
+            return logits, pen
+        if return_attentions:
+            return logits, atts
+        return logits
+
+    def get_penultimate_layer_dim(self):
+        return self.seen_fg_network.inter_channels
+
+
+class _Accelerator:
+    def __init__(self, device):
+        self.root_device = torch.device(device)
+
+
+def build_bacs_step(cfg: StepConfig, inp: StepInputs, device="cuda", first_task: bool = False, epoch: int = 3,
+                    max_epochs: int = 30, exact_prototypes: bool = True, **loss_kwargs):
+    """Wires a BACSLoss + FixedOutputNetwork for one training step of the given config.
+    Returns (loss_fn, network, batch, leaves) where ``leaves`` are the tensors that receive
+    gradients (logits, new_att, replay logits, replay sem logits, focal head params)."""
+    from .loss import BACSLoss
+
+    dev = torch.device(device)
+    task_num = cfg.T - 1
+    loss_fn = BACSLoss(name="bacs", bg_weighted_ce=True, **loss_kwargs)
+    loss_fn.init_prototype_compute()
+    loss_fn._prototypes.exact = exact_prototypes
+    loss_fn.set_continual_task_size(cfg.initial_classes, cfg.increment)
+    loss_fn._update_task(task_num)
+    loss_fn.old_classes, loss_fn.nb_current_classes = cfg.old_cl, cfg.K
+    loss_fn.first_task = first_task
+    loss_fn._use_der_loss = True
+    loss_fn.set_device(dev)
+    loss_fn.accelerator = _Accelerator(dev)
+    loss_fn.on_train_batch_start(epoch=epoch, max_epochs=max_epochs, batch_idx=0)
+    P = loss_fn._prototypes
+    P._prototypes_tensors = inp.protos.clone().to(dev)
+    P._count_features = inp.counts.clone().to(dev)
+    P.refresh_ready()
+    heads = SeenHeads(inp.head_w, inp.head_b).to(dev)
+    net, prev = FixedOutputNetwork(heads), FixedOutputNetwork(heads)
+
+    def leaf(t):
+        return t.clone().to(dev).requires_grad_(True)
+
+    logits, pen, new_att = leaf(inp.logits), leaf(inp.pen), leaf(inp.new_att)
+    img = torch.zeros(cfg.B, 3, 2, 2, device=dev)
+    net.register(img, logits, pen, [new_att])
+    prev.register(img, inp.logits.to(dev), inp.pen.to(dev), [inp.old_att.to(dev)])
+    loss_fn.prev_model = prev
+    leaves = {"logits": logits, "pen": pen, "new_att": new_att, "head_w": heads.seen_not_seen_clf[task_num].conv.weight,
+              "head_b": heads.seen_not_seen_clf[task_num].conv.bias}
+    mask = inp.mask.clone().to(dev)
+    if inp.replay is not None:
+        rp = inp.replay
+        rimg, limg = torch.zeros(cfg.Br, 3, 2, 2, device=dev), torch.zeros(cfg.Br, 3, 2, 2, device=dev)
+        rlogits, rsem = leaf(rp["logits"]), leaf(rp["sem_logits"])
+        net.register(rimg, rlogits, rp["pen"].to(dev), [new_att])
+        net.register_sem(limg, rsem)
+        batch = {"main": [img, mask], "buffer": [rimg, rp["mask"].clone().to(dev)],
+                 "bufferlogits": [limg, rp["memory_logits"].float().clone().to(dev), rp["n_classes"].to(dev)]}
+        batch = loss_fn.preprocess_batch(batch)
+        # preprocess_batch makes new image tensors (.float()); keep the registered ones
+        batch["main"][0], batch["buffer"][0], batch["bufferlogits"][0] = img, rimg, limg
+        leaves.update(replay_logits=rlogits, replay_sem=rsem)
+    else:
+        loss_fn.alpha = loss_fn.beta = 0.0
+        batch = [img, mask]
+    return loss_fn, net, batch, leaves

@@ -42,6 +42,8 @@ int bacs_version(void);
 const char* bacs_last_error_string(void);
 /* number of SMs of the current device (grid sizing by the host side) */
 int bacs_device_sm_count(void);
+/* kernels launched by this library in this process so far (bench.py's gpu_launches) */
+unsigned long long bacs_launch_count(void);
 
 /* ---------------------------------------------------------------------------------
  * Labels
@@ -134,10 +136,11 @@ int bacs_seen_head_backward(const void* features, int dtype, int B, int D, int h
 
 /* Device-side normaliser of the focal term (base_loss.py:221-222,242-250,260-262):
  *   scale = weight * [ready] * [#background pixels > 0] / #kept pixels, read from the
- *   accumulators of bacs_pixel_loss (acc) and bacs_proto_update (ready, may be NULL);
- *   focal_out = scale * acc[BACS_ACC_FOCAL].  Outputs float[1], either may be NULL. */
+ *   accumulators of bacs_pixel_loss (acc) and bacs_proto_update (ready, may be NULL).
+ *   scale_out float[1] (for bacs_seen_head_backward); out2 double[2] = {scale,
+ *   scale * acc[BACS_ACC_FOCAL]} (for bacs_combine_scalars).  Either may be NULL. */
 int bacs_focal_scale(const double* acc, const int32_t* ready, float weight, float* scale_out,
-                     float* focal_out, bacs_stream_t stream);
+                     double* out2, bacs_stream_t stream);
 
 /* ---------------------------------------------------------------------------------
  * The fused per-pixel kernel: softmax statistics read ONCE per pixel, then
@@ -176,6 +179,10 @@ typedef struct bacs_pixel_args {
   void* dlogits;          /* [B,K,H,W] same dtype as logits, or NULL (no gradient) */
   int64_t* preds;         /* [B,H,W] arg-max (ties -> lowest channel), or NULL */
   const float* z;         /* [B,T,h,w] low-res seen logits, or NULL */
+  const float* seen_max;  /* [B,H,W] max_t seen probability already at full resolution, or NULL;
+                             when given it replaces sigmoid(max_t upsample(z)) in the CE
+                             modulation and the distill mask (stand-alone WeightedCrossEntropy
+                             API, training/loss_utils.py:586-588) */
   uint8_t* distill_mask;  /* [B,H,W] out: (label==0) & (max_t seen > lkd_threshold), or NULL */
   float* gz;              /* [B,h,w] out: d(focal sum)/dz of head focal_head, atomically
                              accumulated (caller zeroes), or NULL = no focal term */
@@ -229,6 +236,9 @@ int bacs_der_mse(const void* sem_logits, int dtype, const void* memory_logits, i
                  float grad_coef, double* loss_sum, void* dsem, void* workspace,
                  size_t workspace_bytes, bacs_stream_t stream);
 size_t bacs_der_workspace_bytes(int Br, int K, int hw);
+/* cut[j] from the stored class counts n_classes int64[Br] (values < 1024), on the device,
+ * reproducing `for i, n in enumerate(unique(n_classes)): j = inverse[i]` (Q5). */
+int bacs_der_cut(const int64_t* n_classes, int Br, int K, int32_t* cut, bacs_stream_t stream);
 
 /* ---------------------------------------------------------------------------------
  * Confusion matrix (training/metrics.py:38-88 over torchmetrics 0.6.0 ConfusionMatrix)

@@ -214,7 +214,7 @@ def test_pixel_weighted_ce(ops, synth, name, dtype, ukd):
     close(out["acc"][_cabi.ACC_LOSS] / N, want, what="loss")
     assert torch.equal(out["preds"].cpu(), O.argmax_first(inp.logits.float()))
     want_g = (x.grad * scale).to(dtype).float()
-    tol = RTOL if dtype == torch.float32 else 2.0 ** (-8 if dtype == torch.bfloat16 else -11)
+    tol = RTOL if dtype == torch.float32 else 2.0 ** (-7 if dtype == torch.bfloat16 else -10)   # 1 ulp of the storage type
     close(out["dlogits"].float(), want_g, atol=tol * float(want_g.abs().max()), what="dlogits")
     # teacher-distill pixel mask: exact away from the fp32 rounding band of the threshold
     want_m = (mask == 0) & (smax > 0.5)
@@ -242,8 +242,9 @@ def test_pixel_focal_term(ops, synth):
                              z=z.detach().cuda(), focal_head=t, old_cl=cfg.old_cl, focal_alpha=alpha)
         close(out["acc"][_cabi.ACC_FOCAL] / kept, want, what="focal loss")
         close(out["gz"] / kept, z.grad[:, t], atol=2e-5 * float(z.grad.abs().max()), what="gz")
-        scale, focal = ops.focal_scale(out["acc"], None, 0.75)
-        close(focal, 0.75 * want, what="focal scaled")
+        scale, out2 = ops.focal_scale(out["acc"], None, 0.75)
+        close(out2[1], 0.75 * want, what="focal scaled")
+        close(scale, 0.75 / kept, what="focal scale")
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -255,7 +256,7 @@ def test_pixel_ce_modes(ops, synth, dtype):
     mask = synth.make_labels(cfg, g, classes=list(range(1, cfg.K)))
     w = torch.zeros(cfg.K)
     w[1:cfg.old_cl] = 1
-    tol = RTOL if dtype == torch.float32 else 2.0 ** -8
+    tol = RTOL if dtype == torch.float32 else 2.0 ** -7            # 1 bf16 ulp
     for weight in (None, w):
         x = inp.logits.float().clone().requires_grad_(True)
         want = O.cross_entropy(x, mask, weight)
@@ -335,7 +336,7 @@ def test_teacher_distill(ops, synth, name, dtype, with_mask):
     mask_u8 = None if m is None else m.to(torch.uint8).cuda()
     s, dnew = ops.teacher_distill(inp.old_att.cuda(), inp.new_att.cuda(), mask_u8, (cfg.H, cfg.W), coef, True)
     close(s * coef, want, what="distill loss")
-    tol = RTOL * 3 if dtype == torch.float32 else 2.0 ** -8
+    tol = RTOL * 3 if dtype == torch.float32 else 2.0 ** -7
     wg = new.grad.to(dtype).float()
     close(dnew.float(), wg, atol=tol * float(wg.abs().max()), what="dnew")
 
@@ -359,6 +360,8 @@ def test_der_mse(ops, ncls, ignore_bg):
     want.backward()
     cut = torch.from_numpy(ops.der_transplant_cut(ncls, K)).cuda()
     assert np.array_equal(ops.der_transplant_cut(ncls, K), O.der_transplant_cut(np.array(ncls), K))
+    assert np.array_equal(ops.der_cut(torch.tensor(ncls, dtype=torch.uint8).cuda(), K).cpu().numpy(),
+                          O.der_transplant_cut(np.array(ncls), K))
     coef = 0.8 / s.numel()
     for mem in (m.cuda(), m.long().cuda()):                      # float (truncated in-kernel) or int64 (Q4)
         tot, ds = ops.der_mse(s.cuda(), mem, cut, ignore_bg, True, coef, True)
