@@ -84,23 +84,101 @@ constexpr int kDistillWarps = 8;
 constexpr int kChanPerWarp = 2;
 constexpr int kChanPerCta = kDistillWarps * kChanPerWarp;
 
+// Value of a quantity that is linear in the row weight ty:  v(ty) = p + q * ty.
+struct Lin {
+  float p, q;
+  __device__ __forceinline__ float at(float ty) const { return fmaf(q, ty, p); }
+};
+__device__ __forceinline__ Lin lin(float v0, float v1) { return Lin{v0, v1 - v0}; }  // v0 at ty=0, v1 at ty=1
+
+__device__ __forceinline__ void dist_mbar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)));
+}
+__device__ __forceinline__ void dist_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  const uint32_t b32 = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b32), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(dst)),
+               "l"(src), "r"(bytes), "r"(b32)
+               : "memory");
+}
+__device__ __forceinline__ void dist_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "DWAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DWAIT_DONE;\n"
+      "bra DWAIT_LOOP;\n"
+      "DWAIT_DONE:\n"
+      "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// One warp owns kChanPerWarp channels of one image; lane j owns low-res column(s) j (+32m).
+// The CTA walks the source-row intervals top to bottom; the five mask moments of every
+// row of the interval are staged in shared memory once and reused by all its channels.
+//
+// Per (channel, row, cell), with a = value at the cell centre and d = r[j+1]-r[j] of the
+// y-interpolated row (both linear in ty):
+//   alpha = a_o - a_n, sigma = a_o + a_n, delta = d_o - d_n, eps = d_o + d_n
+//   c0 = alpha*sigma, c1 = 2(alpha*d_o + a_n*delta), c2 = delta*eps     (exactly 0 for old == new)
+//   u = G c (G = Hankel matrix of the moments), S_cell = c.u, dS/dc = 2u
+//   dL/da_n = -2 rs (u0 a_n + u1 d_n) ... accumulated against {1, ty} so that the corner
+//   gradients are assembled once per interval instead of once per row.
 template <typename T, int CPL>
-__global__ void __launch_bounds__(32 * kDistillWarps) distill_kernel(const T* __restrict__ old_att,
+__global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T* __restrict__ old_att,
                                                                       const T* __restrict__ new_att, int A, int h,
                                                                       int w, int H, DistillTables tb,
                                                                       const float* __restrict__ moments, int rows_max,
                                                                       float grad_coef, T* __restrict__ dnew,
                                                                       double* __restrict__ partials) {
-  extern __shared__ float s_mom[];  // [rows_max][5][w]
-  __shared__ double red_scratch[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int b = blockIdx.y;
+  const int b = blockIdx.y, b_img = blockIdx.y;
   const int ch0 = blockIdx.x * kChanPerCta + wid * kChanPerWarp;
   const bool want_grad = dnew != nullptr;
+  // dynamic smem: 2 x [rows_max][5][WP] moment buffers (columns zero-padded to WP) | ty[H]
+  extern __shared__ __align__(16) float s_dyn[];
+  __shared__ double red_scratch[32];
+  __shared__ uint64_t mom_bar[2];
+  constexpr int WP = 32 * CPL;
+  const size_t mom_stride = (size_t)rows_max * 5 * WP;
+  float* s_ty = s_dyn + 2 * mom_stride;
+  const bool bulk_ok = (w == WP);  // contiguous rows -> one TMA bulk copy per interval
+  for (int k = threadIdx.x; k < H; k += blockDim.x) s_ty[k] = tb.ywt[k];
+  if (threadIdx.x == 0) {
+    dist_mbar_init(&mom_bar[0]);
+    dist_mbar_init(&mom_bar[1]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto stage_moments = [&](int i, int buf) {
+    // moments of the rows of interval i -> buffer buf
+    const int Y0 = tb.rowstart[i], nr = tb.rowstart[i + 1] - Y0;
+    const float* src = moments + ((int64_t)b_img * H + Y0) * 5 * w;
+    float* dst = s_dyn + buf * mom_stride;
+    if (bulk_ok) {
+      if (threadIdx.x == 0) dist_bulk_load(dst, src, (uint32_t)(nr * 5 * w * sizeof(float)), &mom_bar[buf]);
+    } else {
+      const int n = nr * 5 * WP;
+      for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const int rk = k / WP, j = k - rk * WP;
+        dst[k] = j < w ? __ldg(src + rk * w + j) : 0.f;
+      }
+    }
+  };
+  constexpr int NC = kChanPerWarp;
 
-  // per-lane cells: j = lane + 32*m
-  float o_prev[kChanPerWarp][CPL], o_prev1[kChanPerWarp][CPL], n_prev[kChanPerWarp][CPL], n_prev1[kChanPerWarp][CPL];
-  float carry[kChanPerWarp][CPL];
+  // corner values of the current interval's upper source row (columns j and j+1)
+  float o_prev[NC][CPL], o_prev1[NC][CPL], n_prev[NC][CPL], n_prev1[NC][CPL];
+  float carry[NC][CPL];  // gradient already collected for the upper row by the interval above
   float loss_acc = 0.f;
 
   auto load_row = [&](const T* base, int ch, int row, float* v, float* v1) {
@@ -116,99 +194,146 @@ __global__ void __launch_bounds__(32 * kDistillWarps) distill_kernel(const T* __
     }
   };
 #pragma unroll
-  for (int c = 0; c < kChanPerWarp; ++c) {
+  for (int c = 0; c < NC; ++c) {
     load_row(old_att, ch0 + c, 0, o_prev[c], o_prev1[c]);
     load_row(new_att, ch0 + c, 0, n_prev[c], n_prev1[c]);
 #pragma unroll
     for (int m = 0; m < CPL; ++m) carry[c][m] = 0.f;
   }
 
+  stage_moments(0, 0);
+  // corner rows of the NEXT interval are fetched one interval ahead (latency hidden by the row loop)
+  float o_nxt[NC][CPL], o_nxt1[NC][CPL], n_nxt[NC][CPL], n_nxt1[NC][CPL];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    load_row(old_att, ch0 + c, min(1, h - 1), o_nxt[c], o_nxt1[c]);
+    load_row(new_att, ch0 + c, min(1, h - 1), n_nxt[c], n_nxt1[c]);
+  }
   for (int i = 0; i < h; ++i) {
     const int Y0 = tb.rowstart[i], Y1 = tb.rowstart[i + 1];
     const int nrows = Y1 - Y0;
     const int row1 = min(i + 1, h - 1);
-    // stage the moments of this interval's rows (shared by every channel of the CTA)
+    const int buf = i & 1;
+    const float* s_mom = s_dyn + buf * mom_stride;
+    // every warp is done with buffer buf^1 (interval i-1): refill it with interval i+1
     __syncthreads();
-    {
-      const float* src = moments + ((int64_t)b * H + Y0) * 5 * w;
-      const int n = nrows * 5 * w;
-      for (int k = threadIdx.x; k < n; k += blockDim.x) s_mom[k] = __ldg(src + k);
-    }
-    __syncthreads();
+    if (i + 1 < h) stage_moments(i + 1, buf ^ 1);
+    if (bulk_ok) dist_mbar_wait(&mom_bar[buf], (uint32_t)((i >> 1) & 1));
+    else if (i == 0) __syncthreads();
+
+    float o_cur[NC][CPL], o_cur1[NC][CPL], n_cur[NC][CPL], n_cur1[NC][CPL];
+    Lin alpha[NC][CPL], sigma[NC][CPL], delta[NC][CPL], eps[NC][CPL], an[NC][CPL], dn[NC][CPL], dold[NC][CPL];
+    float GA0[NC][CPL], GA1[NC][CPL], GD0[NC][CPL], GD1[NC][CPL];
 #pragma unroll
-    for (int c = 0; c < kChanPerWarp; ++c) {
-      const int ch = ch0 + c;
-      float o_cur[CPL], o_cur1[CPL], n_cur[CPL], n_cur1[CPL];
+    for (int c = 0; c < NC; ++c) {
       if (row1 != i) {
-        load_row(old_att, ch, row1, o_cur, o_cur1);
-        load_row(new_att, ch, row1, n_cur, n_cur1);
+#pragma unroll
+        for (int m = 0; m < CPL; ++m) {
+          o_cur[c][m] = o_nxt[c][m]; o_cur1[c][m] = o_nxt1[c][m];
+          n_cur[c][m] = n_nxt[c][m]; n_cur1[c][m] = n_nxt1[c][m];
+        }
+        if (i + 2 < h) {
+          load_row(old_att, ch0 + c, i + 2, o_nxt[c], o_nxt1[c]);
+          load_row(new_att, ch0 + c, i + 2, n_nxt[c], n_nxt1[c]);
+        }
       } else {
 #pragma unroll
         for (int m = 0; m < CPL; ++m) {
-          o_cur[m] = o_prev[c][m]; o_cur1[m] = o_prev1[c][m];
-          n_cur[m] = n_prev[c][m]; n_cur1[m] = n_prev1[c][m];
+          o_cur[c][m] = o_prev[c][m]; o_cur1[c][m] = o_prev1[c][m];
+          n_cur[c][m] = n_prev[c][m]; n_cur1[c][m] = n_prev1[c][m];
         }
       }
-      // gradient accumulators w.r.t. new[row i][j], new[row1][j] and the same at column j+1
-      float g0[CPL], g1[CPL], g0n[CPL], g1n[CPL];
 #pragma unroll
-      for (int m = 0; m < CPL; ++m) g0[m] = g1[m] = g0n[m] = g1n[m] = 0.f;
+      for (int m = 0; m < CPL; ++m) {
+        // values at ty = 0 (upper source row) and ty = 1 (lower source row)
+        const float ao0 = 0.5f * (o_prev[c][m] + o_prev1[c][m]), ao1 = 0.5f * (o_cur[c][m] + o_cur1[c][m]);
+        const float an0 = 0.5f * (n_prev[c][m] + n_prev1[c][m]), an1 = 0.5f * (n_cur[c][m] + n_cur1[c][m]);
+        const float do0 = o_prev1[c][m] - o_prev[c][m], do1 = o_cur1[c][m] - o_cur[c][m];
+        const float dn0 = n_prev1[c][m] - n_prev[c][m], dn1 = n_cur1[c][m] - n_cur[c][m];
+        alpha[c][m] = lin(ao0 - an0, ao1 - an1);
+        sigma[c][m] = lin(ao0 + an0, ao1 + an1);
+        delta[c][m] = lin(do0 - dn0, do1 - dn1);
+        eps[c][m] = lin(do0 + dn0, do1 + dn1);
+        an[c][m] = lin(an0, an1);
+        dn[c][m] = lin(dn0, dn1);
+        dold[c][m] = lin(do0, do1);
+        GA0[c][m] = GA1[c][m] = GD0[c][m] = GD1[c][m] = 0.f;
+      }
+    }
 
-      for (int r = 0; r < nrows; ++r) {
-        const float ty = tb.ywt[Y0 + r];
-        const float sy0 = 1.f - ty;
-        const float* mr = s_mom + r * 5 * w;
-        float a_n[CPL], d_n[CPL], c0[CPL], c1[CPL], c2[CPL];
-        float M0[CPL], M1[CPL], M2[CPL], M3[CPL], M4[CPL];
-        float S = 0.f;
+#pragma unroll 2
+    for (int r = 0; r < nrows; ++r) {
+      const float ty = s_ty[Y0 + r];
+      const float* mr = s_mom + r * 5 * WP + lane;
+      float M0[CPL], M1[CPL], M2[CPL], M3[CPL], M4[CPL];
+#pragma unroll
+      for (int m = 0; m < CPL; ++m) {
+        M0[m] = mr[32 * m];
+        M1[m] = mr[WP + 32 * m];
+        M2[m] = mr[2 * WP + 32 * m];
+        M3[m] = mr[3 * WP + 32 * m];
+        M4[m] = mr[4 * WP + 32 * m];
+      }
+      float u0[NC][CPL], u1[NC][CPL], u2[NC][CPL], va[NC][CPL], vd[NC][CPL], S[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
 #pragma unroll
         for (int m = 0; m < CPL; ++m) {
-          const int j = lane + 32 * m;
-          const bool on = j < w;
-          const float ro = sy0 * o_prev[c][m] + ty * o_cur[m];
-          const float ro1 = sy0 * o_prev1[c][m] + ty * o_cur1[m];
-          const float rn = sy0 * n_prev[c][m] + ty * n_cur[m];
-          const float rn1 = sy0 * n_prev1[c][m] + ty * n_cur1[m];
-          const float d_o = ro1 - ro;
-          const float a_o = ro + 0.5f * d_o;
-          d_n[m] = rn1 - rn;
-          a_n[m] = rn + 0.5f * d_n[m];
-          c0[m] = (a_o - a_n[m]) * (a_o + a_n[m]);
-          // a_o d_o - a_n d_n written so that identical maps give exactly 0 (no FMA residue)
-          c1[m] = 2.f * ((a_o - a_n[m]) * d_o + a_n[m] * (d_o - d_n[m]));
-          c2[m] = (d_o - d_n[m]) * (d_o + d_n[m]);
-          M0[m] = on ? mr[j] : 0.f;
-          M1[m] = on ? mr[w + j] : 0.f;
-          M2[m] = on ? mr[2 * w + j] : 0.f;
-          M3[m] = on ? mr[3 * w + j] : 0.f;
-          M4[m] = on ? mr[4 * w + j] : 0.f;
-          S += c0[m] * c0[m] * M0[m] + 2.f * c0[m] * c1[m] * M1[m] + (c1[m] * c1[m] + 2.f * c0[m] * c2[m]) * M2[m] +
-               2.f * c1[m] * c2[m] * M3[m] + c2[m] * c2[m] * M4[m];
-        }
-        S = warp_sum(S);
-        if (!(S > 0.f)) continue;  // zero (or rounding-negative) row: norm 0, sub-gradient 0
-        const float nrm = sqrtf(S);
-        loss_acc += nrm;
-        if (!want_grad) continue;
-        const float gS = 0.5f / nrm;
-#pragma unroll
-        for (int m = 0; m < CPL; ++m) {
-          const float dS0 = 2.f * (c0[m] * M0[m] + c1[m] * M1[m] + c2[m] * M2[m]);
-          const float dS1 = 2.f * (c0[m] * M1[m] + c1[m] * M2[m] + c2[m] * M3[m]);
-          const float dS2 = 2.f * (c0[m] * M2[m] + c1[m] * M3[m] + c2[m] * M4[m]);
-          const float gA = gS * (-2.f * a_n[m] * dS0 - 2.f * d_n[m] * dS1);
-          const float gD = gS * (-2.f * a_n[m] * dS1 - 2.f * d_n[m] * dS2);
-          const float gj = 0.5f * gA - gD;   // d/d rn[j]
-          const float gj1 = 0.5f * gA + gD;  // d/d rn[j+1]
-          g0[m] += sy0 * gj;
-          g1[m] += ty * gj;
-          g0n[m] += sy0 * gj1;
-          g1n[m] += ty * gj1;
+          const float al = alpha[c][m].at(ty), sg = sigma[c][m].at(ty), de = delta[c][m].at(ty);
+          const float ep = eps[c][m].at(ty), d_o = dold[c][m].at(ty);
+          va[c][m] = an[c][m].at(ty);
+          vd[c][m] = dn[c][m].at(ty);
+          const float c0 = al * sg;
+          const float c1 = 2.f * fmaf(al, d_o, va[c][m] * de);
+          const float c2 = de * ep;
+          u0[c][m] = fmaf(c2, M2[m], fmaf(c1, M1[m], c0 * M0[m]));
+          u1[c][m] = fmaf(c2, M3[m], fmaf(c1, M2[m], c0 * M1[m]));
+          u2[c][m] = fmaf(c2, M4[m], fmaf(c1, M3[m], c0 * M2[m]));
+          const float sc = fmaf(c2, u2[c][m], fmaf(c1, u1[c][m], c0 * u0[c][m]));
+          S[c] = m == 0 ? sc : S[c] + sc;
         }
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) S[c] += __shfl_xor_sync(0xffffffffu, S[c], o);
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        // zero (or rounding-negative) row: norm 0 and sub-gradient 0, as torch's norm backward
+        const float rs = S[c] > 0.f ? rsqrt_fast(S[c]) : 0.f;
+        loss_acc = fmaf(S[c], rs, loss_acc);
+        if (want_grad) {
+#pragma unroll
+          for (int m = 0; m < CPL; ++m) {
+            // dL/dc = rs * u ;  d/da_n = -2 (g0 a_n + g1 d_n) ; d/dd_n = -2 (g1 a_n + g2 d_n)
+            const float gA = rs * fmaf(u1[c][m], vd[c][m], u0[c][m] * va[c][m]);
+            const float gD = rs * fmaf(u2[c][m], vd[c][m], u1[c][m] * va[c][m]);
+            GA0[c][m] += gA;
+            GA1[c][m] = fmaf(gA, ty, GA1[c][m]);
+            GD0[c][m] += gD;
+            GD1[c][m] = fmaf(gD, ty, GD1[c][m]);
+          }
+        }
+      }
+    }
 
-      if (want_grad) {
-        // move the column-(j+1) contributions to their owner (last column owns its own)
+    if (want_grad) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int ch = ch0 + c;
+        // a_n(ty) = an0 + (an1-an0) ty, d_n likewise; an0 = (n0[j]+n0[j+1])/2, dn0 = n0[j+1]-n0[j]
+        // (index 0 = upper source row, 1 = lower).  The factor -2 of gA / gD is applied here.
+        float g0[CPL], g1[CPL], g0n[CPL], g1n[CPL];
+#pragma unroll
+        for (int m = 0; m < CPL; ++m) {
+          const float dA0 = -2.f * (GA0[c][m] - GA1[c][m]), dA1 = -2.f * GA1[c][m];  // d/d an0, d/d an1
+          const float dD0 = -2.f * (GD0[c][m] - GD1[c][m]), dD1 = -2.f * GD1[c][m];
+          g0[m] = 0.5f * dA0 - dD0;   // upper row, column j
+          g0n[m] = 0.5f * dA0 + dD0;  // upper row, column j+1
+          g1[m] = 0.5f * dA1 - dD1;   // lower row, column j
+          g1n[m] = 0.5f * dA1 + dD1;  // lower row, column j+1
+        }
 #pragma unroll
         for (int m = 0; m < CPL; ++m) {
           const int j = lane + 32 * m;
@@ -223,12 +348,11 @@ __global__ void __launch_bounds__(32 * kDistillWarps) distill_kernel(const T* __
             g0[m] += up0;
             g1[m] += up1;
           }
-          if (j == w - 1) {
+          if (j == w - 1) {  // the last column is its own right neighbour
             g0[m] += g0n[m];
             g1[m] += g1n[m];
           }
         }
-        // row i is complete: carry from the interval above + this interval's share
 #pragma unroll
         for (int m = 0; m < CPL; ++m) {
           const int j = lane + 32 * m;
@@ -238,15 +362,18 @@ __global__ void __launch_bounds__(32 * kDistillWarps) distill_kernel(const T* __
           carry[c][m] = g1[m];
         }
       }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
 #pragma unroll
       for (int m = 0; m < CPL; ++m) {
-        o_prev[c][m] = o_cur[m]; o_prev1[c][m] = o_cur1[m];
-        n_prev[c][m] = n_cur[m]; n_prev1[c][m] = n_cur1[m];
+        o_prev[c][m] = o_cur[c][m]; o_prev1[c][m] = o_cur1[c][m];
+        n_prev[c][m] = n_cur[c][m]; n_prev1[c][m] = n_cur1[c][m];
       }
     }
   }
-  // every lane holds the same loss_acc (warp_sum broadcasts); count it once per warp
-  const double mine = (lane == 0 && ch0 < A) ? (double)loss_acc : 0.0;
+  // every lane holds the same loss_acc (the shuffle reduction broadcasts); count it once per warp
+  const double mine = (lane == 0) ? (double)loss_acc : 0.0;
   const double tot = block_sum(mine, red_scratch);
   if (threadIdx.x == 0) partials[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
 }
@@ -331,7 +458,8 @@ int bacs_teacher_distill(const void* old_att, const void* new_att, int dtype, in
 
   // an interval holds the rows whose source row is i: at most ceil(H/h) + ceil(H/(2h)) + 2
   const int rows_max = (H + h - 1) / h + (H + 2 * h - 1) / (2 * h) + 2;
-  const size_t smem = sizeof(float) * (size_t)rows_max * 5 * w;
+  const int wp = w <= 32 ? 32 : (w <= 64 ? 64 : 128);
+  const size_t smem = sizeof(float) * ((size_t)2 * rows_max * 5 * wp + H);
   if (smem > 200 * 1024) {
     set_error("bacs_teacher_distill: up-sampling ratio too large for the shared-memory moment tile");
     return BACS_ERR_UNSUPPORTED;

@@ -1,0 +1,458 @@
+// Register-resident fast path of the fused per-pixel kernel (K <= 24, even image sizes,
+// 16-byte aligned rows).  Included by one translation unit per storage type.
+//
+// Persistent CTAs of 8 warps; every thread owns 2 adjacent pixels of a 512-pixel tile.
+// Thread 0 drives a 3-stage TMA ring (1-D bulk copies, mbarrier completion): while tile k
+// is computed, tile k+1 has landed or is landing, and the stage of tile k-1 is being
+// written back by a bulk store and then refilled with tile k+2.  The K logits of both
+// pixels live in registers from the first shared-memory read to the gradient write, so
+// each logit costs one exp and the tile is read from shared memory exactly once.
+#pragma once
+#include "pixel_common.cuh"
+
+namespace bacs {
+
+constexpr int kFastThreads = 256;
+constexpr int kFastP = 512;
+
+template <typename T> struct Pair;  // two adjacent pixels of one channel row in shared memory
+template <> struct Pair<float> {
+  __device__ static __forceinline__ void ld(const float* p, float& a, float& b) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    a = t.x; b = t.y;
+  }
+  __device__ static __forceinline__ void st(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+  __device__ static __forceinline__ void fill(float* p, float v) { *p = v; }
+};
+template <> struct Pair<__nv_bfloat16> {
+  __device__ static __forceinline__ void ld(const __nv_bfloat16* p, float& a, float& b) {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+    a = __uint_as_float(u << 16);
+    b = __uint_as_float(u & 0xffff0000u);
+  }
+  __device__ static __forceinline__ void st(__nv_bfloat16* p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+  }
+  __device__ static __forceinline__ void fill(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+template <> struct Pair<__half> {
+  __device__ static __forceinline__ void ld(const __half* p, float& a, float& b) {
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(p));
+    a = t.x; b = t.y;
+  }
+  __device__ static __forceinline__ void st(__half* p, float a, float b) {
+    *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b);
+  }
+  __device__ static __forceinline__ void fill(__half* p, float v) { *p = __float2half_rn(v); }
+};
+
+__device__ __forceinline__ void fast_sync() { __syncthreads(); }
+
+// Shared memory (dynamic): [3][KREG*512] tiles (rows K..KREG-1 hold -inf forever) | zr[T][w] | gacc[w+1]
+template <typename T, int KREG, bool ROWTILE>
+__global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const PixelParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t bar_full[3];
+  __shared__ uint64_t bar_done[3];
+  __shared__ float red_scratch[8][BACS_NACC];
+  __shared__ float s_norm_sh;
+
+  constexpr int P = kFastP, S = 3;
+  const bacs_pixel_args& a = p.a;
+  const int K = a.K;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, wid = tid >> 5;
+  const int64_t HW = (int64_t)a.H * a.W;
+  constexpr size_t tile_elems = (size_t)KREG * P;
+  T* tiles = reinterpret_cast<T*>(smem_raw);
+  float* zr = reinterpret_cast<float*>(smem_raw + S * tile_elems * sizeof(T));
+  float* gacc = zr + (ROWTILE ? a.T * a.w : 0);
+  const int grid = (int)gridDim.x;
+  const int my_tiles = (p.n_tiles - (int)blockIdx.x + grid - 1) / grid;
+  const int tpi = p.tiles_per_image;
+  const uint32_t row_bytes = (uint32_t)(P * sizeof(T));
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_done[s], kFastThreads);
+    }
+    fence_mbar_init();
+    s_norm_sh = 0.f;
+  }
+  // padding rows stay -inf: exp -> 0, never the arg-max, never stored
+  for (int i = tid; i < S * (KREG - K) * P; i += kFastThreads) {
+    const int s = i / ((KREG - K) * P), r = i - s * (KREG - K) * P;
+    Pair<T>::fill(tiles + (size_t)s * tile_elems + (size_t)K * P + r, -INFINITY);
+  }
+  __syncthreads();
+  if (tid < 32 && a.mode != BACS_PIX_WEIGHTED_CE && a.dlogits != nullptr) {
+    double s = 0.0;
+    for (int c = tid; c < K && c < 256; c += 32)
+      if (c != a.ignore_index)
+        s += (double)a.hist[c] * ((a.mode == BACS_PIX_CE && a.class_w) ? (double)a.class_w[c] : 1.0);
+    s = warp_sum(s);
+    if (tid == 0) s_norm_sh = s > 0.0 ? (float)(1.0 / s) : 0.f;
+  }
+  __syncthreads();
+
+  // tile geometry is advanced incrementally (no integer divisions in the loop)
+  const int step_b = grid / tpi, step_t = grid - step_b * tpi;
+  int tb = (int)blockIdx.x / tpi, tt = (int)blockIdx.x - tb * tpi;  // tile k of this CTA: image tb, tile tt
+  auto issue_load = [&](int b, int t, int s) {
+    // thread 0 only; all tiles are full on this path
+    const T* src = reinterpret_cast<const T*>(a.logits) + (int64_t)b * K * HW + (int64_t)t * P;
+    T* dst = tiles + (size_t)s * tile_elems;
+    mbar_expect_tx(&bar_full[s], (uint32_t)K * row_bytes);
+    for (int c = 0; c < K; ++c) bulk_g2s(dst + (size_t)c * P, src + (int64_t)c * HW, row_bytes, &bar_full[s]);
+  };
+  // thread 0 keeps its own cursor for the tile to prefetch (k + 2)
+  int pb = tb, pt = tt;
+  auto advance = [&](int& b, int& t) {
+    b += step_b;
+    t += step_t;
+    if (t >= tpi) {
+      t -= tpi;
+      ++b;
+    }
+  };
+  if (tid == 0) {
+    for (int k = 0; k < 2 && k < my_tiles; ++k) {
+      issue_load(pb, pt, k);
+      advance(pb, pt);
+    }
+  }
+
+  const int px0 = tid * 2;
+  const int old_cl = min(max(a.old_cl, 0), K);
+  const bool have_seen = (a.z != nullptr) || (a.seen_max != nullptr);
+  const float s_norm = s_norm_sh;
+  float acc[BACS_NACC];
+#pragma unroll
+  for (int i = 0; i < BACS_NACC; ++i) acc[i] = 0.f;
+
+  // per-thread constants of the row-tile seen-map staging
+  const int tiles_per_row = ROWTILE ? a.W / P : 1;
+  const int zt0 = ROWTILE ? tid / max(a.w, 1) : 0, zj0 = ROWTILE ? tid - zt0 * a.w : 0;
+  const int zstep = ROWTILE ? kFastThreads / max(a.w, 1) : 1;  // host guarantees kFastThreads % w == 0
+
+  auto label_ptr = [&](int b, int t) { return a.labels + (int64_t)b * HW + (int64_t)t * P + px0; };
+  longlong2 lab_next = make_longlong2(a.ignore_index, a.ignore_index);
+  if (my_tiles > 0) lab_next = __ldg(reinterpret_cast<const longlong2*>(label_ptr(tb, tt)));
+
+  for (int k = 0; k < my_tiles; ++k) {
+    const int b = tb, t_in = tt;
+    advance(tb, tt);
+    const int s = k % S;
+    const uint32_t parity = (uint32_t)((k / S) & 1);
+    T* tile = tiles + (size_t)s * tile_elems;
+    const int64_t p0 = (int64_t)t_in * P;
+    const longlong2 lab = lab_next;
+    if (k + 1 < my_tiles) lab_next = __ldg(reinterpret_cast<const longlong2*>(label_ptr(tb, tt)));
+
+    // ---- per-pixel side inputs --------------------------------------------------------
+    int y[2];
+    bool is_ign[2];
+    float seen[2], zfoc[2], wx1[2];
+    int cx0[2], cdx[2];
+    int cell[2], cell_dy[2];
+    float wy1g[2];
+    Lerp ly_row = {0, 0, 0.f};
+    int Yrow = 0, Xbase = 0;
+    if (ROWTILE) {
+      Yrow = t_in / tiles_per_row;  // tiles_per_row is 1 for the 512-wide crops
+      Xbase = (t_in - Yrow * tiles_per_row) * P;
+      ly_row = lerp_align_corners(Yrow, a.h, p.sy);
+      fast_sync();  // previous tile's readers of zr / gacc are done
+      const float* zb = a.z + (int64_t)b * a.T * a.h * a.w;
+      const float wy0 = 1.f - ly_row.w1;
+      for (int t = zt0; t < a.T; t += zstep) {
+        const float* zt = zb + (int64_t)t * a.h * a.w;
+        zr[t * a.w + zj0] = __fadd_rn(__fmul_rn(wy0, __ldg(zt + ly_row.i0 * a.w + zj0)),
+                                      __fmul_rn(ly_row.w1, __ldg(zt + ly_row.i1 * a.w + zj0)));
+      }
+      if (a.gz && tid <= a.w) gacc[tid] = 0.f;
+      fast_sync();
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int64_t l = j == 0 ? lab.x : lab.y;
+      y[j] = -1;
+      is_ign[j] = true;
+      seen[j] = zfoc[j] = wx1[j] = wy1g[j] = 0.f;
+      cx0[j] = cell[j] = -1;
+      cdx[j] = cell_dy[j] = 0;
+      if (l == a.ignore_index) {
+      } else if (l >= 0 && l < K) {
+        y[j] = (int)l;
+        is_ign[j] = false;
+      } else {
+        acc[BACS_ACC_INVALID] += 1.f;
+      }
+      if (a.seen_max) seen[j] = __ldg(a.seen_max + (int64_t)b * HW + p0 + px0 + j);
+      if (a.z) {
+        float zmax = -INFINITY;
+        if (ROWTILE) {
+          const Lerp lx = lerp_align_corners(Xbase + px0 + j, a.w, p.sx);
+          const float wx0 = 1.f - lx.w1;
+          const float* z0 = zr + lx.i0;
+          const int dx = lx.i1 - lx.i0;
+          for (int t = 0; t < a.T; ++t) {
+            const float v = __fadd_rn(__fmul_rn(wx0, z0[t * a.w]), __fmul_rn(lx.w1, z0[t * a.w + dx]));
+            zmax = fmaxf(zmax, v);
+            if (t == a.focal_head) zfoc[j] = v;
+          }
+          cx0[j] = lx.i0;
+          cdx[j] = dx;
+          wx1[j] = lx.w1;
+        } else {
+          const int64_t pix = p0 + px0 + j;
+          const int Y = (int)(pix / a.W), X = (int)(pix - (int64_t)Y * a.W);
+          const Lerp ly = lerp_align_corners(Y, a.h, p.sy), lx = lerp_align_corners(X, a.w, p.sx);
+          const float wx0 = 1.f - lx.w1, wy0 = 1.f - ly.w1;
+          const float* zb = a.z + (int64_t)b * a.T * a.h * a.w;
+          const int o00 = ly.i0 * a.w + lx.i0, o01 = ly.i0 * a.w + lx.i1;
+          const int o10 = ly.i1 * a.w + lx.i0, o11 = ly.i1 * a.w + lx.i1;
+          for (int t = 0; t < a.T; ++t) {
+            const float* zt = zb + (int64_t)t * a.h * a.w;
+            const float left = __fadd_rn(__fmul_rn(wy0, __ldg(zt + o00)), __fmul_rn(ly.w1, __ldg(zt + o10)));
+            const float right = __fadd_rn(__fmul_rn(wy0, __ldg(zt + o01)), __fmul_rn(ly.w1, __ldg(zt + o11)));
+            const float v = __fadd_rn(__fmul_rn(wx0, left), __fmul_rn(lx.w1, right));
+            zmax = fmaxf(zmax, v);
+            if (t == a.focal_head) zfoc[j] = v;
+          }
+          cell[j] = o00;
+          cdx[j] = lx.i1 - lx.i0;
+          cell_dy[j] = (ly.i1 - ly.i0) * a.w;
+          wy1g[j] = ly.w1;
+          wx1[j] = lx.w1;
+        }
+        if (!a.seen_max) seen[j] = sigmoid_acc(zmax);
+      }
+    }
+
+    // ---- the tile: registers <- shared memory, softmax statistics, gradients -------------
+    mbar_wait(&bar_full[s], parity);
+    T* col = tile + px0;
+    float xy[2], x0[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) xy[j] = (y[j] >= 0) ? DT<T>::to_f(col[(size_t)y[j] * P + j]) : 0.f;
+    float e0[KREG], e1[KREG];
+#pragma unroll
+    for (int c = 0; c < KREG; ++c) Pair<T>::ld(col + (size_t)c * P, e0[c], e1[c]);
+    x0[0] = e0[0];
+    x0[1] = e1[0];
+    float mx0 = e0[0], mx1 = e1[0];
+    int am0 = 0, am1 = 0;
+#pragma unroll
+    for (int c = 1; c < KREG; ++c) {
+      if (e0[c] > mx0) { mx0 = e0[c]; am0 = c; }
+      if (e1[c] > mx1) { mx1 = e1[c]; am1 = c; }
+    }
+    const float nm0 = -mx0 * kLog2e, nm1 = -mx1 * kLog2e;
+    float sa0 = 0.f, sa1 = 0.f, so0 = 0.f, so1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < KREG; ++c) {
+      e0[c] = ex2_fast(fmaf(e0[c], kLog2e, nm0));
+      e1[c] = ex2_fast(fmaf(e1[c], kLog2e, nm1));
+      sa0 += e0[c];
+      sa1 += e1[c];
+      if (c < old_cl) {
+        so0 += e0[c];
+        so1 += e1[c];
+      }
+    }
+    PixCoef pc[2];
+    float gfoc[2];
+    uint8_t dmask[2];
+    pixel_terms(a, p.inv_n, s_norm, old_cl, y[0], is_ign[0], mx0, sa0, so0, e0[0], x0[0], xy[0], seen[0], have_seen,
+                zfoc[0], acc, pc[0], gfoc[0], dmask[0]);
+    pixel_terms(a, p.inv_n, s_norm, old_cl, y[1], is_ign[1], mx1, sa1, so1, e1[0], x0[1], xy[1], seen[1], have_seen,
+                zfoc[1], acc, pc[1], gfoc[1], dmask[1]);
+    if (a.dlogits) {
+      Pair<T>::st(col, e0[0] * pc[0].cg0 - pc[0].d0, e1[0] * pc[1].cg0 - pc[1].d0);
+#pragma unroll
+      for (int c = 1; c < KREG; ++c) {
+        const bool oldc = c < old_cl;
+        const float g0 = e0[c] * (oldc ? pc[0].cg1 : pc[0].cg2);
+        const float g1 = e1[c] * (oldc ? pc[1].cg1 : pc[1].cg2);
+        if (c < K) Pair<T>::st(col + (size_t)c * P, g0, g1);
+      }
+      // the label's own channel: recomputed in fp32 so that -dy is applied before rounding
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (y[j] >= 0 && pc[j].dy != 0.f) {
+          const int kk = y[j];
+          const float cgk = kk == 0 ? pc[j].cg0 : (kk < old_cl ? pc[j].cg1 : pc[j].cg2);
+          const float ey = ex2_fast(fmaf(xy[j], kLog2e, j == 0 ? nm0 : nm1));
+          col[(size_t)kk * P + j] = DT<T>::from_f(ey * cgk - pc[j].dy - (kk == 0 ? pc[j].d0 : 0.f));
+        }
+      }
+      fence_proxy_async();
+    }
+    mbar_arrive(&bar_done[s]);
+
+    // ---- thread 0: write tile k back, refill the stage of tile k-1 with tile k+2 ----------
+    if (tid == 0) {
+      mbar_wait(&bar_done[s], parity);
+      if (a.dlogits) {
+        T* dst = reinterpret_cast<T*>(a.dlogits) + (int64_t)b * K * HW + p0;
+        for (int c = 0; c < K; ++c) bulk_s2g(dst + (int64_t)c * HW, tile + (size_t)c * P, row_bytes);
+        bulk_commit();
+        // the store of tile k-1 (issued one tile ago) must have finished reading its stage
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      }
+      if (k + 2 < my_tiles) {
+        issue_load(pb, pt, (k + 2) % S);
+        advance(pb, pt);
+      }
+    }
+
+    // ---- arg-max / mask stores ---------------------------------------------------------------
+    if (a.preds)
+      *reinterpret_cast<longlong2*>(a.preds + (int64_t)b * HW + p0 + px0) = make_longlong2((long long)am0, (long long)am1);
+    if (a.distill_mask)
+      *reinterpret_cast<uchar2*>(a.distill_mask + (int64_t)b * HW + p0 + px0) = make_uchar2(dmask[0], dmask[1]);
+
+    // ---- focal gradient: adjoint of the bilinear up-sample -------------------------------------
+    if (a.gz) {
+      const unsigned full = 0xffffffffu;
+      if (ROWTILE) {
+        float c0 = gfoc[0] * (1.f - wx1[0]), c1 = gfoc[0] * wx1[0];
+        const int key = cx0[0] * 2 + cdx[0];
+        float d0 = 0.f, d1 = 0.f;
+        int x2 = -1, dx2 = 0;
+        {
+          const float f0 = gfoc[1] * (1.f - wx1[1]), f1 = gfoc[1] * wx1[1];
+          if (cx0[1] * 2 + cdx[1] == key) {
+            c0 += f0;
+            c1 += f1;
+          } else {  // low-res column boundary inside the pair
+            d0 = f0; d1 = f1; x2 = cx0[1]; dx2 = cdx[1];
+          }
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float n0 = __shfl_down_sync(full, c0, o), n1 = __shfl_down_sync(full, c1, o);
+          const int nk = __shfl_down_sync(full, key, o);
+          if (lane + o < 32 && nk == key) {
+            c0 += n0;
+            c1 += n1;
+          }
+        }
+        const int pk = __shfl_up_sync(full, key, 1);
+        if (((lane == 0) || (pk != key)) && cx0[0] >= 0) {
+          if (c0 != 0.f) atomicAdd(&gacc[cx0[0]], c0);
+          if (c1 != 0.f) atomicAdd(&gacc[cx0[0] + cdx[0]], c1);
+        }
+        if (x2 >= 0) {
+          if (d0 != 0.f) atomicAdd(&gacc[x2], d0);
+          if (d1 != 0.f) atomicAdd(&gacc[x2 + dx2], d1);
+        }
+        fast_sync();
+        if (tid < a.w) {
+          const float v = gacc[tid];
+          if (v != 0.f) {
+            float* g = a.gz + (int64_t)b * a.h * a.w;
+            atomicAdd(g + ly_row.i0 * a.w + tid, (1.f - ly_row.w1) * v);
+            if (ly_row.w1 != 0.f) atomicAdd(g + ly_row.i1 * a.w + tid, ly_row.w1 * v);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float c00 = gfoc[j] * (1.f - wy1g[j]) * (1.f - wx1[j]);
+          float c01 = gfoc[j] * (1.f - wy1g[j]) * wx1[j];
+          float c10 = gfoc[j] * wy1g[j] * (1.f - wx1[j]);
+          float c11 = gfoc[j] * wy1g[j] * wx1[j];
+          const int key = cell[j] * 4 + cdx[j] + 2 * (cell_dy[j] != 0);
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float n00 = __shfl_down_sync(full, c00, o), n01 = __shfl_down_sync(full, c01, o);
+            const float n10 = __shfl_down_sync(full, c10, o), n11 = __shfl_down_sync(full, c11, o);
+            const int nk = __shfl_down_sync(full, key, o);
+            if (lane + o < 32 && nk == key) {
+              c00 += n00; c01 += n01; c10 += n10; c11 += n11;
+            }
+          }
+          const int pk = __shfl_up_sync(full, key, 1);
+          if (((lane == 0) || (pk != key)) && cell[j] >= 0) {
+            float* g = a.gz + (int64_t)b * a.h * a.w + cell[j];
+            if (c00 != 0.f) atomicAdd(g, c00);
+            if (c01 != 0.f) atomicAdd(g + cdx[j], c01);
+            if (c10 != 0.f) atomicAdd(g + cell_dy[j], c10);
+            if (c11 != 0.f) atomicAdd(g + cell_dy[j] + cdx[j], c11);
+          }
+        }
+      }
+    }
+
+    if (a.mode == BACS_PIX_SCORE) {  // per-image sums: flush the accumulators per tile
+#pragma unroll
+      for (int i = 0; i < BACS_NACC; ++i) {
+        const float r = warp_sum(acc[i]);
+        if (lane == 0) red_scratch[wid][i] = r;
+        acc[i] = 0.f;
+      }
+      fast_sync();
+      if (tid < BACS_NACC) {
+        float r = 0.f;
+        for (int wv = 0; wv < 8; ++wv) r += red_scratch[wv][tid];
+        p.partials[((int64_t)b * tpi + t_in) * BACS_NACC + tid] = (double)r;
+      }
+      fast_sync();
+    }
+  }
+  if (tid == 0) bulk_wait_all();
+
+  if (a.mode != BACS_PIX_SCORE) {
+#pragma unroll
+    for (int i = 0; i < BACS_NACC; ++i) {
+      const float r = warp_sum(acc[i]);
+      if (lane == 0) red_scratch[wid][i] = r;
+    }
+    fast_sync();
+    if (tid < BACS_NACC) {
+      double r = 0.0;
+      for (int wv = 0; wv < 8; ++wv) r += (double)red_scratch[wv][tid];
+      p.partials[(int64_t)blockIdx.x * BACS_NACC + tid] = r;
+    }
+  }
+}
+
+template <typename T, int KREG, bool ROWTILE>
+static int launch_fast_one(const PixelParams& p, const PixelPlan& plan, cudaStream_t s) {
+  auto kern = pixel_fast_kernel<T, KREG, ROWTILE>;
+  if (plan.smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    if (e != cudaSuccess) {
+      set_error("bacs_pixel_loss: cannot opt in to %zu bytes of shared memory: %s", plan.smem, cudaGetErrorString(e));
+      return BACS_ERR_CUDA;
+    }
+  }
+  kern<<<plan.grid, kFastThreads, plan.smem, s>>>(p);
+  return BACS_OK;
+}
+
+template <typename T>
+static int launch_fast_dtype(const PixelParams& p, const PixelPlan& plan, cudaStream_t s) {
+#define BACS_FAST_CASE(KR)                                             \
+  case KR:                                                             \
+    return plan.rowtile ? launch_fast_one<T, KR, true>(p, plan, s)     \
+                        : launch_fast_one<T, KR, false>(p, plan, s);
+  switch (plan.kreg) {
+    BACS_FAST_CASE(4)
+    BACS_FAST_CASE(8)
+    BACS_FAST_CASE(12)
+    BACS_FAST_CASE(16)
+    BACS_FAST_CASE(20)
+    BACS_FAST_CASE(21)
+    BACS_FAST_CASE(24)
+    default:
+      set_error("bacs_pixel_loss: no fast kernel for KREG=%d", plan.kreg);
+      return BACS_ERR_UNSUPPORTED;
+  }
+#undef BACS_FAST_CASE
+}
+
+}  // namespace bacs

@@ -1,0 +1,9 @@
+// Instantiation of the register-resident per-pixel kernels for one storage type
+// (one translation unit per type so that nvcc compiles them in parallel).
+#include "pixel_fast.cuh"
+
+namespace bacs {
+int launch_pixel_fast_f16(const PixelParams& p, const PixelPlan& plan, cudaStream_t s) {
+  return launch_fast_dtype<__half>(p, plan, s);
+}
+}  // namespace bacs

@@ -1,10 +1,11 @@
 // The fused per-pixel kernel of the BACS loss step.
 //
-// One CTA owns a tile of P consecutive pixels of one image.  The K logit rows of the tile
-// ([K][P], NCHW so each row is contiguous) are staged in shared memory by 1-D TMA bulk
-// copies (cp.async.bulk + mbarrier); labels, the low-res seen logits and the bilinear taps
-// are fetched into registers while the copies are in flight.  Softmax statistics are then
-// computed once per pixel and feed, in the same pass:
+// Persistent, warp-specialised CTAs (one producer warp + 8 consumer warps).  A tile is P
+// consecutive pixels of one image; its K logit rows ([K][P], NCHW so every row is one
+// contiguous segment) travel global -> shared memory by 1-D TMA bulk copies
+// (cp.async.bulk + mbarrier) through a ring of stages.  Consumers pull the tile into
+// registers, compute the softmax statistics ONCE per pixel and derive from them, in the
+// same pass:
 //   * background-aware unbiased CE  (training/loss_utils.py:542-585)   mode WEIGHTED_CE
 //   * plain / class-weighted CE     (loss/base_loss.py:237-240)        mode CE
 //   * MiB unbiased CE               (training/loss_utils.py:492-520)   mode UNBIASED_CE
@@ -14,550 +15,618 @@
 //      evaluated on the fly, networks/bg_detector.py:13-15)
 //   * the teacher-distill pixel mask (loss/bacs_loss.py:282-285)
 //   * arg-max (loss/bacs_loss.py:255)
-// The gradient rows overwrite the logits in shared memory and leave through TMA bulk
-// stores, so HBM sees one read and one write of [B,K,H,W] plus 8+8(+1) bytes per pixel.
-#include "common.cuh"
+// The gradient rows overwrite the logits of the stage in place and leave through TMA bulk
+// stores issued by the producer warp, so HBM sees one read and one write of [B,K,H,W]
+// plus 8 + 8 (+1) bytes per pixel, and the consumers never wait for a store.
+#include <algorithm>
+
+#include "pixel_common.cuh"
 
 namespace bacs {
 
-struct PixelParams {
-  bacs_pixel_args a;
-  int P;                // pixels per tile
-  int tiles_per_image;
-  int use_bulk;         // rows are 16-byte aligned -> TMA bulk copies
-  float inv_n;          // 1 / (B*H*W)
-  float sy, sx;         // align_corners=True scales (h-1)/(H-1), (w-1)/(W-1)
-  double* partials;     // [n_tiles, BACS_NACC]
-};
-
-// ---- PTX wrappers: mbarrier + 1-D bulk async copy (TMA) ------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-// ---- vector access to PPT adjacent pixels of one shared-memory row -------------------
-template <typename T, int PPT> struct Vec;
-template <> struct Vec<float, 1> {
-  __device__ static __forceinline__ void ld(const float* p, float* v) { v[0] = p[0]; }
-  __device__ static __forceinline__ void st(float* p, const float* v) { p[0] = v[0]; }
-};
-template <> struct Vec<float, 2> {
-  __device__ static __forceinline__ void ld(const float* p, float* v) {
-    const float2 t = *reinterpret_cast<const float2*>(p);
-    v[0] = t.x; v[1] = t.y;
-  }
-  __device__ static __forceinline__ void st(float* p, const float* v) {
-    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
-  }
-};
-template <> struct Vec<__nv_bfloat16, 1> {
-  __device__ static __forceinline__ void ld(const __nv_bfloat16* p, float* v) { v[0] = __bfloat162float(p[0]); }
-  __device__ static __forceinline__ void st(__nv_bfloat16* p, const float* v) { p[0] = __float2bfloat16_rn(v[0]); }
-};
-template <> struct Vec<__nv_bfloat16, 2> {
-  __device__ static __forceinline__ void ld(const __nv_bfloat16* p, float* v) {
-    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
-    v[0] = t.x; v[1] = t.y;
-  }
-  __device__ static __forceinline__ void st(__nv_bfloat16* p, const float* v) {
-    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v[0], v[1]);
-  }
-};
-template <> struct Vec<__half, 1> {
-  __device__ static __forceinline__ void ld(const __half* p, float* v) { v[0] = __half2float(p[0]); }
-  __device__ static __forceinline__ void st(__half* p, const float* v) { p[0] = __float2half_rn(v[0]); }
-};
-template <> struct Vec<__half, 2> {
-  __device__ static __forceinline__ void ld(const __half* p, float* v) {
-    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(p));
-    v[0] = t.x; v[1] = t.y;
-  }
-  __device__ static __forceinline__ void st(__half* p, const float* v) {
-    *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v[0], v[1]);
-  }
-};
-
-__device__ __forceinline__ float pow_gamma(float base, float gamma) {
-  if (gamma == 2.f) return base * base;
-  if (gamma == 1.f) return base;
-  if (gamma == 0.f) return 1.f;
-  return powf(base, gamma);
-}
-
-constexpr float kLog2e = 1.4426950408889634f;
-
-template <typename T, int PPT>
-__global__ void __launch_bounds__(256) pixel_loss_kernel(const PixelParams p) {
+// Shared-memory layout (dynamic): [stages][K*P] tiles | zr[T][w] | gacc[w+1]
+template <typename T, int PPT, int KREG, bool ROWTILE>
+__global__ void __launch_bounds__(kConsumers + 32, (KREG > 0 ? 2 : 1)) pixel_loss_kernel(const PixelParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t mbar;
-  __shared__ float red_scratch[32];
-  __shared__ float s_norm;  // CE-type gradient normaliser (1 / sum of weights)
+  __shared__ uint64_t bar_full[kMaxStages];  // producer -> consumers: tile landed
+  __shared__ uint64_t bar_done[kMaxStages];  // consumers -> producer: gradients written; store / refill the stage
+  __shared__ float red_scratch[kConsumerWarps][BACS_NACC];
+  __shared__ float s_norm_sh;
 
   const bacs_pixel_args& a = p.a;
-  T* tile = reinterpret_cast<T*>(smem_raw);
-  const int P = p.P;
-  const int K = a.K;
+  const int P = p.P, K = a.K, S = p.stages;
   const int tid = threadIdx.x;
-  const int b = blockIdx.x / p.tiles_per_image;
-  const int tile_in_img = blockIdx.x - b * p.tiles_per_image;
   const int64_t HW = (int64_t)a.H * a.W;
-  const int64_t p0 = (int64_t)tile_in_img * P;
-  const int npx = (int)min((int64_t)P, HW - p0);
-  const T* __restrict__ src = reinterpret_cast<const T*>(a.logits) + (int64_t)b * K * HW + p0;
-  const bool bulk = p.use_bulk && ((npx * (int)sizeof(T)) & 15) == 0;
+  const size_t tile_elems = (size_t)K * P;
+  T* tiles = reinterpret_cast<T*>(smem_raw);
+  float* zr = reinterpret_cast<float*>(smem_raw + ((S * tile_elems * sizeof(T) + 15) / 16) * 16);
+  float* gacc = zr + (ROWTILE ? a.T * a.w : 0);
+  const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  // ---- 1. start the tile load -------------------------------------------------------
-  if (bulk) {
-    if (tid == 0) {
-      mbar_init(&mbar, 1);
-      fence_mbar_init();
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_done[s], kConsumers);
     }
-    __syncthreads();
-    if (tid < 32) {
-      if (tid == 0) mbar_expect_tx(&mbar, (uint32_t)(K * npx * (int)sizeof(T)));
-      __syncwarp();
-      for (int c = tid; c < K; c += 32) bulk_g2s(tile + (int64_t)c * P, src + (int64_t)c * HW, (uint32_t)(npx * sizeof(T)), &mbar);
+    fence_mbar_init();
+    s_norm_sh = 0.f;
+  }
+  __syncthreads();
+  // CE-type modes: gradient normaliser from the label histogram (device-side, no host sync)
+  if (tid < 32 && a.mode != BACS_PIX_WEIGHTED_CE && a.dlogits != nullptr) {
+    double s = 0.0;
+    for (int c = tid; c < K && c < 256; c += 32)
+      if (c != a.ignore_index)
+        s += (double)a.hist[c] * ((a.mode == BACS_PIX_CE && a.class_w) ? (double)a.class_w[c] : 1.0);
+    s = warp_sum(s);
+    if (tid == 0) s_norm_sh = s > 0.0 ? (float)(1.0 / s) : 0.f;
+  }
+  __syncthreads();
+
+  // =====================================================================================
+  // producer warp
+  // =====================================================================================
+  if (tid >= kConsumers) {
+    const int lane = tid - kConsumers;
+    auto tile_geom = [&](int k, int& b, int64_t& p0, int& npx) {
+      const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+      b = tile / p.tiles_per_image;
+      p0 = (int64_t)(tile - b * p.tiles_per_image) * P;
+      npx = (int)min((int64_t)P, HW - p0);
+    };
+    auto load_tile = [&](int k) {
+      int b, npx;
+      int64_t p0;
+      tile_geom(k, b, p0, npx);
+      const int s = k % S;
+      T* dst = tiles + (size_t)s * tile_elems;
+      const T* src = reinterpret_cast<const T*>(a.logits) + (int64_t)b * K * HW + p0;
+      const bool bulk = p.use_bulk && ((npx * (int)sizeof(T)) & 15) == 0;
+      if (bulk) {
+        if (lane == 0) mbar_expect_tx(&bar_full[s], (uint32_t)(K * npx * (int)sizeof(T)));
+        __syncwarp();
+        for (int c = lane; c < K; c += 32)
+          bulk_g2s(dst + (size_t)c * P, src + (int64_t)c * HW, (uint32_t)(npx * sizeof(T)), &bar_full[s]);
+      } else {  // ragged / unaligned rows: plain copies by the producer warp
+        for (int c = 0; c < K; ++c)
+          for (int i = lane; i < npx; i += 32) dst[(size_t)c * P + i] = src[(int64_t)c * HW + i];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_full[s]);
+      }
+    };
+    const int pre = min(S, my_tiles);
+    for (int k = 0; k < pre; ++k) load_tile(k);
+    for (int k = 0; k < my_tiles; ++k) {
+      const int s = k % S;
+      mbar_wait(&bar_done[s], (uint32_t)((k / S) & 1));
+      if (a.dlogits) {
+        int b, npx;
+        int64_t p0;
+        tile_geom(k, b, p0, npx);
+        const T* src = tiles + (size_t)s * tile_elems;
+        T* dst = reinterpret_cast<T*>(a.dlogits) + (int64_t)b * K * HW + p0;
+        const bool bulk = p.use_bulk && ((npx * (int)sizeof(T)) & 15) == 0;
+        if (bulk) {
+          for (int c = lane; c < K; c += 32)
+            bulk_s2g(dst + (int64_t)c * HW, src + (size_t)c * P, (uint32_t)(npx * sizeof(T)));
+          bulk_commit();
+          if (k + S < my_tiles) bulk_wait_read0();  // the stage is about to be refilled
+        } else {
+          for (int c = 0; c < K; ++c)
+            for (int i = lane; i < npx; i += 32) dst[(int64_t)c * HW + i] = src[(size_t)c * P + i];
+        }
+        __syncwarp();
+      }
+      if (k + S < my_tiles) load_tile(k + S);
     }
-  } else {
-    for (int c = 0; c < K; ++c)
-      for (int i = tid; i < npx; i += blockDim.x) tile[(int64_t)c * P + i] = src[(int64_t)c * HW + i];
+    bulk_wait_all();
+    return;
   }
 
-  // ---- 2. per-pixel side inputs while the copies fly --------------------------------
+  // =====================================================================================
+  // consumer warps
+  // =====================================================================================
+  const int lane = tid & 31, wid = tid >> 5;
   const int px0 = tid * PPT;
-  int y[PPT];         // label, -1 = ignore / invalid
-  bool is_ign[PPT];
-  float zmax[PPT], zfoc[PPT];
-  int cell[PPT];      // low-res cell id y0*w+x0 (focal scatter key)
-  int cell_dx[PPT], cell_dy[PPT];
-  float wy1[PPT], wx1[PPT];
+  const int old_cl = min(max(a.old_cl, 0), K);
+  const bool have_seen = (a.z != nullptr) || (a.seen_max != nullptr);
+  const float s_norm = s_norm_sh;
   float acc[BACS_NACC];
 #pragma unroll
   for (int i = 0; i < BACS_NACC; ++i) acc[i] = 0.f;
 
-  const int64_t* lab = a.labels + (int64_t)b * HW + p0;
+  auto tile_geom = [&](int k, int& b, int64_t& p0, int& npx) {
+    const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+    b = tile / p.tiles_per_image;
+    p0 = (int64_t)(tile - b * p.tiles_per_image) * P;
+    npx = (int)min((int64_t)P, HW - p0);
+  };
+  auto load_labels = [&](int k, int64_t* lab) {
+    int b, npx;
+    int64_t p0;
+    tile_geom(k, b, p0, npx);
+    const int64_t* src = a.labels + (int64_t)b * HW + p0 + px0;
+    if (PPT == 2 && px0 + 1 < npx && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+      const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(src));
+      lab[0] = v.x;
+      lab[PPT - 1] = v.y;
+    } else {
 #pragma unroll
-  for (int j = 0; j < PPT; ++j) {
-    const int px = px0 + j;
-    y[j] = -1;
-    is_ign[j] = true;
-    zmax[j] = 0.f;
-    zfoc[j] = 0.f;
-    cell[j] = -1;
-    cell_dx[j] = cell_dy[j] = 0;
-    wy1[j] = wx1[j] = 0.f;
-    if (px < npx) {
-      const int64_t l = __ldg(lab + px);
-      if (l == a.ignore_index) {
-        // ignored
-      } else if (l >= 0 && l < K) {
-        y[j] = (int)l;
-        is_ign[j] = false;
-      } else {
-        acc[BACS_ACC_INVALID] += 1.f;
-      }
-      if (a.z) {
-        const int64_t pix = p0 + px;
-        const int Y = (int)(pix / a.W), X = (int)(pix - (int64_t)Y * a.W);
-        const Lerp ly = lerp_align_corners(Y, a.h, p.sy), lx = lerp_align_corners(X, a.w, p.sx);
-        const float wx0 = 1.f - lx.w1, wy0 = 1.f - ly.w1;
-        const float* zb = a.z + (int64_t)b * a.T * a.h * a.w;
-        const int o00 = ly.i0 * a.w + lx.i0, o01 = ly.i0 * a.w + lx.i1;
-        const int o10 = ly.i1 * a.w + lx.i0, o11 = ly.i1 * a.w + lx.i1;
-        float m = -INFINITY;
-        for (int t = 0; t < a.T; ++t) {
-          const float* zt = zb + (int64_t)t * a.h * a.w;
-          // operation order of ATen's upsample_bilinear2d (no FMA contraction)
-          const float top = __fadd_rn(__fmul_rn(wx0, __ldg(zt + o00)), __fmul_rn(lx.w1, __ldg(zt + o01)));
-          const float bot = __fadd_rn(__fmul_rn(wx0, __ldg(zt + o10)), __fmul_rn(lx.w1, __ldg(zt + o11)));
-          const float v = __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(ly.w1, bot));
-          m = fmaxf(m, v);
-          if (t == a.focal_head) zfoc[j] = v;
-        }
-        zmax[j] = m;
-        cell[j] = o00;
-        cell_dx[j] = lx.i1 - lx.i0;
-        cell_dy[j] = (ly.i1 - ly.i0) * a.w;
-        wy1[j] = ly.w1;
-        wx1[j] = lx.w1;
-      }
+      for (int j = 0; j < PPT; ++j) lab[j] = (px0 + j < npx) ? __ldg(src + j) : (int64_t)a.ignore_index;
     }
-  }
+  };
+  int64_t lab_next[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) lab_next[j] = a.ignore_index;
+  if (my_tiles > 0) load_labels(0, lab_next);
 
-  // CE-type modes: gradient normaliser from the label histogram (device-side, no sync)
-  if (a.mode != BACS_PIX_WEIGHTED_CE && a.dlogits != nullptr) {
-    if (tid < 32) {
-      double s = 0.0;
-      if (a.mode == BACS_PIX_CE) {
-        for (int c = tid; c < K && c < 256; c += 32)
-          if (c != a.ignore_index) s += (double)a.hist[c] * (a.class_w ? (double)a.class_w[c] : 1.0);
-      } else {  // UNBIASED_CE: number of non-ignored pixels
-        for (int c = tid; c < K && c < 256; c += 32)
-          if (c != a.ignore_index) s += (double)a.hist[c];
+  for (int k = 0; k < my_tiles; ++k) {
+    int b, npx;
+    int64_t p0;
+    tile_geom(k, b, p0, npx);
+    const int s = k % S;
+    T* tile = tiles + (size_t)s * tile_elems;
+    int64_t lab[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) lab[j] = lab_next[j];
+    if (k + 1 < my_tiles) load_labels(k + 1, lab_next);
+
+    // ---- per-pixel side inputs --------------------------------------------------------
+    int y[PPT];
+    bool is_ign[PPT];
+    float seen[PPT], zfoc[PPT], wx1[PPT];
+    int cx0[PPT], cdx[PPT];
+    int cell[PPT], cell_dy[PPT];  // generic (non row-tile) focal scatter bookkeeping
+    float wy1g[PPT];
+    int Yrow = 0;
+    Lerp ly_row = {0, 0, 0.f};
+    if (ROWTILE && a.z) {
+      // the tile lies inside image row Yrow: interpolate the T head rows in y once
+      Yrow = (int)(p0 / a.W);
+      ly_row = lerp_align_corners(Yrow, a.h, p.sy);
+      consumer_sync();  // previous tile's readers of zr / gacc are done
+      const float* zb = a.z + (int64_t)b * a.T * a.h * a.w;
+      const float wy0 = 1.f - ly_row.w1;
+      for (int i = tid; i < a.T * a.w; i += kConsumers) {
+        const int t = i / a.w, j = i - t * a.w;
+        const float* zt = zb + (int64_t)t * a.h * a.w;
+        zr[i] = __fadd_rn(__fmul_rn(wy0, __ldg(zt + ly_row.i0 * a.w + j)),
+                          __fmul_rn(ly_row.w1, __ldg(zt + ly_row.i1 * a.w + j)));
       }
-      s = warp_sum(s);
-      if (tid == 0) s_norm = s > 0.0 ? (float)(1.0 / s) : 0.f;
+      if (a.gz)
+        for (int i = tid; i < a.w + 1; i += kConsumers) gacc[i] = 0.f;
+      consumer_sync();
     }
-  }
-
-  // ---- 3. wait for the tile ----------------------------------------------------------
-  if (bulk) mbar_wait(&mbar, 0);
-  __syncthreads();
-
-  // ---- 4. softmax statistics ----------------------------------------------------------
-  const bool live = px0 < npx;  // P and npx are multiples of PPT on the vector path
-  const int old_cl = min(max(a.old_cl, 0), K);
-  float mx[PPT], s_all[PPT], s_old[PPT], e0[PPT], xy[PPT];
-  int amax[PPT];
-#pragma unroll
-  for (int j = 0; j < PPT; ++j) {
-    mx[j] = -INFINITY;
-    amax[j] = 0;
-    s_all[j] = s_old[j] = e0[j] = 0.f;
-    xy[j] = 0.f;
-  }
-  if (live) {
-    const T* col = tile + px0;
-    float v[PPT];
-    for (int c = 0; c < K; ++c) {
-      Vec<T, PPT>::ld(col + (int64_t)c * P, v);
-#pragma unroll
-      for (int j = 0; j < PPT; ++j)
-        if (v[j] > mx[j]) {
-          mx[j] = v[j];
-          amax[j] = c;
-        }
-    }
-    float nm[PPT];
-#pragma unroll
-    for (int j = 0; j < PPT; ++j) nm[j] = -mx[j] * kLog2e;
-    for (int c = 0; c < old_cl; ++c) {
-      Vec<T, PPT>::ld(col + (int64_t)c * P, v);
-#pragma unroll
-      for (int j = 0; j < PPT; ++j) s_old[j] += exp2f(fmaf(v[j], kLog2e, nm[j]));
-    }
-#pragma unroll
-    for (int j = 0; j < PPT; ++j) s_all[j] = s_old[j];
-    for (int c = old_cl; c < K; ++c) {
-      Vec<T, PPT>::ld(col + (int64_t)c * P, v);
-#pragma unroll
-      for (int j = 0; j < PPT; ++j) s_all[j] += exp2f(fmaf(v[j], kLog2e, nm[j]));
-    }
-    Vec<T, PPT>::ld(col, v);
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
-      e0[j] = exp2f(fmaf(v[j], kLog2e, nm[j]));
-      if (y[j] >= 0) xy[j] = DT<T>::to_f(col[(int64_t)y[j] * P + j]);
-    }
-  }
-
-  // ---- 5. per-pixel losses and gradient coefficients ----------------------------------
-  // gradient of pixel:  g_k = e_k * cg[group(k)] - [k==0]*d0 - [k==y]*dy
-  // groups: 0 -> k==0 ; 1 -> 1<=k<old_cl ; 2 -> k>=old_cl
-  float cg0[PPT], cg1[PPT], cg2[PPT], d0[PPT], dy[PPT];
-  float gfoc[PPT];  // d(focal term)/dZ of the pixel
-  uint8_t dmask[PPT];
-  const float gs_bacs = p.inv_n * a.grad_scale;
-#pragma unroll
-  for (int j = 0; j < PPT; ++j) {
-    cg0[j] = cg1[j] = cg2[j] = d0[j] = dy[j] = 0.f;
-    gfoc[j] = 0.f;
-    dmask[j] = 0;
-    if (!(live && px0 + j < npx)) continue;
-    const float S = s_all[j];
-    const float logS = logf(S);
-    const float lse = mx[j] + logS;
-    const float inv_S = 1.f / S;
-    const bool valid = y[j] >= 0;
-    if (!is_ign[j]) acc[BACS_ACC_KEPT] += 1.f;
-    if (valid) acc[BACS_ACC_VALID] += 1.f;
-    if (valid && y[j] == 0) acc[BACS_ACC_BG] += 1.f;
-    float seen = 0.f;
-    if (a.seen_max) seen = __ldg(a.seen_max + (int64_t)b * HW + p0 + px0 + j);
-    else if (a.z) seen = sigmoid_acc(zmax[j]);
-
-    if (a.mode == BACS_PIX_WEIGHTED_CE) {
-      if (valid) {
-        const float S_fg = S - e0[j];
-        const float u = a.ukd ? 1.f : 0.f;
-        const float inv_old = 1.f / s_old[j];
-        const float inv_fg = 1.f / S_fg;
-        float l1, l2;
-        if (y[j] == 0) {
-          float s = seen;
-          if (s > a.threshold) s = 1.f;
-          const float mod = pow_gamma(1.f - s, a.gamma);
-          l1 = mod * (lse - DT<T>::to_f(tile[px0 + j]));
-          l2 = u * (logS - logf(s_old[j]));
-          cg0[j] = mod * inv_S + u * (inv_S - inv_old);
-          cg1[j] = cg0[j];
-          cg2[j] = mod * inv_S + u * inv_S;
-          d0[j] = mod;
-        } else if (y[j] < old_cl) {
-          l1 = logS - logf(S_fg);
-          l2 = u * (logS - logf(s_old[j]));
-          cg0[j] = inv_S + u * (inv_S - inv_old);
-          cg1[j] = inv_S - inv_fg + u * (inv_S - inv_old);
-          cg2[j] = inv_S - inv_fg + u * inv_S;
+      const int px = px0 + j;
+      y[j] = -1;
+      is_ign[j] = true;
+      seen[j] = 0.f;
+      zfoc[j] = 0.f;
+      wx1[j] = 0.f;
+      cx0[j] = -1;
+      cdx[j] = 0;
+      cell[j] = -1;
+      cell_dy[j] = 0;
+      wy1g[j] = 0.f;
+      if (px < npx) {
+        const int64_t l = lab[j];
+        if (l == a.ignore_index) {
+        } else if (l >= 0 && l < K) {
+          y[j] = (int)l;
+          is_ign[j] = false;
         } else {
-          l1 = logS - logf(S_fg);
-          l2 = lse - xy[j];
-          cg0[j] = 2.f * inv_S;
-          cg1[j] = 2.f * inv_S - inv_fg;
-          cg2[j] = cg1[j];
-          dy[j] = 1.f;
+          acc[BACS_ACC_INVALID] += 1.f;
         }
-        acc[BACS_ACC_LOSS] += l1 + l2;
-        cg0[j] *= gs_bacs; cg1[j] *= gs_bacs; cg2[j] *= gs_bacs; d0[j] *= gs_bacs; dy[j] *= gs_bacs;
-      }
-    } else if (a.mode == BACS_PIX_CE || a.mode == BACS_PIX_SCORE) {
-      if (valid) {
-        const float wgt = a.class_w ? __ldg(a.class_w + y[j]) : 1.f;
-        acc[BACS_ACC_LOSS] += wgt * (lse - xy[j]);
-        acc[BACS_ACC_WSUM] += wgt;
-        if (a.dlogits) {
-          const float g = wgt * s_norm * a.grad_scale;
-          cg0[j] = cg1[j] = cg2[j] = g * inv_S;
-          dy[j] = g;
+        if (a.seen_max) seen[j] = __ldg(a.seen_max + (int64_t)b * HW + p0 + px);
+        if (a.z) {
+          const int64_t pix = p0 + px;
+          float zmax = -INFINITY;
+          if (ROWTILE) {
+            const int X = (int)(pix - (int64_t)Yrow * a.W);
+            const Lerp lx = lerp_align_corners(X, a.w, p.sx);
+            const float wx0 = 1.f - lx.w1;
+            for (int t = 0; t < a.T; ++t) {
+              const float v = __fadd_rn(__fmul_rn(wx0, zr[t * a.w + lx.i0]), __fmul_rn(lx.w1, zr[t * a.w + lx.i1]));
+              zmax = fmaxf(zmax, v);
+              if (t == a.focal_head) zfoc[j] = v;
+            }
+            cx0[j] = lx.i0;
+            cdx[j] = lx.i1 - lx.i0;
+            wx1[j] = lx.w1;
+          } else {
+            const int Y = (int)(pix / a.W), X = (int)(pix - (int64_t)Y * a.W);
+            const Lerp ly = lerp_align_corners(Y, a.h, p.sy), lx = lerp_align_corners(X, a.w, p.sx);
+            const float wx0 = 1.f - lx.w1, wy0 = 1.f - ly.w1;
+            const float* zb = a.z + (int64_t)b * a.T * a.h * a.w;
+            const int o00 = ly.i0 * a.w + lx.i0, o01 = ly.i0 * a.w + lx.i1;
+            const int o10 = ly.i1 * a.w + lx.i0, o11 = ly.i1 * a.w + lx.i1;
+            for (int t = 0; t < a.T; ++t) {
+              const float* zt = zb + (int64_t)t * a.h * a.w;
+              const float left = __fadd_rn(__fmul_rn(wy0, __ldg(zt + o00)), __fmul_rn(ly.w1, __ldg(zt + o10)));
+              const float right = __fadd_rn(__fmul_rn(wy0, __ldg(zt + o01)), __fmul_rn(ly.w1, __ldg(zt + o11)));
+              const float v = __fadd_rn(__fmul_rn(wx0, left), __fmul_rn(lx.w1, right));
+              zmax = fmaxf(zmax, v);
+              if (t == a.focal_head) zfoc[j] = v;
+            }
+            cell[j] = o00;
+            cdx[j] = lx.i1 - lx.i0;
+            cell_dy[j] = (ly.i1 - ly.i0) * a.w;
+            wy1g[j] = ly.w1;
+            wx1[j] = lx.w1;
+          }
+          if (!a.seen_max) seen[j] = sigmoid_acc(zmax);
         }
-      }
-    } else {  // BACS_PIX_UNBIASED_CE
-      if (valid) {
-        const float g = a.dlogits ? s_norm * a.grad_scale : 0.f;
-        if (y[j] < old_cl) {
-          acc[BACS_ACC_LOSS] += logS - logf(s_old[j]);
-          cg0[j] = cg1[j] = g * (inv_S - 1.f / s_old[j]);
-          cg2[j] = g * inv_S;
-        } else {
-          acc[BACS_ACC_LOSS] += lse - xy[j];
-          cg0[j] = cg1[j] = cg2[j] = g * inv_S;
-          dy[j] = g;
-        }
-        acc[BACS_ACC_WSUM] += 1.f;
       }
     }
 
-    // teacher-distill pixel mask: background label and confidently "seen"
-    if (a.distill_mask) {
-      const bool m = valid && y[j] == 0 && ((a.z == nullptr && a.seen_max == nullptr) || seen > a.lkd_threshold);
-      dmask[j] = m ? 1 : 0;
-      if (m) acc[BACS_ACC_DISTILL_PIX] += 1.f;
-    }
-
-    // seen-detector focal loss of head `focal_head` (binary, target = foreground)
-    if (a.gz && !is_ign[j]) {
-      const float Z = zfoc[j];
-      const float t = (valid && y[j] == 0) ? 0.f : 1.f;
-      const float bce = fmaxf(Z, 0.f) - Z * t + log1pf(expf(-fabsf(Z)));
-      const float pt = expf(-bce);
-      const float om = 1.f - pt;
-      float term = pow_gamma(om, a.focal_gamma) * bce;
-      const float sig = sigmoid_acc(Z);
-      float dterm;
-      if (a.focal_gamma == 2.f) dterm = (sig - t) * (om * om + 2.f * om * pt * bce);
-      else if (a.focal_gamma == 0.f) dterm = (sig - t);
-      else dterm = (sig - t) * (pow_gamma(om, a.focal_gamma) + a.focal_gamma * powf(om, a.focal_gamma - 1.f) * pt * bce);
-      if (a.focal_alpha >= 0.f) {
-        const float aw = a.focal_alpha * t + (1.f - a.focal_alpha) * (1.f - t);
-        term *= aw;
-        dterm *= aw;
-      }
-      acc[BACS_ACC_FOCAL] += term;
-      gfoc[j] = dterm;
-    }
-  }
-
-  // ---- 6. gradient rows overwrite the tile; arg-max / mask stores ----------------------
-  if (a.dlogits && live) {
-    T* col = tile + px0;
-    float v[PPT], g[PPT], nm[PPT], ey[PPT];
+    // ---- wait for the tile, softmax statistics, gradients ------------------------------
+    mbar_wait(&bar_full[s], (uint32_t)((k / S) & 1));
+    const bool live = px0 < npx;
+    PixCoef pc[PPT];
+    float gfoc[PPT];
+    uint8_t dmask[PPT];
+    int amax[PPT];
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
-      nm[j] = -mx[j] * kLog2e;
-      ey[j] = exp2f(fmaf(xy[j], kLog2e, nm[j]));
+      gfoc[j] = 0.f;
+      dmask[j] = 0;
+      amax[j] = 0;
     }
+    if (live) {
+      T* col = tile + px0;
+      float xy[PPT], x0[PPT];
 #pragma unroll
-    for (int j = 0; j < PPT; ++j) g[j] = e0[j] * cg0[j] - d0[j];
-    Vec<T, PPT>::st(col, g);
-    for (int c = 1; c < old_cl; ++c) {
-      Vec<T, PPT>::ld(col + (int64_t)c * P, v);
-#pragma unroll
-      for (int j = 0; j < PPT; ++j) g[j] = exp2f(fmaf(v[j], kLog2e, nm[j])) * cg1[j];
-      Vec<T, PPT>::st(col + (int64_t)c * P, g);
-    }
-    for (int c = max(old_cl, 1); c < K; ++c) {
-      Vec<T, PPT>::ld(col + (int64_t)c * P, v);
-#pragma unroll
-      for (int j = 0; j < PPT; ++j) g[j] = exp2f(fmaf(v[j], kLog2e, nm[j])) * cg2[j];
-      Vec<T, PPT>::st(col + (int64_t)c * P, g);
-    }
-    // the label's own channel: recomputed in fp32 from the saved x_y so the -dy term is
-    // applied before rounding to the storage type
-#pragma unroll
-    for (int j = 0; j < PPT; ++j) {
-      if (y[j] >= 0 && dy[j] != 0.f) {
-        const int k = y[j];
-        const float cgk = k == 0 ? cg0[j] : (k < old_cl ? cg1[j] : cg2[j]);
-        const float gv = ey[j] * cgk - dy[j] - (k == 0 ? d0[j] : 0.f);
-        col[(int64_t)k * P + j] = DT<T>::from_f(gv);
+      for (int j = 0; j < PPT; ++j) {
+        xy[j] = (y[j] >= 0) ? DT<T>::to_f(col[(size_t)y[j] * P + j]) : 0.f;
+        x0[j] = DT<T>::to_f(col[j]);
       }
-    }
-  }
-  if (live) {
-    if (a.preds) {
-      int64_t* out = a.preds + (int64_t)b * HW + p0 + px0;
-      if (PPT == 2 && px0 + 1 < npx && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
-        *reinterpret_cast<longlong2*>(out) = make_longlong2((long long)amax[0], (long long)amax[PPT - 1]);
-      } else {
+      if (KREG > 0) {
+        // ---------------- register-resident path (K <= KREG) ----------------
+        constexpr int KR = KREG > 0 ? KREG : 1;
+        float e[KR][PPT];
+        float mx[PPT], nm[PPT], s_all[PPT], s_old[PPT];
+#pragma unroll
+        for (int c = 0; c < KR; ++c)
+          if (c < K) Vec<T, PPT>::ld(col + (size_t)c * P, e[c]);
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) mx[j] = e[0][j];
+#pragma unroll
+        for (int c = 1; c < KR; ++c)
+          if (c < K) {
+#pragma unroll
+            for (int j = 0; j < PPT; ++j)
+              if (e[c][j] > mx[j]) {
+                mx[j] = e[c][j];
+                amax[j] = c;
+              }
+          }
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+          nm[j] = -mx[j] * kLog2e;
+          s_all[j] = s_old[j] = 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < KR; ++c)
+          if (c < K) {
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+              e[c][j] = ex2_fast(fmaf(e[c][j], kLog2e, nm[j]));
+              s_all[j] += e[c][j];
+              if (c < old_cl) s_old[j] += e[c][j];
+            }
+          }
 #pragma unroll
         for (int j = 0; j < PPT; ++j)
-          if (px0 + j < npx) out[j] = amax[j];
-      }
-    }
-    if (a.distill_mask) {
-      uint8_t* out = a.distill_mask + (int64_t)b * HW + p0 + px0;
+          pixel_terms(a, p.inv_n, s_norm, old_cl, y[j], is_ign[j], mx[j], s_all[j], s_old[j], e[0][j], x0[j], xy[j],
+                      seen[j], have_seen, zfoc[j], acc, pc[j], gfoc[j], dmask[j]);
+        if (a.dlogits) {
+          float g[PPT];
 #pragma unroll
-      for (int j = 0; j < PPT; ++j)
-        if (px0 + j < npx) out[j] = dmask[j];
-    }
-  }
-
-  // ---- 7. focal gradient: adjoint of the bilinear up-sample ----------------------------
-  // lanes of a warp hold consecutive pixels, so equal low-res cells form runs: segmented
-  // warp reduction keyed by the cell id, then one global atomic per run and tap.
-  if (a.gz) {
-    const unsigned full = 0xffffffffu;
-    const int lane = tid & 31;
+          for (int c = 0; c < KR; ++c)
+            if (c < K) {
 #pragma unroll
-    for (int j = 0; j < PPT; ++j) {
-      // process pixel j of every lane; with PPT == 2 runs are still contiguous per j
-      float c00 = gfoc[j] * (1.f - wy1[j]) * (1.f - wx1[j]);
-      float c01 = gfoc[j] * (1.f - wy1[j]) * wx1[j];
-      float c10 = gfoc[j] * wy1[j] * (1.f - wx1[j]);
-      float c11 = gfoc[j] * wy1[j] * wx1[j];
-      const int key = cell[j] * 4 + cell_dx[j] + 2 * (cell_dy[j] != 0);
+              for (int j = 0; j < PPT; ++j) {
+                const float cg = c == 0 ? pc[j].cg0 : (c < old_cl ? pc[j].cg1 : pc[j].cg2);
+                g[j] = e[c][j] * cg;
+                if (c == 0) g[j] -= pc[j].d0;
+                if (c == y[j]) g[j] -= pc[j].dy;
+              }
+              Vec<T, PPT>::st(col + (size_t)c * P, g);
+            }
+        }
+      } else {
+        // ---------------- generic path: three passes over the shared-memory tile ----------------
+        float mx[PPT], nm[PPT], s_all[PPT], s_old[PPT], e0[PPT], v[PPT];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const float n00 = __shfl_down_sync(full, c00, o), n01 = __shfl_down_sync(full, c01, o);
-        const float n10 = __shfl_down_sync(full, c10, o), n11 = __shfl_down_sync(full, c11, o);
-        const int nk = __shfl_down_sync(full, key, o);
-        if (lane + o < 32 && nk == key) {
-          c00 += n00; c01 += n01; c10 += n10; c11 += n11;
+        for (int j = 0; j < PPT; ++j) {
+          mx[j] = -INFINITY;
+          s_all[j] = s_old[j] = 0.f;
+        }
+        for (int c = 0; c < K; ++c) {
+          Vec<T, PPT>::ld(col + (size_t)c * P, v);
+#pragma unroll
+          for (int j = 0; j < PPT; ++j)
+            if (v[j] > mx[j]) {
+              mx[j] = v[j];
+              amax[j] = c;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) nm[j] = -mx[j] * kLog2e;
+        for (int c = 0; c < old_cl; ++c) {
+          Vec<T, PPT>::ld(col + (size_t)c * P, v);
+#pragma unroll
+          for (int j = 0; j < PPT; ++j) s_old[j] += ex2_fast(fmaf(v[j], kLog2e, nm[j]));
+        }
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) s_all[j] = s_old[j];
+        for (int c = old_cl; c < K; ++c) {
+          Vec<T, PPT>::ld(col + (size_t)c * P, v);
+#pragma unroll
+          for (int j = 0; j < PPT; ++j) s_all[j] += ex2_fast(fmaf(v[j], kLog2e, nm[j]));
+        }
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+          e0[j] = ex2_fast(fmaf(x0[j], kLog2e, nm[j]));
+          pixel_terms(a, p.inv_n, s_norm, old_cl, y[j], is_ign[j], mx[j], s_all[j], s_old[j], e0[j], x0[j], xy[j],
+                      seen[j], have_seen, zfoc[j], acc, pc[j], gfoc[j], dmask[j]);
+        }
+        if (a.dlogits) {
+          float g[PPT];
+#pragma unroll
+          for (int j = 0; j < PPT; ++j) g[j] = e0[j] * pc[j].cg0 - pc[j].d0;
+          Vec<T, PPT>::st(col, g);
+          for (int c = 1; c < old_cl; ++c) {
+            Vec<T, PPT>::ld(col + (size_t)c * P, v);
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) g[j] = ex2_fast(fmaf(v[j], kLog2e, nm[j])) * pc[j].cg1;
+            Vec<T, PPT>::st(col + (size_t)c * P, g);
+          }
+          for (int c = max(old_cl, 1); c < K; ++c) {
+            Vec<T, PPT>::ld(col + (size_t)c * P, v);
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) g[j] = ex2_fast(fmaf(v[j], kLog2e, nm[j])) * pc[j].cg2;
+            Vec<T, PPT>::st(col + (size_t)c * P, g);
+          }
+          // the label's own channel, recomputed in fp32 so -dy is applied before rounding
+#pragma unroll
+          for (int j = 0; j < PPT; ++j) {
+            if (y[j] >= 0 && pc[j].dy != 0.f) {
+              const int kk = y[j];
+              const float cgk = kk == 0 ? pc[j].cg0 : (kk < old_cl ? pc[j].cg1 : pc[j].cg2);
+              const float ey = ex2_fast(fmaf(xy[j], kLog2e, nm[j]));
+              col[(size_t)kk * P + j] = DT<T>::from_f(ey * cgk - pc[j].dy - (kk == 0 ? pc[j].d0 : 0.f));
+            }
+          }
         }
       }
-      const int pk = __shfl_up_sync(full, key, 1);
-      const bool head = (lane == 0) || (pk != key);
-      if (head && cell[j] >= 0) {
-        float* g = a.gz + (int64_t)b * a.h * a.w + cell[j];
-        if (c00 != 0.f) atomicAdd(g, c00);
-        if (c01 != 0.f) atomicAdd(g + cell_dx[j], c01);
-        if (c10 != 0.f) atomicAdd(g + cell_dy[j], c10);
-        if (c11 != 0.f) atomicAdd(g + cell_dy[j] + cell_dx[j], c11);
-      }
     }
-  }
+    // hand the stage back to the producer (gradient rows are complete)
+    fence_proxy_async();
+    mbar_arrive(&bar_done[s]);
 
-  // ---- 8. ship the gradient tile ---------------------------------------------------------
-  if (a.dlogits) {
-    T* dst = reinterpret_cast<T*>(a.dlogits) + (int64_t)b * K * HW + p0;
-    if (bulk) {
-      fence_proxy_async();
-      __syncthreads();
-      if (tid < 32) {
-        for (int c = tid; c < K; c += 32) bulk_s2g(dst + (int64_t)c * HW, tile + (int64_t)c * P, (uint32_t)(npx * sizeof(T)));
-        bulk_commit();
-      }
-    } else {
-      __syncthreads();
-      for (int c = 0; c < K; ++c)
-        for (int i = tid; i < npx; i += blockDim.x) dst[(int64_t)c * HW + i] = tile[(int64_t)c * P + i];
-    }
-  }
-
-  // ---- 9. per-tile partial sums ------------------------------------------------------------
+    // ---- arg-max / mask stores -------------------------------------------------------------
+    if (live) {
+      if (a.preds) {
+        int64_t* out = a.preds + (int64_t)b * HW + p0 + px0;
+        if (PPT == 2 && px0 + 1 < npx && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+          *reinterpret_cast<longlong2*>(out) = make_longlong2((long long)amax[0], (long long)amax[PPT - 1]);
+        } else {
 #pragma unroll
-  for (int i = 0; i < BACS_NACC; ++i) {
-    const float r = block_sum(acc[i], red_scratch);
-    if (tid == 0) p.partials[(int64_t)blockIdx.x * BACS_NACC + i] = (double)r;
+          for (int j = 0; j < PPT; ++j)
+            if (px0 + j < npx) out[j] = amax[j];
+        }
+      }
+      if (a.distill_mask) {
+        uint8_t* out = a.distill_mask + (int64_t)b * HW + p0 + px0;
+        if (PPT == 2 && px0 + 1 < npx) {
+          *reinterpret_cast<uchar2*>(out) = make_uchar2(dmask[0], dmask[PPT - 1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < PPT; ++j)
+            if (px0 + j < npx) out[j] = dmask[j];
+        }
+      }
+    }
+
+    // ---- focal gradient: adjoint of the bilinear up-sample ----------------------------------
+    if (a.gz) {
+      const unsigned full = 0xffffffffu;
+      if (ROWTILE) {
+        // all pixels share the row weights; reduce (g*(1-wx), g*wx) per low-res column.
+        // A thread's PPT pixels are adjacent: combine them when they share the column.
+        float c0 = gfoc[0] * (1.f - wx1[0]), c1 = gfoc[0] * wx1[0];
+        const int key = cx0[0] * 2 + cdx[0];
+        float d0 = 0.f, d1 = 0.f;
+        int x2 = -1, dx2 = 0;
+        if (PPT == 2) {
+          const float f0 = gfoc[PPT - 1] * (1.f - wx1[PPT - 1]), f1 = gfoc[PPT - 1] * wx1[PPT - 1];
+          const int k2 = cx0[PPT - 1] * 2 + cdx[PPT - 1];
+          if (k2 == key) {
+            c0 += f0;
+            c1 += f1;
+          } else {  // column boundary inside the pair: flushed on its own
+            d0 = f0; d1 = f1; x2 = cx0[PPT - 1]; dx2 = cdx[PPT - 1];
+          }
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float n0 = __shfl_down_sync(full, c0, o), n1 = __shfl_down_sync(full, c1, o);
+          const int nk = __shfl_down_sync(full, key, o);
+          if (lane + o < 32 && nk == key) {
+            c0 += n0;
+            c1 += n1;
+          }
+        }
+        const int pk = __shfl_up_sync(full, key, 1);
+        if (((lane == 0) || (pk != key)) && cx0[0] >= 0) {
+          if (c0 != 0.f) atomicAdd(&gacc[cx0[0]], c0);
+          if (c1 != 0.f) atomicAdd(&gacc[cx0[0] + cdx[0]], c1);
+        }
+        if (x2 >= 0) {
+          if (d0 != 0.f) atomicAdd(&gacc[x2], d0);
+          if (d1 != 0.f) atomicAdd(&gacc[x2 + dx2], d1);
+        }
+        consumer_sync();
+        float* g = a.gz + (int64_t)b * a.h * a.w;
+        const float wy0 = 1.f - ly_row.w1;
+        for (int i = tid; i < a.w; i += kConsumers) {
+          const float v = gacc[i];
+          if (v != 0.f) {
+            atomicAdd(g + ly_row.i0 * a.w + i, wy0 * v);
+            if (ly_row.w1 != 0.f) atomicAdd(g + ly_row.i1 * a.w + i, ly_row.w1 * v);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+          float c00 = gfoc[j] * (1.f - wy1g[j]) * (1.f - wx1[j]);
+          float c01 = gfoc[j] * (1.f - wy1g[j]) * wx1[j];
+          float c10 = gfoc[j] * wy1g[j] * (1.f - wx1[j]);
+          float c11 = gfoc[j] * wy1g[j] * wx1[j];
+          const int key = cell[j] * 4 + cdx[j] + 2 * (cell_dy[j] != 0);
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float n00 = __shfl_down_sync(full, c00, o), n01 = __shfl_down_sync(full, c01, o);
+            const float n10 = __shfl_down_sync(full, c10, o), n11 = __shfl_down_sync(full, c11, o);
+            const int nk = __shfl_down_sync(full, key, o);
+            if (lane + o < 32 && nk == key) {
+              c00 += n00; c01 += n01; c10 += n10; c11 += n11;
+            }
+          }
+          const int pk = __shfl_up_sync(full, key, 1);
+          if (((lane == 0) || (pk != key)) && cell[j] >= 0) {
+            float* g = a.gz + (int64_t)b * a.h * a.w + cell[j];
+            if (c00 != 0.f) atomicAdd(g, c00);
+            if (c01 != 0.f) atomicAdd(g + cdx[j], c01);
+            if (c10 != 0.f) atomicAdd(g + cell_dy[j], c10);
+            if (c11 != 0.f) atomicAdd(g + cell_dy[j] + cdx[j], c11);
+          }
+        }
+      }
+    }
+
+    // SCORE mode needs per-image sums: flush the accumulators per tile
+    if (a.mode == BACS_PIX_SCORE) {
+#pragma unroll
+      for (int i = 0; i < BACS_NACC; ++i) {
+        const float r = warp_sum(acc[i]);
+        if (lane == 0) red_scratch[wid][i] = r;
+        acc[i] = 0.f;
+      }
+      consumer_sync();
+      if (tid < BACS_NACC) {
+        float r = 0.f;
+        for (int wv = 0; wv < kConsumerWarps; ++wv) r += red_scratch[wv][tid];
+        const int tile_id = (int)blockIdx.x + k * (int)gridDim.x;
+        p.partials[(int64_t)tile_id * BACS_NACC + tid] = (double)r;
+      }
+      consumer_sync();
+    }
   }
-  if (a.dlogits && bulk && tid < 32) bulk_wait_read0();
+
+  // ---- per-CTA partial sums ------------------------------------------------------------------
+  if (a.mode != BACS_PIX_SCORE) {
+#pragma unroll
+    for (int i = 0; i < BACS_NACC; ++i) {
+      const float r = warp_sum(acc[i]);
+      if (lane == 0) red_scratch[wid][i] = r;
+    }
+    consumer_sync();
+    if (tid < BACS_NACC) {
+      double r = 0.0;
+      for (int wv = 0; wv < kConsumerWarps; ++wv) r += (double)red_scratch[wv][tid];
+      p.partials[(int64_t)blockIdx.x * BACS_NACC + tid] = r;
+    }
+  }
 }
 
-// Deterministic reduction of the per-tile partials: grid.x = 1 (whole batch -> acc) plus,
-// in SCORE mode, one block per image (-> score[b] = -sum / (H*W)).
-__global__ void __launch_bounds__(1024) pixel_reduce_kernel(const double* __restrict__ partials, int n_tiles,
-                                                            int tiles_per_image, double* __restrict__ acc,
-                                                            double* __restrict__ score, double inv_hw) {
-  __shared__ double scratch[32];
+// Deterministic reduction of the partials: block 0 -> acc; in SCORE mode block 1+b -> score[b].
+__global__ void __launch_bounds__(256) pixel_reduce_kernel(const double* __restrict__ partials, int n_part,
+                                                           int tiles_per_image, double* __restrict__ acc,
+                                                           double* __restrict__ score, double inv_hw) {
+  __shared__ double scratch[8][BACS_NACC];
   const bool whole = blockIdx.x == 0;
   const int t0 = whole ? 0 : (blockIdx.x - 1) * tiles_per_image;
-  const int t1 = whole ? n_tiles : t0 + tiles_per_image;
-  const int nacc = whole ? BACS_NACC : 1;
-  for (int i = 0; i < nacc; ++i) {
-    double s = 0.0;
-    for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) s += partials[(int64_t)t * BACS_NACC + i];
-    s = block_sum(s, scratch);
-    if (threadIdx.x == 0) {
-      if (whole) acc[i] = s;
-      else score[blockIdx.x - 1] = -s * inv_hw;
-    }
+  const int t1 = whole ? n_part : t0 + tiles_per_image;
+  // thread (g, i): accumulator i of partial rows g, g+32, ... (a partial row is 64 contiguous bytes)
+  const int i = threadIdx.x & 7, g = threadIdx.x >> 3;
+  double s = 0.0;
+  for (int t = t0 + g; t < t1; t += 32) s += partials[(int64_t)t * BACS_NACC + i];
+  s += __shfl_xor_sync(0xffffffffu, s, 8);
+  s += __shfl_xor_sync(0xffffffffu, s, 16);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane < 8) scratch[wid][lane] = s;
+  __syncthreads();
+  if (threadIdx.x < BACS_NACC) {
+    double r = 0.0;
+    for (int wv = 0; wv < 8; ++wv) r += scratch[wv][threadIdx.x];
+    if (whole) acc[threadIdx.x] = r;
+    else if (threadIdx.x == BACS_ACC_LOSS) score[blockIdx.x - 1] = -r * inv_hw;
   }
 }
-
-struct PixelPlan {
-  int ppt, threads, P;
-  size_t smem;
-};
 
 static bool make_plan(const bacs_pixel_args& a, PixelPlan* plan) {
   const size_t es = dtype_size(a.dtype);
   const int64_t HW = (int64_t)a.H * a.W;
-  const int cand[4][2] = {{2, 256}, {2, 128}, {1, 128}, {1, 64}};
-  const size_t soft = 57 * 1024, hard = 200 * 1024;
-  for (int pass = 0; pass < 2; ++pass)
-    for (int i = 0; i < 4; ++i) {
-      if (cand[i][0] == 2 && (HW & 1)) continue;  // pixel pairs need even image sizes
-      const int P = cand[i][0] * cand[i][1];
-      const size_t smem = (size_t)a.K * P * es;
-      if (smem <= (pass == 0 ? soft : hard)) {
-        plan->ppt = cand[i][0];
-        plan->threads = cand[i][1];
-        plan->P = P;
-        plan->smem = smem;
-        return true;
+  const int sms = sm_count();
+  const size_t extra = (a.z ? (size_t)a.T * a.w * 4 : 0) + (size_t)(a.w + 1) * 4 + 64;
+  const size_t cap = 220 * 1024;
+  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+
+  // ---- fast path: K <= 24 logits per pixel stay in registers, full 512-pixel tiles, TMA ring ----
+  const bool fast_ok = a.K <= 24 && HW % 512 == 0 && (HW * es) % 16 == 0 && aligned16(a.logits) &&
+                       aligned16(a.labels) && (!a.dlogits || aligned16(a.dlogits)) && (!a.preds || aligned16(a.preds)) &&
+                       (!a.distill_mask || (reinterpret_cast<uintptr_t>(a.distill_mask) & 1) == 0);
+  if (fast_ok) {
+    static const int kregs[7] = {4, 8, 12, 16, 20, 21, 24};
+    int kreg = 24;
+    for (int i = 0; i < 7; ++i)
+      if (kregs[i] >= a.K) {
+        kreg = kregs[i];
+        break;
       }
+    const size_t smem = (size_t)3 * kreg * 512 * es + extra;
+    if (smem + 1024 <= cap) {
+      const int per_sm = (2 * (smem + 1024) <= cap) ? 2 : 1;
+      const int64_t tiles = HW / 512 * a.B;
+      plan->fast = 1;
+      plan->ppt = 2;
+      plan->P = 512;
+      plan->kreg = kreg;
+      plan->stages = 3;
+      plan->smem = smem;
+      plan->grid = (int)std::min<int64_t>(tiles, (int64_t)sms * per_sm);
+      plan->rowtile = (a.z != nullptr && a.W % 512 == 0 && a.w >= 1 && a.w <= 128 && 256 % a.w == 0) ? 1 : 0;
+      return true;
+    }
+  }
+
+  // ---- generic path: any K that fits a shared-memory tile, ragged / unaligned shapes ----
+  plan->fast = 0;
+  plan->kreg = 0;
+  for (int min_stages = 2; min_stages >= 1; --min_stages)
+    for (int ppt = 2; ppt >= 1; --ppt) {
+      if (ppt == 2 && (HW & 1)) continue;  // pixel pairs need even image sizes
+      const int P = ppt * kConsumers;
+      const size_t tile = (size_t)a.K * P * es;
+      int stages = 0;
+      for (int st = 3; st >= min_stages; --st)
+        if ((size_t)st * tile + extra + 1024 <= cap) {
+          stages = st;
+          break;
+        }
+      if (!stages) continue;
+      const int64_t tiles = (HW + P - 1) / P * a.B;
+      plan->ppt = ppt;
+      plan->P = P;
+      plan->stages = stages;
+      plan->smem = (size_t)stages * tile + extra;
+      plan->grid = (int)std::min<int64_t>(tiles, (int64_t)sms);
+      plan->rowtile = (a.z != nullptr && P <= a.W && a.W % P == 0) ? 1 : 0;
+      return true;
     }
   return false;
 }
@@ -574,15 +643,15 @@ size_t bacs_pixel_workspace_bytes(const bacs_pixel_args* a) {
   if (!make_plan(*a, &plan)) return 0;
   const int64_t HW = (int64_t)a->H * a->W;
   const int64_t tiles = (HW + plan.P - 1) / plan.P * a->B;
-  return align_up((size_t)tiles * BACS_NACC * sizeof(double), 256);
+  const int64_t n_part = a->mode == BACS_PIX_SCORE ? tiles : plan.grid;
+  return align_up((size_t)n_part * BACS_NACC * sizeof(double), 256);
 }
 
 int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_bytes, bacs_stream_t stream) {
   BACS_REQUIRE(a, "bacs_pixel_loss: null args");
   BACS_REQUIRE(a->logits && a->labels && a->acc, "bacs_pixel_loss: logits, labels and acc are required");
   BACS_REQUIRE(a->B > 0 && a->K > 0 && a->H > 0 && a->W > 0, "bacs_pixel_loss: bad shape");
-  BACS_REQUIRE(a->K <= 255 || a->ignore_index >= a->K || a->ignore_index < 0,
-               "bacs_pixel_loss: ignore_index inside the class range");
+  BACS_REQUIRE(a->ignore_index >= a->K || a->ignore_index < 0, "bacs_pixel_loss: ignore_index inside the class range");
   BACS_REQUIRE(a->mode >= 0 && a->mode <= BACS_PIX_SCORE, "bacs_pixel_loss: unknown mode %d", a->mode);
   BACS_REQUIRE(a->dtype >= 0 && a->dtype <= BACS_F16, "bacs_pixel_loss: unknown dtype %d", a->dtype);
   if (a->z) {
@@ -596,7 +665,8 @@ int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_
                  "bacs_pixel_loss: WEIGHTED_CE needs old_cl >= 1 and the seen logits / probabilities");
   if (a->mode != BACS_PIX_WEIGHTED_CE && a->dlogits)
     BACS_REQUIRE(a->hist, "bacs_pixel_loss: CE-type gradients need the label histogram");
-  if (a->mode == BACS_PIX_SCORE) BACS_REQUIRE(a->score && !a->dlogits, "bacs_pixel_loss: SCORE mode needs score and no gradient");
+  if (a->mode == BACS_PIX_SCORE)
+    BACS_REQUIRE(a->score && !a->dlogits, "bacs_pixel_loss: SCORE mode needs score and no gradient");
   PixelPlan plan;
   if (!make_plan(*a, &plan)) {
     set_error("bacs_pixel_loss: K=%d too large for a shared-memory tile", a->K);
@@ -606,7 +676,8 @@ int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_
   const int64_t tiles_per_image = (HW + plan.P - 1) / plan.P;
   const int64_t n_tiles = tiles_per_image * a->B;
   BACS_REQUIRE(n_tiles < 0x7fffffff, "bacs_pixel_loss: too many tiles");
-  if (workspace_bytes < (size_t)n_tiles * BACS_NACC * sizeof(double) || !workspace) {
+  const int64_t n_part = a->mode == BACS_PIX_SCORE ? n_tiles : plan.grid;
+  if (!workspace || workspace_bytes < (size_t)n_part * BACS_NACC * sizeof(double)) {
     set_error("bacs_pixel_loss: workspace too small (%zu bytes)", workspace_bytes);
     return BACS_ERR_WORKSPACE;
   }
@@ -615,37 +686,55 @@ int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_
   p.a = *a;
   p.P = plan.P;
   p.tiles_per_image = (int)tiles_per_image;
+  p.n_tiles = (int)n_tiles;
+  p.stages = plan.stages;
   p.inv_n = (float)(1.0 / ((double)a->B * (double)HW));
   p.sy = a->z ? ac_scale(a->h, a->H) : 0.f;
   p.sx = a->z ? ac_scale(a->w, a->W) : 0.f;
   p.partials = reinterpret_cast<double*>(workspace);
-  const bool aligned = ((HW * es) % 16 == 0) && ((reinterpret_cast<uintptr_t>(a->logits) & 15) == 0) &&
-                       (!a->dlogits || (reinterpret_cast<uintptr_t>(a->dlogits) & 15) == 0);
-  p.use_bulk = aligned ? 1 : 0;
-  const int64_t tiles2 = n_tiles;
+  p.use_bulk = (((HW * es) % 16 == 0) && ((reinterpret_cast<uintptr_t>(a->logits) & 15) == 0) &&
+                (!a->dlogits || (reinterpret_cast<uintptr_t>(a->dlogits) & 15) == 0))
+                   ? 1
+                   : 0;
   cudaStream_t s = (cudaStream_t)stream;
-#define LAUNCH_PIX(TT, PPT)                                                                                  \
-  do {                                                                                                       \
-    auto kern = pixel_loss_kernel<TT, PPT>;                                                                  \
-    if (plan.smem > 48 * 1024) {                                                                             \
+#define LAUNCH_PIX(TT, PPT, KREG, ROWT)                                                                        \
+  do {                                                                                                         \
+    auto kern = pixel_loss_kernel<TT, PPT, KREG, ROWT>;                                                        \
+    if (plan.smem > 48 * 1024) {                                                                               \
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem); \
-      if (e != cudaSuccess) {                                                                                \
-        set_error("bacs_pixel_loss: cannot opt in to %zu bytes of shared memory: %s", plan.smem,            \
-                  cudaGetErrorString(e));                                                                    \
-        return BACS_ERR_CUDA;                                                                                \
-      }                                                                                                      \
-    }                                                                                                        \
-    kern<<<(unsigned)tiles2, plan.threads, plan.smem, s>>>(p);                                               \
+      if (e != cudaSuccess) {                                                                                  \
+        set_error("bacs_pixel_loss: cannot opt in to %zu bytes of shared memory: %s", plan.smem,              \
+                  cudaGetErrorString(e));                                                                      \
+        return BACS_ERR_CUDA;                                                                                  \
+      }                                                                                                        \
+    }                                                                                                          \
+    kern<<<plan.grid, kConsumers + 32, plan.smem, s>>>(p);                                                     \
   } while (0)
-  BACS_DISPATCH_DTYPE(a->dtype, TT, {
-    if (plan.ppt == 2) LAUNCH_PIX(TT, 2);
-    else LAUNCH_PIX(TT, 1);
-  });
+#define LAUNCH_PIX_K(TT, PPT)                       \
+  do {                                              \
+    if (plan.rowtile) LAUNCH_PIX(TT, PPT, 0, true); \
+    else LAUNCH_PIX(TT, PPT, 0, false);             \
+  } while (0)
+  if (plan.fast) {
+    int rc;
+    switch (a->dtype) {
+      case BACS_F32: rc = launch_pixel_fast_f32(p, plan, s); break;
+      case BACS_BF16: rc = launch_pixel_fast_bf16(p, plan, s); break;
+      default: rc = launch_pixel_fast_f16(p, plan, s); break;
+    }
+    if (rc != BACS_OK) return rc;
+  } else {
+    BACS_DISPATCH_DTYPE(a->dtype, TT, {
+      if (plan.ppt == 2) LAUNCH_PIX_K(TT, 2);
+      else LAUNCH_PIX_K(TT, 1);
+    });
+  }
+#undef LAUNCH_PIX_K
 #undef LAUNCH_PIX
   BACS_CHECK_LAUNCH("bacs_pixel_loss");
   const int nblk = 1 + (a->mode == BACS_PIX_SCORE ? a->B : 0);
-  pixel_reduce_kernel<<<nblk, 1024, 0, s>>>(p.partials, (int)tiles2, p.tiles_per_image, a->acc, a->score,
-                                            1.0 / (double)HW);
+  pixel_reduce_kernel<<<nblk, 256, 0, s>>>(p.partials, (int)n_part, p.tiles_per_image, a->acc, a->score,
+                                           1.0 / (double)HW);
   BACS_CHECK_LAUNCH("bacs_pixel_loss(reduce)");
   return BACS_OK;
 }
