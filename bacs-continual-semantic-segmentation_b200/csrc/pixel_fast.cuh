@@ -15,40 +15,96 @@ namespace bacs {
 constexpr int kFastThreads = 256;
 constexpr int kFastP = 512;
 
-template <typename T> struct Pair;  // two adjacent pixels of one channel row in shared memory
-template <> struct Pair<float> {
-  __device__ static __forceinline__ void ld(const float* p, float& a, float& b) {
-    const float2 t = *reinterpret_cast<const float2*>(p);
-    a = t.x; b = t.y;
-  }
+// Two adjacent pixels of one channel row, as they sit in shared memory, plus the running
+// (max, arg-max) of both pixels.  For the 16-bit types the maximum and the arg-max are
+// tracked on the PACKED pair (HMNMX2 + HSET2 mask + LOP3): 3 instructions per channel
+// for both pixels; ties keep the lowest channel (strict >), as torch.argmax does.
+template <typename T> struct Raw;
+template <> struct Raw<float> {
+  using reg_t = float2;
+  struct Max {
+    float m0, m1;
+    int a0, a1;
+  };
+  __device__ static __forceinline__ reg_t ld(const float* p) { return *reinterpret_cast<const float2*>(p); }
   __device__ static __forceinline__ void st(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
   __device__ static __forceinline__ void fill(float* p, float v) { *p = v; }
-};
-template <> struct Pair<__nv_bfloat16> {
-  __device__ static __forceinline__ void ld(const __nv_bfloat16* p, float& a, float& b) {
-    const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
-    a = __uint_as_float(u << 16);
-    b = __uint_as_float(u & 0xffff0000u);
+  __device__ static __forceinline__ void unpack(reg_t r, float& a, float& b) { a = r.x; b = r.y; }
+  __device__ static __forceinline__ Max init(reg_t r) { return Max{r.x, r.y, 0, 0}; }
+  __device__ static __forceinline__ void update(Max& m, reg_t r, int c) {
+    if (r.x > m.m0) { m.m0 = r.x; m.a0 = c; }
+    if (r.y > m.m1) { m.m1 = r.y; m.a1 = c; }
   }
+  __device__ static __forceinline__ void finish(const Max& m, float& m0, float& m1, int& a0, int& a1) {
+    m0 = m.m0; m1 = m.m1; a0 = m.a0; a1 = m.a1;
+  }
+};
+template <> struct Raw<__nv_bfloat16> {
+  using reg_t = uint32_t;
+  struct Max {
+    __nv_bfloat162 m;
+    uint32_t a;
+  };
+  __device__ static __forceinline__ reg_t ld(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
   __device__ static __forceinline__ void st(__nv_bfloat16* p, float a, float b) {
     *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
   }
   __device__ static __forceinline__ void fill(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
-};
-template <> struct Pair<__half> {
-  __device__ static __forceinline__ void ld(const __half* p, float& a, float& b) {
-    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(p));
-    a = t.x; b = t.y;
+  __device__ static __forceinline__ void unpack(reg_t u, float& a, float& b) {
+    a = __uint_as_float(u << 16);
+    b = __uint_as_float(u & 0xffff0000u);
   }
+  __device__ static __forceinline__ Max init(reg_t r) { return Max{*reinterpret_cast<__nv_bfloat162*>(&r), 0u}; }
+  __device__ static __forceinline__ void update(Max& m, reg_t r, int c) {
+    const __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&r);
+    const uint32_t mask = __hgt2_mask(v, m.m);
+    m.m = __hmax2(v, m.m);
+    const uint32_t cc = (uint32_t)c | ((uint32_t)c << 16);
+    m.a = (m.a & ~mask) | (cc & mask);
+  }
+  __device__ static __forceinline__ void finish(const Max& m, float& m0, float& m1, int& a0, int& a1) {
+    const float2 f = __bfloat1622float2(m.m);
+    m0 = f.x; m1 = f.y;
+    a0 = (int)(m.a & 0xffffu); a1 = (int)(m.a >> 16);
+  }
+};
+template <> struct Raw<__half> {
+  using reg_t = uint32_t;
+  struct Max {
+    __half2 m;
+    uint32_t a;
+  };
+  __device__ static __forceinline__ reg_t ld(const __half* p) { return *reinterpret_cast<const uint32_t*>(p); }
   __device__ static __forceinline__ void st(__half* p, float a, float b) {
     *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b);
   }
   __device__ static __forceinline__ void fill(__half* p, float v) { *p = __float2half_rn(v); }
+  __device__ static __forceinline__ void unpack(reg_t u, float& a, float& b) {
+    const float2 f = __half22float2(*reinterpret_cast<__half2*>(&u));
+    a = f.x; b = f.y;
+  }
+  __device__ static __forceinline__ Max init(reg_t r) { return Max{*reinterpret_cast<__half2*>(&r), 0u}; }
+  __device__ static __forceinline__ void update(Max& m, reg_t r, int c) {
+    const __half2 v = *reinterpret_cast<__half2*>(&r);
+    const uint32_t mask = __hgt2_mask(v, m.m);
+    m.m = __hmax2(v, m.m);
+    const uint32_t cc = (uint32_t)c | ((uint32_t)c << 16);
+    m.a = (m.a & ~mask) | (cc & mask);
+  }
+  __device__ static __forceinline__ void finish(const Max& m, float& m0, float& m1, int& a0, int& a1) {
+    const float2 f = __half22float2(m.m);
+    m0 = f.x; m1 = f.y;
+    a0 = (int)(m.a & 0xffffu); a1 = (int)(m.a >> 16);
+  }
 };
 
 __device__ __forceinline__ void fast_sync() { __syncthreads(); }
 
-// Shared memory (dynamic): [3][KREG*512] tiles (rows K..KREG-1 hold -inf forever) | zr[T][w] | gacc[w+1]
+constexpr int kZCols = 8;          // low-res columns a warp's 64 pixels can touch (x16 up-sampling: <= 6)
+constexpr int kLabelBytes = kFastP * 8;
+
+// Shared memory (dynamic): 3 stages of { [KREG][512] logits (rows K..KREG-1 hold -inf forever),
+// 512 int64 labels } followed by one warp-private [T][kZCols] seen-logit strip per warp.
 template <typename T, int KREG, bool ROWTILE>
 __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const PixelParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -58,15 +114,18 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
   __shared__ float s_norm_sh;
 
   constexpr int P = kFastP, S = 3;
+  constexpr size_t tile_elems = (size_t)KREG * P;
+  constexpr size_t stage_bytes = tile_elems * sizeof(T) + kLabelBytes;
   const bacs_pixel_args& a = p.a;
   const int K = a.K;
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
   const int64_t HW = (int64_t)a.H * a.W;
-  constexpr size_t tile_elems = (size_t)KREG * P;
-  T* tiles = reinterpret_cast<T*>(smem_raw);
-  float* zr = reinterpret_cast<float*>(smem_raw + S * tile_elems * sizeof(T));
-  float* gacc = zr + (ROWTILE ? a.T * a.w : 0);
+  auto stage_tile = [&](int s) { return reinterpret_cast<T*>(smem_raw + (size_t)s * stage_bytes); };
+  auto stage_labels = [&](int s) {
+    return reinterpret_cast<const int64_t*>(smem_raw + (size_t)s * stage_bytes + tile_elems * sizeof(T));
+  };
+  float* zrw = reinterpret_cast<float*>(smem_raw + S * stage_bytes) + (size_t)wid * a.T * kZCols;
   const int grid = (int)gridDim.x;
   const int my_tiles = (p.n_tiles - (int)blockIdx.x + grid - 1) / grid;
   const int tpi = p.tiles_per_image;
@@ -83,7 +142,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
   // padding rows stay -inf: exp -> 0, never the arg-max, never stored
   for (int i = tid; i < S * (KREG - K) * P; i += kFastThreads) {
     const int s = i / ((KREG - K) * P), r = i - s * (KREG - K) * P;
-    Pair<T>::fill(tiles + (size_t)s * tile_elems + (size_t)K * P + r, -INFINITY);
+    Raw<T>::fill(stage_tile(s) + (size_t)K * P + r, -INFINITY);
   }
   __syncthreads();
   if (tid < 32 && a.mode != BACS_PIX_WEIGHTED_CE && a.dlogits != nullptr) {
@@ -99,15 +158,6 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
   // tile geometry is advanced incrementally (no integer divisions in the loop)
   const int step_b = grid / tpi, step_t = grid - step_b * tpi;
   int tb = (int)blockIdx.x / tpi, tt = (int)blockIdx.x - tb * tpi;  // tile k of this CTA: image tb, tile tt
-  auto issue_load = [&](int b, int t, int s) {
-    // thread 0 only; all tiles are full on this path
-    const T* src = reinterpret_cast<const T*>(a.logits) + (int64_t)b * K * HW + (int64_t)t * P;
-    T* dst = tiles + (size_t)s * tile_elems;
-    mbar_expect_tx(&bar_full[s], (uint32_t)K * row_bytes);
-    for (int c = 0; c < K; ++c) bulk_g2s(dst + (size_t)c * P, src + (int64_t)c * HW, row_bytes, &bar_full[s]);
-  };
-  // thread 0 keeps its own cursor for the tile to prefetch (k + 2)
-  int pb = tb, pt = tt;
   auto advance = [&](int& b, int& t) {
     b += step_b;
     t += step_t;
@@ -116,7 +166,18 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
       ++b;
     }
   };
-  if (tid == 0) {
+  // warp 0 is also the TMA producer: lane c moves logit row c, lane 31 the label strip
+  auto issue_load = [&](int b, int t, int s) {
+    const T* src = reinterpret_cast<const T*>(a.logits) + (int64_t)b * K * HW + (int64_t)t * P;
+    if (lane == 0) mbar_expect_tx(&bar_full[s], (uint32_t)K * row_bytes + kLabelBytes);
+    __syncwarp();
+    if (lane < K) bulk_g2s(stage_tile(s) + (size_t)lane * P, src + (int64_t)lane * HW, row_bytes, &bar_full[s]);
+    if (lane == 31)
+      bulk_g2s(const_cast<int64_t*>(stage_labels(s)), a.labels + (int64_t)b * HW + (int64_t)t * P, kLabelBytes,
+               &bar_full[s]);
+  };
+  int pb = tb, pt = tt;  // producer cursor (tile k + 2)
+  if (wid == 0) {
     for (int k = 0; k < 2 && k < my_tiles; ++k) {
       issue_load(pb, pt, k);
       advance(pb, pt);
@@ -130,50 +191,46 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
   float acc[BACS_NACC];
 #pragma unroll
   for (int i = 0; i < BACS_NACC; ++i) acc[i] = 0.f;
-
-  // per-thread constants of the row-tile seen-map staging
   const int tiles_per_row = ROWTILE ? a.W / P : 1;
-  const int zt0 = ROWTILE ? tid / max(a.w, 1) : 0, zj0 = ROWTILE ? tid - zt0 * a.w : 0;
-  const int zstep = ROWTILE ? kFastThreads / max(a.w, 1) : 1;  // host guarantees kFastThreads % w == 0
-
-  auto label_ptr = [&](int b, int t) { return a.labels + (int64_t)b * HW + (int64_t)t * P + px0; };
-  longlong2 lab_next = make_longlong2(a.ignore_index, a.ignore_index);
-  if (my_tiles > 0) lab_next = __ldg(reinterpret_cast<const longlong2*>(label_ptr(tb, tt)));
 
   for (int k = 0; k < my_tiles; ++k) {
     const int b = tb, t_in = tt;
     advance(tb, tt);
     const int s = k % S;
     const uint32_t parity = (uint32_t)((k / S) & 1);
-    T* tile = tiles + (size_t)s * tile_elems;
+    T* tile = stage_tile(s);
     const int64_t p0 = (int64_t)t_in * P;
-    const longlong2 lab = lab_next;
-    if (k + 1 < my_tiles) lab_next = __ldg(reinterpret_cast<const longlong2*>(label_ptr(tb, tt)));
 
-    // ---- per-pixel side inputs --------------------------------------------------------
+    // ---- seen logits of this warp's 64 pixels: y-interpolated strip in warp-private smem ------
+    Lerp ly_row = {0, 0, 0.f};
+    int Xw = 0, c_first = 0;
+    if (ROWTILE && a.z) {
+      const int Yrow = t_in / tiles_per_row;  // tiles_per_row is 1 for the 512-wide crops
+      Xw = (t_in - Yrow * tiles_per_row) * P + wid * 64;
+      ly_row = lerp_align_corners(Yrow, a.h, p.sy);
+      c_first = lerp_align_corners(Xw, a.w, p.sx).i0;
+      const float* zb = a.z + (int64_t)b * a.T * a.h * a.w;
+      const float wy0 = 1.f - ly_row.w1;
+      const int col = min(c_first + (lane & (kZCols - 1)), a.w - 1);
+      __syncwarp();
+      for (int t = lane / kZCols; t < a.T; t += 32 / kZCols) {
+        const float* zt = zb + (int64_t)t * a.h * a.w;
+        zrw[t * kZCols + (lane & (kZCols - 1))] =
+            __fadd_rn(__fmul_rn(wy0, __ldg(zt + ly_row.i0 * a.w + col)), __fmul_rn(ly_row.w1, __ldg(zt + ly_row.i1 * a.w + col)));
+      }
+      __syncwarp();
+    }
+
+    // ---- wait for the tile (logit rows + labels) ------------------------------------------------
+    mbar_wait(&bar_full[s], parity);
+    const longlong2 lab = *reinterpret_cast<const longlong2*>(stage_labels(s) + px0);
+
     int y[2];
     bool is_ign[2];
     float seen[2], zfoc[2], wx1[2];
     int cx0[2], cdx[2];
     int cell[2], cell_dy[2];
     float wy1g[2];
-    Lerp ly_row = {0, 0, 0.f};
-    int Yrow = 0, Xbase = 0;
-    if (ROWTILE) {
-      Yrow = t_in / tiles_per_row;  // tiles_per_row is 1 for the 512-wide crops
-      Xbase = (t_in - Yrow * tiles_per_row) * P;
-      ly_row = lerp_align_corners(Yrow, a.h, p.sy);
-      fast_sync();  // previous tile's readers of zr / gacc are done
-      const float* zb = a.z + (int64_t)b * a.T * a.h * a.w;
-      const float wy0 = 1.f - ly_row.w1;
-      for (int t = zt0; t < a.T; t += zstep) {
-        const float* zt = zb + (int64_t)t * a.h * a.w;
-        zr[t * a.w + zj0] = __fadd_rn(__fmul_rn(wy0, __ldg(zt + ly_row.i0 * a.w + zj0)),
-                                      __fmul_rn(ly_row.w1, __ldg(zt + ly_row.i1 * a.w + zj0)));
-      }
-      if (a.gz && tid <= a.w) gacc[tid] = 0.f;
-      fast_sync();
-    }
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int64_t l = j == 0 ? lab.x : lab.y;
@@ -193,12 +250,12 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
       if (a.z) {
         float zmax = -INFINITY;
         if (ROWTILE) {
-          const Lerp lx = lerp_align_corners(Xbase + px0 + j, a.w, p.sx);
+          const Lerp lx = lerp_align_corners(Xw + 2 * lane + j, a.w, p.sx);
           const float wx0 = 1.f - lx.w1;
-          const float* z0 = zr + lx.i0;
           const int dx = lx.i1 - lx.i0;
+          const float* z0 = zrw + (lx.i0 - c_first);
           for (int t = 0; t < a.T; ++t) {
-            const float v = __fadd_rn(__fmul_rn(wx0, z0[t * a.w]), __fmul_rn(lx.w1, z0[t * a.w + dx]));
+            const float v = __fadd_rn(__fmul_rn(wx0, z0[t * kZCols]), __fmul_rn(lx.w1, z0[t * kZCols + dx]));
             zmax = fmaxf(zmax, v);
             if (t == a.focal_head) zfoc[j] = v;
           }
@@ -231,52 +288,74 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
       }
     }
 
-    // ---- the tile: registers <- shared memory, softmax statistics, gradients -------------
-    mbar_wait(&bar_full[s], parity);
+    // ---- registers <- shared memory; max / arg-max on the packed pair ------------------------------
     T* col = tile + px0;
-    float xy[2], x0[2];
+    float xy[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) xy[j] = (y[j] >= 0) ? DT<T>::to_f(col[(size_t)y[j] * P + j]) : 0.f;
-    float e0[KREG], e1[KREG];
+    typename Raw<T>::reg_t raw[KREG];
 #pragma unroll
-    for (int c = 0; c < KREG; ++c) Pair<T>::ld(col + (size_t)c * P, e0[c], e1[c]);
-    x0[0] = e0[0];
-    x0[1] = e1[0];
-    float mx0 = e0[0], mx1 = e1[0];
-    int am0 = 0, am1 = 0;
+    for (int c = 0; c < KREG; ++c) raw[c] = Raw<T>::ld(col + (size_t)c * P);
+    typename Raw<T>::Max mt = Raw<T>::init(raw[0]);
 #pragma unroll
-    for (int c = 1; c < KREG; ++c) {
-      if (e0[c] > mx0) { mx0 = e0[c]; am0 = c; }
-      if (e1[c] > mx1) { mx1 = e1[c]; am1 = c; }
-    }
+    for (int c = 1; c < KREG; ++c) Raw<T>::update(mt, raw[c], c);
+    float mx0, mx1;
+    int am0, am1;
+    Raw<T>::finish(mt, mx0, mx1, am0, am1);
+
+    // ---- one exp per logit; sums in groups of four so that S_old costs one add per full group ------
     const float nm0 = -mx0 * kLog2e, nm1 = -mx1 * kLog2e;
+    float e0[KREG], e1[KREG];
     float sa0 = 0.f, sa1 = 0.f, so0 = 0.f, so1 = 0.f;
+    float x00, x01;
+    Raw<T>::unpack(raw[0], x00, x01);
 #pragma unroll
-    for (int c = 0; c < KREG; ++c) {
-      e0[c] = ex2_fast(fmaf(e0[c], kLog2e, nm0));
-      e1[c] = ex2_fast(fmaf(e1[c], kLog2e, nm1));
-      sa0 += e0[c];
-      sa1 += e1[c];
-      if (c < old_cl) {
-        so0 += e0[c];
-        so1 += e1[c];
+    for (int g = 0; g < (KREG + 3) / 4; ++g) {
+      float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = 4 * g + i;
+        if (c < KREG) {
+          float v0, v1;
+          Raw<T>::unpack(raw[c], v0, v1);
+          e0[c] = ex2_fast(fmaf(v0, kLog2e, nm0));
+          e1[c] = ex2_fast(fmaf(v1, kLog2e, nm1));
+          g0 = i == 0 ? e0[c] : g0 + e0[c];
+          g1 = i == 0 ? e1[c] : g1 + e1[c];
+        }
+      }
+      sa0 += g0;
+      sa1 += g1;
+      if (4 * g + 4 <= old_cl) {  // uniform: the whole group is old
+        so0 += g0;
+        so1 += g1;
+      } else if (4 * g < old_cl) {  // uniform: the boundary group
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = 4 * g + i;
+          if (c < KREG && c < old_cl) {
+            so0 += e0[c];
+            so1 += e1[c];
+          }
+        }
       }
     }
+
     PixCoef pc[2];
     float gfoc[2];
     uint8_t dmask[2];
-    pixel_terms(a, p.inv_n, s_norm, old_cl, y[0], is_ign[0], mx0, sa0, so0, e0[0], x0[0], xy[0], seen[0], have_seen,
+    pixel_terms(a, p.inv_n, s_norm, old_cl, y[0], is_ign[0], mx0, sa0, so0, e0[0], x00, xy[0], seen[0], have_seen,
                 zfoc[0], acc, pc[0], gfoc[0], dmask[0]);
-    pixel_terms(a, p.inv_n, s_norm, old_cl, y[1], is_ign[1], mx1, sa1, so1, e1[0], x0[1], xy[1], seen[1], have_seen,
+    pixel_terms(a, p.inv_n, s_norm, old_cl, y[1], is_ign[1], mx1, sa1, so1, e1[0], x01, xy[1], seen[1], have_seen,
                 zfoc[1], acc, pc[1], gfoc[1], dmask[1]);
     if (a.dlogits) {
-      Pair<T>::st(col, e0[0] * pc[0].cg0 - pc[0].d0, e1[0] * pc[1].cg0 - pc[1].d0);
+      Raw<T>::st(col, e0[0] * pc[0].cg0 - pc[0].d0, e1[0] * pc[1].cg0 - pc[1].d0);
 #pragma unroll
       for (int c = 1; c < KREG; ++c) {
         const bool oldc = c < old_cl;
         const float g0 = e0[c] * (oldc ? pc[0].cg1 : pc[0].cg2);
         const float g1 = e1[c] * (oldc ? pc[1].cg1 : pc[1].cg2);
-        if (c < K) Pair<T>::st(col + (size_t)c * P, g0, g1);
+        if (c < K) Raw<T>::st(col + (size_t)c * P, g0, g1);
       }
       // the label's own channel: recomputed in fp32 so that -dy is applied before rounding
 #pragma unroll
@@ -292,32 +371,34 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
     }
     mbar_arrive(&bar_done[s]);
 
-    // ---- thread 0: write tile k back, refill the stage of tile k-1 with tile k+2 ----------
-    if (tid == 0) {
+    // ---- warp 0: write tile k back, refill the stage of tile k-1 with tile k+2 ---------------------
+    if (wid == 0) {
       mbar_wait(&bar_done[s], parity);
       if (a.dlogits) {
         T* dst = reinterpret_cast<T*>(a.dlogits) + (int64_t)b * K * HW + p0;
-        for (int c = 0; c < K; ++c) bulk_s2g(dst + (int64_t)c * HW, tile + (size_t)c * P, row_bytes);
+        if (lane < K) bulk_s2g(dst + (int64_t)lane * HW, tile + (size_t)lane * P, row_bytes);
         bulk_commit();
-        // the store of tile k-1 (issued one tile ago) must have finished reading its stage
+        // this lane's store of tile k-1 (issued one tile ago) must have finished reading its stage
         asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       }
+      __syncwarp();
       if (k + 2 < my_tiles) {
         issue_load(pb, pt, (k + 2) % S);
         advance(pb, pt);
       }
     }
 
-    // ---- arg-max / mask stores ---------------------------------------------------------------
+    // ---- arg-max / mask stores -------------------------------------------------------------------------
     if (a.preds)
       *reinterpret_cast<longlong2*>(a.preds + (int64_t)b * HW + p0 + px0) = make_longlong2((long long)am0, (long long)am1);
     if (a.distill_mask)
       *reinterpret_cast<uchar2*>(a.distill_mask + (int64_t)b * HW + p0 + px0) = make_uchar2(dmask[0], dmask[1]);
 
-    // ---- focal gradient: adjoint of the bilinear up-sample -------------------------------------
+    // ---- focal gradient: adjoint of the bilinear up-sample, reduced per warp ------------------------------
     if (a.gz) {
       const unsigned full = 0xffffffffu;
       if (ROWTILE) {
+        // the warp's pixels share the row weights: reduce (g*(1-wx), g*wx) over runs of equal low-res column
         float c0 = gfoc[0] * (1.f - wx1[0]), c1 = gfoc[0] * wx1[0];
         const int key = cx0[0] * 2 + cdx[0];
         float d0 = 0.f, d1 = 0.f;
@@ -341,21 +422,27 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
           }
         }
         const int pk = __shfl_up_sync(full, key, 1);
+        float* g0p = a.gz + (int64_t)b * a.h * a.w + ly_row.i0 * a.w;
+        float* g1p = a.gz + (int64_t)b * a.h * a.w + ly_row.i1 * a.w;
+        const float wy0 = 1.f - ly_row.w1, wy1 = ly_row.w1;
         if (((lane == 0) || (pk != key)) && cx0[0] >= 0) {
-          if (c0 != 0.f) atomicAdd(&gacc[cx0[0]], c0);
-          if (c1 != 0.f) atomicAdd(&gacc[cx0[0] + cdx[0]], c1);
+          if (c0 != 0.f) {
+            atomicAdd(g0p + cx0[0], wy0 * c0);
+            if (wy1 != 0.f) atomicAdd(g1p + cx0[0], wy1 * c0);
+          }
+          if (c1 != 0.f) {
+            atomicAdd(g0p + cx0[0] + cdx[0], wy0 * c1);
+            if (wy1 != 0.f) atomicAdd(g1p + cx0[0] + cdx[0], wy1 * c1);
+          }
         }
         if (x2 >= 0) {
-          if (d0 != 0.f) atomicAdd(&gacc[x2], d0);
-          if (d1 != 0.f) atomicAdd(&gacc[x2 + dx2], d1);
-        }
-        fast_sync();
-        if (tid < a.w) {
-          const float v = gacc[tid];
-          if (v != 0.f) {
-            float* g = a.gz + (int64_t)b * a.h * a.w;
-            atomicAdd(g + ly_row.i0 * a.w + tid, (1.f - ly_row.w1) * v);
-            if (ly_row.w1 != 0.f) atomicAdd(g + ly_row.i1 * a.w + tid, ly_row.w1 * v);
+          if (d0 != 0.f) {
+            atomicAdd(g0p + x2, wy0 * d0);
+            if (wy1 != 0.f) atomicAdd(g1p + x2, wy1 * d0);
+          }
+          if (d1 != 0.f) {
+            atomicAdd(g0p + x2 + dx2, wy0 * d1);
+            if (wy1 != 0.f) atomicAdd(g1p + x2 + dx2, wy1 * d1);
           }
         }
       } else {
@@ -403,7 +490,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
       fast_sync();
     }
   }
-  if (tid == 0) bulk_wait_all();
+  if (wid == 0) bulk_wait_all();
 
   if (a.mode != BACS_PIX_SCORE) {
 #pragma unroll

@@ -588,7 +588,8 @@ static bool make_plan(const bacs_pixel_args& a, PixelPlan* plan) {
         kreg = kregs[i];
         break;
       }
-    const size_t smem = (size_t)3 * kreg * 512 * es + extra;
+    // 3 stages of {kreg logit rows, 512 int64 labels} + one [T][8] seen-logit strip per warp
+    const size_t smem = (size_t)3 * ((size_t)kreg * 512 * es + 4096) + (a.z ? (size_t)8 * a.T * 8 * 4 : 0) + 64;
     if (smem + 1024 <= cap) {
       const int per_sm = (2 * (smem + 1024) <= cap) ? 2 : 1;
       const int64_t tiles = HW / 512 * a.B;
@@ -599,7 +600,8 @@ static bool make_plan(const bacs_pixel_args& a, PixelPlan* plan) {
       plan->stages = 3;
       plan->smem = smem;
       plan->grid = (int)std::min<int64_t>(tiles, (int64_t)sms * per_sm);
-      plan->rowtile = (a.z != nullptr && a.W % 512 == 0 && a.w >= 1 && a.w <= 128 && 256 % a.w == 0) ? 1 : 0;
+      // row tiles: a tile lies inside one image row and 64 pixels touch <= 6 low-res columns
+      plan->rowtile = (a.z != nullptr && a.W % 512 == 0 && a.seen_scale >= 16) ? 1 : 0;
       return true;
     }
   }
