@@ -88,7 +88,8 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
   return r;
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// fast sigmoid (ex2.approx + rcp.approx, ~2 ulp): used on the bulk feature data
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 // accurate sigmoid (used where a threshold decision depends on it)
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 

@@ -13,6 +13,8 @@
 // This is algebraically identical to the reference and cuts the work per (channel,row) from
 // W pixel evaluations to w cell evaluations (16x fewer for the stride-16 networks).  The
 // centring of tau keeps the fp32 error at the level of the direct evaluation.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace bacs {
@@ -80,8 +82,11 @@ __global__ void __launch_bounds__(256) distill_moments_kernel(const uint8_t* __r
   out[4 * w] = m4;
 }
 
+#ifndef BACS_DISTILL_RB
+#define BACS_DISTILL_RB 4
+#endif
 constexpr int kDistillWarps = 8;
-constexpr int kChanPerWarp = 2;
+constexpr int kChanPerWarp = 1;
 constexpr int kChanPerCta = kDistillWarps * kChanPerWarp;
 
 // Value of a quantity that is linear in the row weight ty:  v(ty) = p + q * ty.
@@ -134,7 +139,7 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
 //   dL/da_n = -2 rs (u0 a_n + u1 d_n) ... accumulated against {1, ty} so that the corner
 //   gradients are assembled once per interval instead of once per row.
 template <typename T, int CPL>
-__global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T* __restrict__ old_att,
+__global__ void __launch_bounds__(32 * kDistillWarps, 3) distill_kernel(const T* __restrict__ old_att,
                                                                       const T* __restrict__ new_att, int A, int h,
                                                                       int w, int H, DistillTables tb,
                                                                       const float* __restrict__ moments, int rows_max,
@@ -261,61 +266,83 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T*
       }
     }
 
-#pragma unroll 2
-    for (int r = 0; r < nrows; ++r) {
-      const float ty = s_ty[Y0 + r];
-      const float* mr = s_mom + r * 5 * WP + lane;
-      float M0[CPL], M1[CPL], M2[CPL], M3[CPL], M4[CPL];
+    // rows are processed RB at a time so that RB independent dependency chains (shared-memory
+    // loads -> FMAs -> 5-step shuffle reduction -> rsqrt) are in flight per warp
+    // rows are processed RB at a time (RB independent dependency chains per warp: shared-memory
+    // loads -> FMAs -> 5-step shuffle reduction -> rsqrt); a 1-row tail handles odd counts
+    auto process_rows = [&](auto rb_tag, const float* mrow, const float* tyrow) {
+      constexpr int RB = decltype(rb_tag)::value;
+      float ty[RB];
+      float u0[RB][NC][CPL], u1[RB][NC][CPL], u2[RB][NC][CPL], va[RB][NC][CPL], vd[RB][NC][CPL], S[RB][NC];
 #pragma unroll
-      for (int m = 0; m < CPL; ++m) {
-        M0[m] = mr[32 * m];
-        M1[m] = mr[WP + 32 * m];
-        M2[m] = mr[2 * WP + 32 * m];
-        M3[m] = mr[3 * WP + 32 * m];
-        M4[m] = mr[4 * WP + 32 * m];
-      }
-      float u0[NC][CPL], u1[NC][CPL], u2[NC][CPL], va[NC][CPL], vd[NC][CPL], S[NC];
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
+      for (int q = 0; q < RB; ++q) {
+        ty[q] = tyrow[q];
+        const float* mr = mrow + q * 5 * WP;
+        float M0[CPL], M1[CPL], M2[CPL], M3[CPL], M4[CPL];
 #pragma unroll
         for (int m = 0; m < CPL; ++m) {
-          const float al = alpha[c][m].at(ty), sg = sigma[c][m].at(ty), de = delta[c][m].at(ty);
-          const float ep = eps[c][m].at(ty), d_o = dold[c][m].at(ty);
-          va[c][m] = an[c][m].at(ty);
-          vd[c][m] = dn[c][m].at(ty);
-          const float c0 = al * sg;
-          const float c1 = 2.f * fmaf(al, d_o, va[c][m] * de);
-          const float c2 = de * ep;
-          u0[c][m] = fmaf(c2, M2[m], fmaf(c1, M1[m], c0 * M0[m]));
-          u1[c][m] = fmaf(c2, M3[m], fmaf(c1, M2[m], c0 * M1[m]));
-          u2[c][m] = fmaf(c2, M4[m], fmaf(c1, M3[m], c0 * M2[m]));
-          const float sc = fmaf(c2, u2[c][m], fmaf(c1, u1[c][m], c0 * u0[c][m]));
-          S[c] = m == 0 ? sc : S[c] + sc;
+          M0[m] = mr[32 * m];
+          M1[m] = mr[WP + 32 * m];
+          M2[m] = mr[2 * WP + 32 * m];
+          M3[m] = mr[3 * WP + 32 * m];
+          M4[m] = mr[4 * WP + 32 * m];
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+#pragma unroll
+          for (int m = 0; m < CPL; ++m) {
+            const float al = alpha[c][m].at(ty[q]), sg = sigma[c][m].at(ty[q]), de = delta[c][m].at(ty[q]);
+            const float ep = eps[c][m].at(ty[q]), d_o = dold[c][m].at(ty[q]);
+            va[q][c][m] = an[c][m].at(ty[q]);
+            vd[q][c][m] = dn[c][m].at(ty[q]);
+            const float c0 = al * sg;
+            const float c1 = 2.f * fmaf(al, d_o, va[q][c][m] * de);
+            const float c2 = de * ep;
+            u0[q][c][m] = fmaf(c2, M2[m], fmaf(c1, M1[m], c0 * M0[m]));
+            u1[q][c][m] = fmaf(c2, M3[m], fmaf(c1, M2[m], c0 * M1[m]));
+            u2[q][c][m] = fmaf(c2, M4[m], fmaf(c1, M3[m], c0 * M2[m]));
+            const float sc = fmaf(c2, u2[q][c][m], fmaf(c1, u1[q][c][m], c0 * u0[q][c][m]));
+            S[q][c] = m == 0 ? sc : S[q][c] + sc;
+          }
         }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) S[c] += __shfl_xor_sync(0xffffffffu, S[c], o);
+        for (int q = 0; q < RB; ++q)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) S[q][c] += __shfl_xor_sync(0xffffffffu, S[q][c], o);
       }
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        // zero (or rounding-negative) row: norm 0 and sub-gradient 0, as torch's norm backward
-        const float rs = S[c] > 0.f ? rsqrt_fast(S[c]) : 0.f;
-        loss_acc = fmaf(S[c], rs, loss_acc);
-        if (want_grad) {
+      for (int q = 0; q < RB; ++q) {
 #pragma unroll
-          for (int m = 0; m < CPL; ++m) {
-            // dL/dc = rs * u ;  d/da_n = -2 (g0 a_n + g1 d_n) ; d/dd_n = -2 (g1 a_n + g2 d_n)
-            const float gA = rs * fmaf(u1[c][m], vd[c][m], u0[c][m] * va[c][m]);
-            const float gD = rs * fmaf(u2[c][m], vd[c][m], u1[c][m] * va[c][m]);
-            GA0[c][m] += gA;
-            GA1[c][m] = fmaf(gA, ty, GA1[c][m]);
-            GD0[c][m] += gD;
-            GD1[c][m] = fmaf(gD, ty, GD1[c][m]);
+        for (int c = 0; c < NC; ++c) {
+          // zero (or rounding-negative) row: norm 0 and sub-gradient 0, as torch's norm backward
+          const float rs = S[q][c] > 0.f ? rsqrt_fast(S[q][c]) : 0.f;
+          loss_acc = fmaf(S[q][c], rs, loss_acc);
+          if (want_grad) {
+#pragma unroll
+            for (int m = 0; m < CPL; ++m) {
+              // dL/dc = rs * u ;  d/da_n = -2 (g0 a_n + g1 d_n) ; d/dd_n = -2 (g1 a_n + g2 d_n)
+              const float gA = rs * fmaf(u1[q][c][m], vd[q][c][m], u0[q][c][m] * va[q][c][m]);
+              const float gD = rs * fmaf(u2[q][c][m], vd[q][c][m], u1[q][c][m] * va[q][c][m]);
+              GA0[c][m] += gA;
+              GA1[c][m] = fmaf(gA, ty[q], GA1[c][m]);
+              GD0[c][m] += gD;
+              GD1[c][m] = fmaf(gD, ty[q], GD1[c][m]);
+            }
           }
         }
       }
+    };
+    {
+      constexpr int RBM = BACS_DISTILL_RB;
+      const float* mrow = s_mom + lane;  // moments of the current row, this lane's column
+      const float* tyrow = s_ty + Y0;
+      int r0 = 0;
+      for (; r0 + RBM <= nrows; r0 += RBM, mrow += RBM * 5 * WP, tyrow += RBM)
+        process_rows(std::integral_constant<int, RBM>{}, mrow, tyrow);
+      for (; r0 < nrows; ++r0, mrow += 5 * WP, ++tyrow) process_rows(std::integral_constant<int, 1>{}, mrow, tyrow);
     }
 
     if (want_grad) {

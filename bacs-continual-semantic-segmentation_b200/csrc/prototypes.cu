@@ -44,25 +44,27 @@ __global__ void __launch_bounds__(256) proto_accumulate_kernel(const T* __restri
   const T* row = feat + ((int64_t)b * D + c) * hw;
   const int8_t* tk = task + (int64_t)b * hw;
   const int32_t* rk = rank + (int64_t)b * hw;
-  for (int q0 = 0; q0 < hw; q0 += 32) {
-    const int q = q0 + lane;
-    int t = -1;
-    float v = 0.f;
-    int k = 0;
-    if (q < hw) {
-      t = tk[q];
-      if (t >= 0) {
-        v = DT<T>::to_f(row[q]);
-        k = rk[q];
-      }
-    }
-    const int sp = __shfl_sync(0xffffffffu, split, t < 0 ? 0 : t);
-    const bool low = k < sp;
+  constexpr int U = 4;  // independent loads in flight per lane
+  for (int q0 = 0; q0 < hw; q0 += 32 * U) {
+    int t[U], k[U];
+    float v[U];
 #pragma unroll
-    for (int g = 0; g < TMAX; ++g) {
-      const float m = (t == g) ? v : 0.f;
-      lo[g] += low ? m : 0.f;
-      hi[g] += low ? 0.f : m;
+    for (int u = 0; u < U; ++u) {
+      const int q = q0 + u * 32 + lane;
+      t[u] = q < hw ? (int)tk[q] : -1;
+      v[u] = (t[u] >= 0) ? DT<T>::to_f(row[q]) : 0.f;
+      k[u] = (t[u] >= 0) ? rk[q] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int sp = __shfl_sync(0xffffffffu, split, t[u] < 0 ? 0 : t[u]);
+      const bool low = k[u] < sp;
+#pragma unroll
+      for (int g = 0; g < TMAX; ++g) {
+        const float m = (t[u] == g) ? v[u] : 0.f;
+        lo[g] += low ? m : 0.f;
+        hi[g] += low ? 0.f : m;
+      }
     }
   }
   float* out = partial + (((int64_t)b * D + c) * Tn) * 2;
@@ -79,27 +81,49 @@ __global__ void __launch_bounds__(256) proto_accumulate_kernel(const T* __restri
   }
 }
 
-// One thread per (task g, output row r): gathers the partial runs that land in row r.
-__global__ void __launch_bounds__(256) proto_finalize_kernel(const float* __restrict__ partial, int B, int D,
-                                                             const int32_t* __restrict__ n_bt, int Tn, int mode,
-                                                             double* __restrict__ sums, double* __restrict__ counts) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Tn * D) return;
-  const int g = idx / D, r = idx - g * D;
-  long long tot = 0;
-  for (int bb = 0; bb < B; ++bb) tot += n_bt[bb * Tn + g];
-  if (r == 0) counts[g] = (double)tot;
-  double acc = 0.0;
-  if (tot > 0) {
-    if (mode != 0) {
-      for (int bb = 0; bb < B; ++bb) acc += (double)partial[(((int64_t)bb * D + r) * Tn + g) * 2];
-    } else {
-      long long pre = 0;
-      for (int bb = 0; bb < B; ++bb) {
-        const long long nb = n_bt[bb * Tn + g];
-        if (nb > 0) {
+// One block per task g; thread r gathers the partial runs that land in output row r.
+// Image b's masked elements occupy flat positions [D*pre_b, D*(pre_b+n_b)), i.e. rows
+// lo_b .. hi_b of the D x N_g view; row r only looks at images with lo_b <= r <= hi_b + 1.
+constexpr int kFinMaxB = 1024;
+constexpr int kFinRows = 64;  // output rows per block
+__global__ void __launch_bounds__(kFinRows) proto_finalize_kernel(const float* __restrict__ partial, int B, int D,
+                                                                  const int32_t* __restrict__ n_bt, int Tn, int mode,
+                                                                  double* __restrict__ sums,
+                                                                  double* __restrict__ counts) {
+  __shared__ long long s_pre[kFinMaxB];
+  __shared__ int s_nb[kFinMaxB], s_lo[kFinMaxB], s_hi[kFinMaxB];
+  __shared__ long long s_tot;
+  const int g = blockIdx.x;
+  if (threadIdx.x == 0) {
+    long long run = 0;
+    for (int bb = 0; bb < B; ++bb) {
+      const int n = n_bt[bb * Tn + g];
+      s_pre[bb] = run;
+      s_nb[bb] = n;
+      run += n;
+    }
+    s_tot = run;
+    if (blockIdx.y == 0) counts[g] = (double)run;
+  }
+  __syncthreads();
+  const long long tot = s_tot;
+  if (mode == 0 && tot > 0)
+    for (int bb = threadIdx.x; bb < B; bb += blockDim.x) {
+      s_lo[bb] = (int)(((long long)D * s_pre[bb]) / tot);
+      s_hi[bb] = s_nb[bb] > 0 ? (int)(((long long)D * (s_pre[bb] + s_nb[bb]) - 1) / tot) : -2;
+    }
+  __syncthreads();
+  for (int r = blockIdx.y * kFinRows + threadIdx.x; r < D && r < (blockIdx.y + 1) * kFinRows; r += blockDim.x) {
+    double acc = 0.0;
+    if (tot > 0) {
+      if (mode != 0) {
+        for (int bb = 0; bb < B; ++bb) acc += (double)partial[(((int64_t)bb * D + r) * Tn + g) * 2];
+      } else {
+        for (int bb = 0; bb < B; ++bb) {
+          const long long nb = s_nb[bb];
+          if (nb <= 0 || r < s_lo[bb] || r > s_hi[bb] + 1) continue;
           // channels c with r0(c) == r   <=>  r*tot <= D*pre + c*nb < (r+1)*tot
-          const long long off = (long long)D * pre;
+          const long long off = (long long)D * s_pre[bb];
           auto ceil_div = [](long long a, long long d) { return a <= 0 ? 0LL : (a + d - 1) / d; };
           long long c_lo = ceil_div((long long)r * tot - off, nb);
           long long c_hi = ceil_div((long long)(r + 1) * tot - off, nb);
@@ -108,17 +132,16 @@ __global__ void __launch_bounds__(256) proto_finalize_kernel(const float* __rest
           // channels with r0(c) == r - 1 contribute their high part
           if (r > 0) {
             long long d_lo = ceil_div((long long)(r - 1) * tot - off, nb);
-            long long d_hi = ceil_div((long long)r * tot - off, nb);
+            long long d_hi = c_lo;
             if (d_hi > D) d_hi = D;
             for (long long c = d_lo; c < d_hi; ++c)
               acc += (double)partial[(((int64_t)bb * D + c) * Tn + g) * 2 + 1];
           }
         }
-        pre += nb;
       }
     }
+    sums[(int64_t)g * D + r] = acc;
   }
-  sums[idx] = acc;
 }
 
 // proto[g] = (S[g] + cnt[g]*proto[g]) / (cnt[g] + N[g]), cnt[g] += N[g]; separate fp32
@@ -184,7 +207,7 @@ int bacs_proto_accumulate(const void* features, int dtype, int B, int D, int h, 
                           const int32_t* rank, const int32_t* n_bt, int T, int mode, double* sums, double* counts,
                           void* workspace, size_t workspace_bytes, bacs_stream_t stream) {
   BACS_REQUIRE(features && task && rank && n_bt && sums && counts && workspace, "bacs_proto_accumulate: null pointer");
-  BACS_REQUIRE(B > 0 && D > 0 && h > 0 && w > 0 && B < 65536, "bacs_proto_accumulate: bad shape");
+  BACS_REQUIRE(B > 0 && D > 0 && h > 0 && w > 0 && B <= kFinMaxB, "bacs_proto_accumulate: bad shape (B <= 1024)");
   BACS_REQUIRE(T > 0 && T <= 32, "bacs_proto_accumulate: T=%d not in [1,32]", T);
   BACS_REQUIRE(mode == 0 || mode == 1, "bacs_proto_accumulate: mode must be 0 (exact) or 1 (channel)");
   if (workspace_bytes < bacs_proto_workspace_bytes(B, D, T)) {
@@ -206,7 +229,8 @@ int bacs_proto_accumulate(const void* features, int dtype, int B, int D, int h, 
   });
 #undef LAUNCH_ACC
   BACS_CHECK_LAUNCH("bacs_proto_accumulate");
-  proto_finalize_kernel<<<(T * D + 255) / 256, 256, 0, s>>>(partial, B, D, n_bt, T, mode, sums, counts);
+  proto_finalize_kernel<<<dim3(T, (D + kFinRows - 1) / kFinRows), kFinRows, 0, s>>>(partial, B, D, n_bt, T, mode, sums,
+                                                                                   counts);
   BACS_CHECK_LAUNCH("bacs_proto_accumulate(finalize)");
   return BACS_OK;
 }

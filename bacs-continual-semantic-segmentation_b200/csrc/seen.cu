@@ -32,17 +32,29 @@ __global__ void __launch_bounds__(32 * kSeenWarps) seen_logits_kernel(const T* _
     __syncthreads();
     for (int i = tid; i < Tn * cn; i += 32 * kSeenWarps) {
       const int t = i / cn, c = i - t * cn;
-      s_sp[t * chunk + c] = sigmoid_acc(proto[t * D + c0 + c]);
+      s_sp[t * chunk + c] = sigmoid_fast(proto[t * D + c0 + c]);
       s_w[t * chunk + c] = weight[t * D + c0 + c];
     }
     __syncthreads();
-    // warp cg handles channels cg, cg + W, ... of the chunk
-    for (int c = cg; c < cn; c += kSeenWarps) {
-      const float x = live ? DT<T>::to_f(base[(int64_t)(c0 + c) * hw]) : 0.f;
-      const float sx = sigmoid_acc(x);
+    // warp cg handles channels cg, cg + W, ... of the chunk; 8 independent loads in flight per thread
+    constexpr int U = 8;
+    for (int c = cg; c < cn; c += kSeenWarps * U) {
+      float x[U];
 #pragma unroll
-      for (int t = 0; t < TMAX; ++t)
-        if (t < Tn) acc[t] = fmaf(s_w[t * chunk + c], fabsf(sx - s_sp[t * chunk + c]), acc[t]);
+      for (int u = 0; u < U; ++u) {
+        const int cc = c + u * kSeenWarps;
+        x[u] = (live && cc < cn) ? DT<T>::to_f(base[(int64_t)(c0 + cc) * hw]) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int cc = c + u * kSeenWarps;
+        if (cc < cn) {
+          const float sx = sigmoid_fast(x[u]);
+#pragma unroll
+          for (int t = 0; t < TMAX; ++t)
+            if (t < Tn) acc[t] = fmaf(s_w[t * chunk + cc], fabsf(sx - s_sp[t * chunk + cc]), acc[t]);
+        }
+      }
     }
   }
   __syncthreads();
@@ -101,21 +113,34 @@ __global__ void __launch_bounds__(256) seen_head_backward_kernel(const T* __rest
     if (threadIdx.x == 0) dbias[0] = s * scale;
     return;
   }
-  const float sp = sigmoid_acc(proto_t[c]);
+  const float sp = sigmoid_fast(proto_t[c]);
   const float wc = weight_t[c];
   float acc = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const T* row = feat + ((int64_t)b * D + c) * hw;
-    const float* g = gz + (int64_t)b * hw;
-    T* drow = dfeat ? dfeat + ((int64_t)b * D + c) * hw : nullptr;
-    for (int q = threadIdx.x; q < hw; q += blockDim.x) {
-      const float sx = sigmoid_acc(DT<T>::to_f(row[q]));
-      const float d = sx - sp;
-      const float gq = g[q];
-      acc = fmaf(gq, fabsf(d), acc);
-      if (drow) {
-        const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-        drow[q] = DT<T>::from_f(scale * gq * wc * sg * sx * (1.f - sx));
+  constexpr int U = 4;
+  const int total = B * hw;  // element i -> image i / hw, pixel i % hw; rows of one channel are hw apart by D*hw
+  for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * U) {
+    float x[U], gq[U];
+    int64_t off[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * blockDim.x;
+      const int b = i / hw, q = i - b * hw;
+      off[u] = ((int64_t)b * D + c) * hw + q;
+      const bool ok = i < total;
+      x[u] = ok ? DT<T>::to_f(feat[off[u]]) : 0.f;
+      gq[u] = ok ? gz[i] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < total) {
+        const float sx = sigmoid_fast(x[u]);
+        const float d = sx - sp;
+        acc = fmaf(gq[u], fabsf(d), acc);
+        if (dfeat) {
+          const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+          dfeat[off[u]] = DT<T>::from_f(scale * gq[u] * wc * sg * sx * (1.f - sx));
+        }
       }
     }
   }
