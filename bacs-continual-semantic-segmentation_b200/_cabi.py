@@ -53,6 +53,8 @@ _SIGNATURES = {
     "bacs_teacher_distill": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, f32, vp, vp, vp, sz, vp]),
     "bacs_der_workspace_bytes": (sz, [i32, i32, i32]),
     "bacs_der_mse": (i32, [vp, i32, vp, i32, i32, vp, i32, i32, i32, i32, f32, vp, vp, vp, sz, vp]),
+    "bacs_unbiased_kd_workspace_bytes": (sz, [i64]),
+    "bacs_unbiased_kd": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, f32, vp, f32, vp, vp, vp, sz, vp]),
     "bacs_der_cut": (i32, [vp, i32, i32, vp, vp]),
     "bacs_confmat_accumulate": (i32, [vp, i32, vp, i64, i32, vp, vp, vp]),
     "bacs_confmat_metrics": (i32, [vp, i32, vp, vp]),

@@ -121,3 +121,20 @@ class DerMseFunction(torch.autograd.Function):
     def backward(ctx, g):
         dsem, ctx.dsem = ctx.dsem, None
         return _scaled(dsem, g), None, None, None, None, None
+
+
+class UnbiasedKDFunction(torch.autograd.Function):
+    """MiB unbiased KD, -mean(mask * per) (training/loss_utils.py:447-489); gradient to the new logits."""
+
+    @staticmethod
+    def forward(ctx, logits, old_logits, mask, alpha: float):
+        B, _, H, W = logits.shape
+        coef = 1.0 / float(B * H * W)
+        total, dx = ops.unbiased_kd(logits.detach(), old_logits.detach(), mask, alpha, coef, ctx.needs_input_grad[0])
+        ctx.dx = dx
+        return ops.combine_scalars([(total, 0, -coef)], logits.device).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        dx, ctx.dx = ctx.dx, None
+        return _scaled(dx, g), None, None, None

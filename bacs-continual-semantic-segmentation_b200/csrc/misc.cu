@@ -76,6 +76,60 @@ __global__ void __launch_bounds__(256) der_cut_kernel(const int64_t* __restrict_
   }
 }
 
+// -------------------------------------------------------------------------------------
+// MiB unbiased knowledge distillation (training/loss_utils.py:447-489); MiB / SDR only.
+//   per = ( q_0 (lse_{0 u new}(x) - lse(x)) + sum_{c=1}^{Ko-1} q_c (x_c - lse(x)) ) / Ko,  q = softmax(alpha * old)
+//   loss = -mean(mask * per);  d per / d x_k = ( q_0 [k in {0} u new] e^{x_k} / S_B + [1 <= k < Ko] q_k - P_k ) / Ko
+// One thread per pixel; channel planes are read with unit stride across the warp.
+// -------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) unbiased_kd_kernel(const T* __restrict__ x, const T* __restrict__ old, int K,
+                                                          int Ko, int64_t HW, int64_t npix, float alpha,
+                                                          const uint8_t* __restrict__ mask, float grad_coef,
+                                                          T* __restrict__ dx, double* __restrict__ partials) {
+  __shared__ float scratch[32];
+  float acc = 0.f;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = p / HW, q = p - b * HW;
+    const T* xp = x + b * K * HW + q;
+    const T* op = old + b * Ko * HW + q;
+    float mx = -INFINITY, mo = -INFINITY;
+    for (int c = 0; c < K; ++c) mx = fmaxf(mx, DT<T>::to_f(xp[(int64_t)c * HW]));
+    for (int c = 0; c < Ko; ++c) mo = fmaxf(mo, alpha * DT<T>::to_f(op[(int64_t)c * HW]));
+    float S = 0.f, SB = 0.f, So = 0.f;
+    for (int c = 0; c < K; ++c) {
+      const float e = __expf(DT<T>::to_f(xp[(int64_t)c * HW]) - mx);
+      S += e;
+      if (c == 0 || c >= Ko) SB += e;
+    }
+    for (int c = 0; c < Ko; ++c) So += __expf(alpha * DT<T>::to_f(op[(int64_t)c * HW]) - mo);
+    const float den = mx + __logf(S);
+    const float inv_So = 1.f / So;
+    const float q0 = __expf(alpha * DT<T>::to_f(op[0]) - mo) * inv_So;
+    float per = q0 * (mx + __logf(SB) - den);
+    for (int c = 1; c < Ko; ++c) {
+      const float qc = __expf(alpha * DT<T>::to_f(op[(int64_t)c * HW]) - mo) * inv_So;
+      per = fmaf(qc, DT<T>::to_f(xp[(int64_t)c * HW]) - den, per);
+    }
+    const float m = mask ? (mask[p] ? 1.f : 0.f) : 1.f;
+    acc += m * per / (float)Ko;
+    if (dx) {
+      T* dp = dx + b * K * HW + q;
+      const float g = -grad_coef * m / (float)Ko;
+      const float inv_S = 1.f / S, inv_SB = 1.f / SB;
+      for (int c = 0; c < K; ++c) {
+        const float e = __expf(DT<T>::to_f(xp[(int64_t)c * HW]) - mx);
+        float d = -e * inv_S;
+        if (c == 0 || c >= Ko) d += q0 * e * inv_SB;
+        else d += __expf(alpha * DT<T>::to_f(op[(int64_t)c * HW]) - mo) * inv_So;
+        dp[(int64_t)c * HW] = DT<T>::from_f(g * d);
+      }
+    }
+  }
+  const float r = block_sum(acc, scratch);
+  if (threadIdx.x == 0) partials[blockIdx.x] = (double)r;
+}
+
 static int der_blocks(int64_t total) {
   int64_t b = (total + 256 * 4 - 1) / (256 * 4);
   const int64_t cap = (int64_t)sm_count() * 4;
@@ -280,6 +334,34 @@ int bacs_der_mse(const void* sem_logits, int dtype, const void* memory_logits, i
   BACS_CHECK_LAUNCH("bacs_der_mse");
   sum_partials2_kernel<<<1, 1024, 0, s>>>(partials, blocks, loss_sum);
   BACS_CHECK_LAUNCH("bacs_der_mse(reduce)");
+  return BACS_OK;
+}
+
+size_t bacs_unbiased_kd_workspace_bytes(int64_t npix) {
+  return align_up(sizeof(double) * (size_t)der_blocks(npix * 4), 256);
+}
+
+int bacs_unbiased_kd(const void* logits, const void* old_logits, int dtype, int B, int K, int K_old, int H, int W,
+                     float alpha, const uint8_t* mask, float grad_coef, double* loss_sum, void* dlogits,
+                     void* workspace, size_t workspace_bytes, bacs_stream_t stream) {
+  BACS_REQUIRE(logits && old_logits && loss_sum && workspace, "bacs_unbiased_kd: null pointer");
+  BACS_REQUIRE(B > 0 && K > 0 && K_old > 0 && K_old <= K && H > 0 && W > 0, "bacs_unbiased_kd: bad shape");
+  const int64_t HW = (int64_t)H * W, npix = HW * B;
+  const int blocks = der_blocks(npix * 4);
+  if (workspace_bytes < sizeof(double) * (size_t)blocks) {
+    set_error("bacs_unbiased_kd: workspace too small");
+    return BACS_ERR_WORKSPACE;
+  }
+  double* partials = reinterpret_cast<double*>(workspace);
+  cudaStream_t s = (cudaStream_t)stream;
+  BACS_DISPATCH_DTYPE(dtype, TT, {
+    unbiased_kd_kernel<TT><<<blocks, 256, 0, s>>>(reinterpret_cast<const TT*>(logits),
+                                                  reinterpret_cast<const TT*>(old_logits), K, K_old, HW, npix, alpha,
+                                                  mask, grad_coef, reinterpret_cast<TT*>(dlogits), partials);
+  });
+  BACS_CHECK_LAUNCH("bacs_unbiased_kd");
+  sum_partials2_kernel<<<1, 1024, 0, s>>>(partials, blocks, loss_sum);
+  BACS_CHECK_LAUNCH("bacs_unbiased_kd(reduce)");
   return BACS_OK;
 }
 

@@ -317,6 +317,25 @@ def der_mse(sem_logits: torch.Tensor, memory_logits: torch.Tensor, cut: torch.Te
     return loss_sum, dsem
 
 
+def unbiased_kd(logits: torch.Tensor, old_logits: torch.Tensor, mask: Optional[torch.Tensor], alpha: float,
+                grad_coef: float, want_grad: bool):
+    logits = _cuda(logits, "unbiased_kd")
+    old_logits = _cuda(old_logits.to(logits.dtype), "unbiased_kd")
+    B, K, H, W = logits.shape
+    Ko = old_logits.shape[1]
+    if mask is not None:
+        mask = _cuda(mask.to(torch.uint8), "unbiased_kd", torch.uint8)
+    dev = logits.device
+    loss_sum = torch.empty(1, dtype=torch.float64, device=dev)
+    dx = torch.empty_like(logits) if want_grad else None
+    lib = _lib()
+    ws = _ws(lib.bacs_unbiased_kd_workspace_bytes(B * H * W), dev)
+    check(lib.bacs_unbiased_kd(logits.data_ptr(), old_logits.data_ptr(), _dt(logits), B, K, Ko, H, W, float(alpha),
+                               _ptr(mask), float(grad_coef), loss_sum.data_ptr(), _ptr(dx), ws.data_ptr(), ws.numel(),
+                               _stream()), "bacs_unbiased_kd")
+    return loss_sum, dx
+
+
 # --------------------------------------------------------------------------------------
 # confusion matrix
 # --------------------------------------------------------------------------------------

@@ -241,6 +241,19 @@ size_t bacs_der_workspace_bytes(int Br, int K, int hw);
 int bacs_der_cut(const int64_t* n_classes, int Br, int K, int32_t* cut, bacs_stream_t stream);
 
 /* ---------------------------------------------------------------------------------
+ * MiB unbiased knowledge distillation (training/loss_utils.py:447-489).  Instantiated on every
+ * loss object (base_loss.py:78) but called only by the MiB / SDR losses.
+ *   logits [B,K,H,W], old_logits [B,K_old,H,W] (same dtype), mask u8[B,H,W] or NULL.
+ *   loss_sum fp64[1] OVERWRITTEN with sum_p mask * per_p (caller: loss = -loss_sum / (B*H*W));
+ *   dlogits (dtype) OVERWRITTEN with grad_coef * d(-sum)/dlogits, or NULL.
+ * --------------------------------------------------------------------------------- */
+size_t bacs_unbiased_kd_workspace_bytes(int64_t npix);
+int bacs_unbiased_kd(const void* logits, const void* old_logits, int dtype, int B, int K, int K_old,
+                     int H, int W, float alpha, const uint8_t* mask, float grad_coef,
+                     double* loss_sum, void* dlogits, void* workspace, size_t workspace_bytes,
+                     bacs_stream_t stream);
+
+/* ---------------------------------------------------------------------------------
  * Confusion matrix (training/metrics.py:38-88 over torchmetrics 0.6.0 ConfusionMatrix)
  * --------------------------------------------------------------------------------- */
 /* confmat[t*K + p] += 1 for pixels with 0 <= t < K (rows = target).  preds are int64

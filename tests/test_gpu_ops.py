@@ -369,6 +369,24 @@ def test_der_mse(ops, ncls, ignore_bg):
         close(ds, 0.8 * sr.grad, atol=1e-6 * float(sr.grad.abs().max()), what="dsem")
 
 
+def test_unbiased_kd_module(synth):
+    from bacs_b200.training.loss_utils import UnbiasedKnowledgeDistillationLoss
+    cfg = synth.CONFIGS["small"]
+    inp = synth.make_step_inputs(cfg, seed=4)
+    g = torch.Generator().manual_seed(2)
+    old = torch.randn(cfg.B, cfg.old_cl, cfg.H, cfg.W, generator=g)
+    for alpha, use_mask in ((1.0, False), (0.5, True)):
+        pm = (inp.mask == 0) if use_mask else None
+        x = inp.logits.clone().requires_grad_(True)
+        want = O.unbiased_kd(x, old, alpha=alpha, mask=pm)
+        want.backward()
+        xg = inp.logits.clone().cuda().requires_grad_(True)
+        got = UnbiasedKnowledgeDistillationLoss(alpha=alpha)(xg, old.cuda(), None if pm is None else pm.cuda())
+        got.backward()
+        close(got, want, what="ukd")
+        close(xg.grad, x.grad, atol=1e-5 * float(x.grad.abs().max()), what="ukd grad")
+
+
 # --------------------------------------------------------------------------------------
 # confusion matrix
 # --------------------------------------------------------------------------------------
@@ -424,3 +442,23 @@ def test_pack_unpack_and_scale(ops):
     a = torch.tensor([2.0, 8.0], dtype=torch.float64).cuda()
     r = ops.combine_scalars([(a, 0, 3.0), (a, 1, 1.0, a, 0)], a.device)
     assert math.isclose(float(r), 2 * 3 + 8 / 2)
+
+
+def test_transform_label_class(ops):
+    """labels.TransformLabel (reference constructor) incl. the background-shift map builder."""
+    from bacs_b200 import labels as L
+    class_order = [5, 3, 8, 1, 2, 9, 4, 7, 6]                     # shuffled order: aliasing chains (Q13)
+    id2train = {i: i for i in range(10)}
+    id2train[255] = 255
+    rng = np.random.RandomState(1)
+    lbl = rng.randint(0, 10, size=(4, 40, 56)).astype(np.int64)
+    lbl[:, :3] = 255
+    for train, test_bg, tasks in ((True, True, [8, 1]), (False, True, [5, 3, 8, 1]), (False, False, [5, 3])):
+        inv, masking = L.build_inverted_order(class_order, tasks, train, test_bg)
+        winv, wmask = O.build_inverted_order(class_order, tasks, train, test_bg)
+        assert inv == winv and masking == wmask
+        want = np.stack([O.transform_label(lbl[i], id2train, 255, inv, masking) for i in range(lbl.shape[0])])
+        tl = L.TransformLabel(id2train, 255, inv, masking)
+        got = tl(torch.from_numpy(lbl).cuda()).cpu().numpy()
+        assert np.array_equal(got, want)
+        assert np.array_equal(tl(torch.from_numpy(lbl[0]).cuda()).cpu().numpy(), want[0])

@@ -108,9 +108,9 @@ def test_step_is_free_of_host_sync():
         loss.backward()
         return loss, preds
 
-    # eager reference first (default stream), then a side-stream warm-up, then the capture
-    eager_loss, eager_preds = step()
-    eager_grad = leaves["logits"].grad.clone()
+    # PyTorch's capture recipe: warm up on a side stream, capture, replay -- and only then run
+    # the eager reference on the default stream (an eager backward on the default stream before
+    # the capture ties the leaves' AccumulateGrad nodes to it and invalidates the capture)
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
@@ -124,6 +124,11 @@ def test_step_is_free_of_host_sync():
     loss_fn._prototypes._count_features.copy_(counts0)
     g.replay()
     torch.cuda.synchronize()
-    assert float(gl) == float(eager_loss)
-    assert torch.equal(gp, eager_preds)
-    assert torch.equal(leaves["logits"].grad, eager_grad)
+    graph_loss, graph_preds, graph_grad = float(gl), gp.clone(), leaves["logits"].grad.clone()
+    loss_fn._prototypes._prototypes_tensors.copy_(protos0)
+    loss_fn._prototypes._count_features.copy_(counts0)
+    eager_loss, eager_preds = step()
+    eager_grad = leaves["logits"].grad.clone()
+    assert graph_loss == float(eager_loss)
+    assert torch.equal(graph_preds, eager_preds)
+    assert torch.equal(graph_grad, eager_grad)
