@@ -1,6 +1,8 @@
 // Shared pieces of the fused per-pixel kernels: parameters, PTX wrappers (mbarrier + 1-D TMA
 // bulk copies), vector access helpers and the per-pixel loss / gradient-coefficient stage.
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 
 namespace bacs {
@@ -9,7 +11,11 @@ constexpr int kConsumerWarps = 8;
 constexpr int kConsumers = 32 * kConsumerWarps;
 constexpr int kMaxStages = 4;
 
-struct PixelParams {
+struct alignas(64) PixelParams {
+  CUtensorMap tmap_in;   // logits   as a 3-D tensor (H*W, K, B), box (256, K, 1)  -- fast path only
+  CUtensorMap tmap_out;  // dlogits, same geometry
+  CUtensorMap tmap_z;    // seen logits as (w, h, T, B), box (w, 2, T, 1): both source rows of every head
+  int use_tmap;
   bacs_pixel_args a;
   int P;                // pixels per tile
   int tiles_per_image;
@@ -55,6 +61,39 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
                "r"(bytes)
                : "memory");
+}
+// 3-D tiled TMA (tensor map in kernel-parameter space): whole [K][256] boxes per instruction
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, const void* src_smem) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_u32(src_smem)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

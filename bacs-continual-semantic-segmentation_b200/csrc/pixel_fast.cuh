@@ -2,11 +2,13 @@
 // 16-byte aligned rows).  Included by one translation unit per storage type.
 //
 // Persistent CTAs of 8 warps; every thread owns 2 adjacent pixels of a 512-pixel tile.
-// Thread 0 drives a 3-stage TMA ring (1-D bulk copies, mbarrier completion): while tile k
-// is computed, tile k+1 has landed or is landing, and the stage of tile k-1 is being
-// written back by a bulk store and then refilled with tile k+2.  The K logits of both
-// pixels live in registers from the first shared-memory read to the gradient write, so
-// each logit costs one exp and the tile is read from shared memory exactly once.
+// A 4-stage TMA ring moves the tiles: one elected lane issues, per tile, two 3-D tiled TMA
+// loads (tensor map (H*W, K, B), box 256 x K x 1: all K logit rows of 256 pixels in ONE
+// instruction), one bulk copy of the tile's 4 KB label strip, and two tiled TMA stores of the
+// gradient.  While tile k is computed, tile k+1 has landed, tile k+2 is landing into the
+// stage of tile k-2 and tile k-1 is being written back, so the issuing lane never blocks and
+// there is no CTA-wide barrier in the tile loop.  The K logits of both pixels live in
+// registers from the single shared-memory read to the gradient write (one exp per logit).
 #pragma once
 #include "pixel_common.cuh"
 
@@ -103,20 +105,24 @@ __device__ __forceinline__ void fast_sync() { __syncthreads(); }
 constexpr int kZCols = 8;          // low-res columns a warp's 64 pixels can touch (x16 up-sampling: <= 6)
 constexpr int kLabelBytes = kFastP * 8;
 
-// Shared memory (dynamic): 3 stages of { [KREG][512] logits (rows K..KREG-1 hold -inf forever),
-// 512 int64 labels } followed by one warp-private [T][kZCols] seen-logit strip per warp.
+// Shared memory (dynamic): 4 stages of { [2][KREG][256] logits -- two TMA boxes of 256 pixels; rows
+// K..KREG-1 of each box hold -inf forever --, 512 int64 labels } followed by one warp-private
+// [T][kZCols] seen-logit strip per warp.
+constexpr int kBox = 256;
 template <typename T, int KREG, bool ROWTILE>
-__global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const PixelParams p) {
+__global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const __grid_constant__ PixelParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t bar_full[3];
-  __shared__ uint64_t bar_done[3];
+  __shared__ uint64_t bar_full[4];
+  __shared__ uint64_t bar_done[4];
   __shared__ float red_scratch[8][BACS_NACC];
   __shared__ float s_norm_sh;
 
-  constexpr int P = kFastP, S = 3;
+  constexpr int P = kFastP, S = 4;
   constexpr size_t tile_elems = (size_t)KREG * P;
-  constexpr size_t stage_bytes = tile_elems * sizeof(T) + kLabelBytes;
   const bacs_pixel_args& a = p.a;
+  // per stage: logits | labels | (row tiles) the two source rows of every seen head, [T][2][w] fp32
+  const uint32_t zrow_bytes = (ROWTILE && a.z) ? (uint32_t)(a.T * 2 * a.w * sizeof(float)) : 0u;
+  const size_t stage_bytes = tile_elems * sizeof(T) + kLabelBytes + ((zrow_bytes + 127u) & ~127u);
   const int K = a.K;
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
@@ -124,6 +130,9 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
   auto stage_tile = [&](int s) { return reinterpret_cast<T*>(smem_raw + (size_t)s * stage_bytes); };
   auto stage_labels = [&](int s) {
     return reinterpret_cast<const int64_t*>(smem_raw + (size_t)s * stage_bytes + tile_elems * sizeof(T));
+  };
+  auto stage_zrows = [&](int s) {
+    return reinterpret_cast<float*>(smem_raw + (size_t)s * stage_bytes + tile_elems * sizeof(T) + kLabelBytes);
   };
   float* zrw = reinterpret_cast<float*>(smem_raw + S * stage_bytes) + (size_t)wid * a.T * kZCols;
   const int grid = (int)gridDim.x;
@@ -133,16 +142,16 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_done[s], kFastThreads);
+      mbar_init(&bar_full[s], 1);             // the issuing lane's expect-tx arrival
+      mbar_init(&bar_done[s], kFastThreads);  // every thread, after its gradient rows are written
     }
     fence_mbar_init();
     s_norm_sh = 0.f;
   }
   // padding rows stay -inf: exp -> 0, never the arg-max, never stored
-  for (int i = tid; i < S * (KREG - K) * P; i += kFastThreads) {
-    const int s = i / ((KREG - K) * P), r = i - s * (KREG - K) * P;
-    Raw<T>::fill(stage_tile(s) + (size_t)K * P + r, -INFINITY);
+  for (int i = tid; i < S * 2 * (KREG - K) * kBox; i += kFastThreads) {
+    const int sb2 = i / ((KREG - K) * kBox), r = i - sb2 * (KREG - K) * kBox;  // sb2 = stage*2 + box
+    Raw<T>::fill(stage_tile(sb2 >> 1) + (size_t)(sb2 & 1) * KREG * kBox + (size_t)K * kBox + r, -INFINITY);
   }
   __syncthreads();
   if (tid < 32 && a.mode != BACS_PIX_WEIGHTED_CE && a.dlogits != nullptr) {
@@ -166,18 +175,60 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
       ++b;
     }
   };
-  // warp 0 is also the TMA producer: lane c moves logit row c, lane 31 the label strip
+  // one elected lane of warp 0 issues all TMA traffic of the CTA (5 instructions per tile)
+  const uint32_t tile_bytes = (uint32_t)K * row_bytes + kLabelBytes + zrow_bytes;
+  const int tiles_per_row = ROWTILE ? a.W / P : 1;
+  const int tpr_shift = (tiles_per_row & (tiles_per_row - 1)) == 0 ? __ffs(tiles_per_row) - 1 : -1;
+  auto row_of_tile = [&](int t) { return tpr_shift >= 0 ? (t >> tpr_shift) : t / tiles_per_row; };
   auto issue_load = [&](int b, int t, int s) {
-    const T* src = reinterpret_cast<const T*>(a.logits) + (int64_t)b * K * HW + (int64_t)t * P;
-    if (lane == 0) mbar_expect_tx(&bar_full[s], (uint32_t)K * row_bytes + kLabelBytes);
-    __syncwarp();
-    if (lane < K) bulk_g2s(stage_tile(s) + (size_t)lane * P, src + (int64_t)lane * HW, row_bytes, &bar_full[s]);
-    if (lane == 31)
-      bulk_g2s(const_cast<int64_t*>(stage_labels(s)), a.labels + (int64_t)b * HW + (int64_t)t * P, kLabelBytes,
-               &bar_full[s]);
+    mbar_expect_tx(&bar_full[s], tile_bytes);
+    T* dst = stage_tile(s);
+    if (ROWTILE && a.z) {  // rows i0, i0+1 of all T heads for the image row this tile lies in
+      const Lerp ly = lerp_align_corners(row_of_tile(t), a.h, p.sy);
+      if (p.use_tmap) {
+        tma_load_4d(stage_zrows(s), &p.tmap_z, 0, ly.i0, 0, b, &bar_full[s]);
+      } else {
+        const float* zb = a.z + (int64_t)b * a.T * a.h * a.w;
+        for (int h2 = 0; h2 < a.T; ++h2) {
+          bulk_g2s(stage_zrows(s) + (size_t)(2 * h2) * a.w, zb + ((int64_t)h2 * a.h + ly.i0) * a.w,
+                   (uint32_t)(a.w * sizeof(float)), &bar_full[s]);
+          bulk_g2s(stage_zrows(s) + (size_t)(2 * h2 + 1) * a.w, zb + ((int64_t)h2 * a.h + ly.i1) * a.w,
+                   (uint32_t)(a.w * sizeof(float)), &bar_full[s]);
+        }
+      }
+    }
+    if (p.use_tmap) {
+      tma_load_3d(dst, &p.tmap_in, t * P, 0, b, &bar_full[s]);
+      tma_load_3d(dst + (size_t)KREG * kBox, &p.tmap_in, t * P + kBox, 0, b, &bar_full[s]);
+    } else {  // driver without tensor-map support: 2K one-dimensional bulk copies
+      const T* src = reinterpret_cast<const T*>(a.logits) + (int64_t)b * K * HW + (int64_t)t * P;
+      for (int c = 0; c < K; ++c) {
+        bulk_g2s(dst + (size_t)c * kBox, src + (int64_t)c * HW, row_bytes / 2, &bar_full[s]);
+        bulk_g2s(dst + (size_t)(KREG + c) * kBox, src + (int64_t)c * HW + kBox, row_bytes / 2, &bar_full[s]);
+      }
+    }
+    bulk_g2s(const_cast<int64_t*>(stage_labels(s)), a.labels + (int64_t)b * HW + (int64_t)t * P, kLabelBytes,
+             &bar_full[s]);
   };
-  int pb = tb, pt = tt;  // producer cursor (tile k + 2)
-  if (wid == 0) {
+  auto issue_store = [&](int b, int t, int s) {
+    const T* src = stage_tile(s);
+    if (p.use_tmap) {
+      tma_store_3d(&p.tmap_out, t * P, 0, b, src);
+      tma_store_3d(&p.tmap_out, t * P + kBox, 0, b, src + (size_t)KREG * kBox);
+    } else {
+      T* dst = reinterpret_cast<T*>(a.dlogits) + (int64_t)b * K * HW + (int64_t)t * P;
+      for (int c = 0; c < K; ++c) {
+        bulk_s2g(dst + (int64_t)c * HW, src + (size_t)c * kBox, row_bytes / 2);
+        bulk_s2g(dst + (int64_t)c * HW + kBox, src + (size_t)(KREG + c) * kBox, row_bytes / 2);
+      }
+    }
+    bulk_commit();
+  };
+  int pb = tb, pt = tt;  // load cursor (tile k + 2)
+  int sb = tb, st = tt;  // store cursor (tile k - 1)
+  bool issuer = false;   // the elected lane of warp 0 (the same lane every time: bulk groups are per thread)
+  if (wid == 0) issuer = elect_one();
+  if (issuer) {
     for (int k = 0; k < 2 && k < my_tiles; ++k) {
       issue_load(pb, pt, k);
       advance(pb, pt);
@@ -191,7 +242,9 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
   float acc[BACS_NACC];
 #pragma unroll
   for (int i = 0; i < BACS_NACC; ++i) acc[i] = 0.f;
-  const int tiles_per_row = ROWTILE ? a.W / P : 1;
+  // x-interpolation of this thread's two pixels; constant over tiles when a tile is a whole row
+  Lerp lxj[2] = {{0, 0, 0.f}, {0, 0, 0.f}};
+  int c_first = 0;
 
   for (int k = 0; k < my_tiles; ++k) {
     const int b = tb, t_in = tt;
@@ -201,29 +254,32 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
     T* tile = stage_tile(s);
     const int64_t p0 = (int64_t)t_in * P;
 
+    // ---- wait for the tile (logit rows + labels + seen-head rows) -------------------------------
+    mbar_wait(&bar_full[s], parity);
+    const longlong2 lab = *reinterpret_cast<const longlong2*>(stage_labels(s) + px0);
+
     // ---- seen logits of this warp's 64 pixels: y-interpolated strip in warp-private smem ------
     Lerp ly_row = {0, 0, 0.f};
-    int Xw = 0, c_first = 0;
     if (ROWTILE && a.z) {
-      const int Yrow = t_in / tiles_per_row;  // tiles_per_row is 1 for the 512-wide crops
-      Xw = (t_in - Yrow * tiles_per_row) * P + wid * 64;
+      const int Yrow = row_of_tile(t_in);
       ly_row = lerp_align_corners(Yrow, a.h, p.sy);
-      c_first = lerp_align_corners(Xw, a.w, p.sx).i0;
-      const float* zb = a.z + (int64_t)b * a.T * a.h * a.w;
+      if (k == 0 || tiles_per_row != 1) {
+        const int Xw = (t_in - Yrow * tiles_per_row) * P + wid * 64;
+        c_first = lerp_align_corners(Xw, a.w, p.sx).i0;
+        lxj[0] = lerp_align_corners(Xw + 2 * lane, a.w, p.sx);
+        lxj[1] = lerp_align_corners(Xw + 2 * lane + 1, a.w, p.sx);
+      }
+      const float* zs = stage_zrows(s);
       const float wy0 = 1.f - ly_row.w1;
       const int col = min(c_first + (lane & (kZCols - 1)), a.w - 1);
+      const int r1 = (ly_row.i1 - ly_row.i0) * a.w;  // 0 on the last source row (the second TMA row is padding)
       __syncwarp();
       for (int t = lane / kZCols; t < a.T; t += 32 / kZCols) {
-        const float* zt = zb + (int64_t)t * a.h * a.w;
-        zrw[t * kZCols + (lane & (kZCols - 1))] =
-            __fadd_rn(__fmul_rn(wy0, __ldg(zt + ly_row.i0 * a.w + col)), __fmul_rn(ly_row.w1, __ldg(zt + ly_row.i1 * a.w + col)));
+        const float* zt = zs + (size_t)t * 2 * a.w + col;
+        zrw[t * kZCols + (lane & (kZCols - 1))] = __fadd_rn(__fmul_rn(wy0, zt[0]), __fmul_rn(ly_row.w1, zt[r1]));
       }
       __syncwarp();
     }
-
-    // ---- wait for the tile (logit rows + labels) ------------------------------------------------
-    mbar_wait(&bar_full[s], parity);
-    const longlong2 lab = *reinterpret_cast<const longlong2*>(stage_labels(s) + px0);
 
     int y[2];
     bool is_ign[2];
@@ -250,10 +306,10 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
       if (a.z) {
         float zmax = -INFINITY;
         if (ROWTILE) {
-          const Lerp lx = lerp_align_corners(Xw + 2 * lane + j, a.w, p.sx);
+          const Lerp lx = lxj[j];
           const float wx0 = 1.f - lx.w1;
-          const int dx = lx.i1 - lx.i0;
           const float* z0 = zrw + (lx.i0 - c_first);
+          const int dx = lx.i1 - lx.i0;
           for (int t = 0; t < a.T; ++t) {
             const float v = __fadd_rn(__fmul_rn(wx0, z0[t * kZCols]), __fmul_rn(lx.w1, z0[t * kZCols + dx]));
             zmax = fmaxf(zmax, v);
@@ -284,18 +340,19 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
           wy1g[j] = ly.w1;
           wx1[j] = lx.w1;
         }
-        if (!a.seen_max) seen[j] = sigmoid_acc(zmax);
+        if (!a.seen_max) seen[j] = sigmoid_fast(zmax);
       }
     }
 
     // ---- registers <- shared memory; max / arg-max on the packed pair ------------------------------
-    T* col = tile + px0;
+    // pixel pair 2*tid lives in box tid/128 at column (2*tid) % 256; channel rows are kBox apart
+    T* col = tile + (size_t)(tid >> 7) * KREG * kBox + ((2 * tid) & (kBox - 1));
     float xy[2];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) xy[j] = (y[j] >= 0) ? DT<T>::to_f(col[(size_t)y[j] * P + j]) : 0.f;
+    for (int j = 0; j < 2; ++j) xy[j] = (y[j] >= 0) ? DT<T>::to_f(col[(size_t)y[j] * kBox + j]) : 0.f;
     typename Raw<T>::reg_t raw[KREG];
 #pragma unroll
-    for (int c = 0; c < KREG; ++c) raw[c] = Raw<T>::ld(col + (size_t)c * P);
+    for (int c = 0; c < KREG; ++c) raw[c] = Raw<T>::ld(col + (size_t)c * kBox);
     typename Raw<T>::Max mt = Raw<T>::init(raw[0]);
 #pragma unroll
     for (int c = 1; c < KREG; ++c) Raw<T>::update(mt, raw[c], c);
@@ -355,7 +412,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
         const bool oldc = c < old_cl;
         const float g0 = e0[c] * (oldc ? pc[0].cg1 : pc[0].cg2);
         const float g1 = e1[c] * (oldc ? pc[1].cg1 : pc[1].cg2);
-        if (c < K) Raw<T>::st(col + (size_t)c * P, g0, g1);
+        if (c < K) Raw<T>::st(col + (size_t)c * kBox, g0, g1);
       }
       // the label's own channel: recomputed in fp32 so that -dy is applied before rounding
 #pragma unroll
@@ -364,29 +421,32 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
           const int kk = y[j];
           const float cgk = kk == 0 ? pc[j].cg0 : (kk < old_cl ? pc[j].cg1 : pc[j].cg2);
           const float ey = ex2_fast(fmaf(xy[j], kLog2e, j == 0 ? nm0 : nm1));
-          col[(size_t)kk * P + j] = DT<T>::from_f(ey * cgk - pc[j].dy - (kk == 0 ? pc[j].d0 : 0.f));
+          col[(size_t)kk * kBox + j] = DT<T>::from_f(ey * cgk - pc[j].dy - (kk == 0 ? pc[j].d0 : 0.f));
         }
       }
       fence_proxy_async();
     }
     mbar_arrive(&bar_done[s]);
 
-    // ---- warp 0: write tile k back, refill the stage of tile k-1 with tile k+2 ---------------------
-    if (wid == 0) {
-      mbar_wait(&bar_done[s], parity);
-      if (a.dlogits) {
-        T* dst = reinterpret_cast<T*>(a.dlogits) + (int64_t)b * K * HW + p0;
-        if (lane < K) bulk_s2g(dst + (int64_t)lane * HW, tile + (size_t)lane * P, row_bytes);
-        bulk_commit();
-        // this lane's store of tile k-1 (issued one tile ago) must have finished reading its stage
-        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    // ---- issuing lane: write tile k-1 back, refill the stage of tile k-2 with tile k+2 (both
+    //      conditions were met a whole tile ago, so nothing here blocks) ---------------------------------
+    if (issuer) {
+      if (k >= 1) {
+        // every thread has written its gradients of tile k-1 (and finished reading tile k-2)
+        mbar_wait(&bar_done[(k - 1) % S], (uint32_t)(((k - 1) / S) & 1));
+        if (a.dlogits) {
+          issue_store(sb, st, (k - 1) % S);
+          advance(sb, st);
+          // the store of tile k-2 (issued one tile ago) has finished reading its stage
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
       }
-      __syncwarp();
       if (k + 2 < my_tiles) {
         issue_load(pb, pt, (k + 2) % S);
         advance(pb, pt);
       }
     }
+    __syncwarp();
 
     // ---- arg-max / mask stores -------------------------------------------------------------------------
     if (a.preds)
@@ -490,7 +550,12 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const Pixel
       fast_sync();
     }
   }
-  if (wid == 0) bulk_wait_all();
+  if (issuer && my_tiles > 0) {  // the last tile's gradient rows
+    const int kl = my_tiles - 1;
+    mbar_wait(&bar_done[kl % S], (uint32_t)((kl / S) & 1));
+    if (a.dlogits) issue_store(sb, st, kl % S);
+    bulk_wait_all();
+  }
 
   if (a.mode != BACS_PIX_SCORE) {
 #pragma unroll

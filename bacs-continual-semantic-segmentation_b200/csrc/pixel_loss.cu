@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kConsumers + 32, (KREG > 0 ? 2 : 1)) pixel_los
             wy1g[j] = ly.w1;
             wx1[j] = lx.w1;
           }
-          if (!a.seen_max) seen[j] = sigmoid_acc(zmax);
+          if (!a.seen_max) seen[j] = sigmoid_fast(zmax);
         }
       }
     }
@@ -568,6 +568,55 @@ __global__ void __launch_bounds__(256) pixel_reduce_kernel(const double* __restr
   }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// [B,K,H,W] as the 3-D tensor (H*W, K, B) with boxes of 256 pixels x K channels x 1 image
+static bool make_tile_map(CUtensorMap* map, const void* base, int dtype, int B, int K, int64_t HW) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || K > 256) return false;
+  const size_t es = dtype_size(dtype);
+  const CUtensorMapDataType dt = dtype == BACS_F32    ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : dtype == BACS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                      : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)K, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)HW * es, (cuuint64_t)HW * K * es};
+  const cuuint32_t box[3] = {256u, (cuuint32_t)K, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  return fn(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// seen logits [B,T,h,w] as the 4-D tensor (w, h, T, B); one box = rows (i0, i0+1) of every head
+static bool make_z_map(CUtensorMap* map, const float* z, int B, int T, int h, int w) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || w > 256 || T > 256 || (w * 4) % 16 != 0 || (reinterpret_cast<uintptr_t>(z) & 15) != 0) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)T, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)w * 4, (cuuint64_t)h * w * 4, (cuuint64_t)T * h * w * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)w, 2u, (cuuint32_t)T, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(z), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static bool make_plan(const bacs_pixel_args& a, PixelPlan* plan) {
   const size_t es = dtype_size(a.dtype);
   const int64_t HW = (int64_t)a.H * a.W;
@@ -588,20 +637,25 @@ static bool make_plan(const bacs_pixel_args& a, PixelPlan* plan) {
         kreg = kregs[i];
         break;
       }
-    // 3 stages of {kreg logit rows, 512 int64 labels} + one [T][8] seen-logit strip per warp
-    const size_t smem = (size_t)3 * ((size_t)kreg * 512 * es + 4096) + (a.z ? (size_t)8 * a.T * 8 * 4 : 0) + 64;
+    // 4 stages of {kreg logit rows, 512 int64 labels} + one [T][8] seen-logit strip per warp
+    const size_t zrows = a.z ? (((size_t)a.T * 2 * a.w * 4 + 127) & ~(size_t)127) : 0;
+    const size_t smem = (size_t)4 * ((size_t)kreg * 512 * es + 4096 + zrows) + (a.z ? (size_t)8 * a.T * 8 * 4 : 0) + 64;
     if (smem + 1024 <= cap) {
-      const int per_sm = (2 * (smem + 1024) <= cap) ? 2 : 1;
+      // 228 KB of shared memory per SM, 1 KB reserved per resident CTA, < 0.5 KB static
+      const int per_sm = (2 * (smem + 1024 + 512) <= (size_t)228 * 1024) ? 2 : 1;
       const int64_t tiles = HW / 512 * a.B;
       plan->fast = 1;
       plan->ppt = 2;
       plan->P = 512;
       plan->kreg = kreg;
-      plan->stages = 3;
+      plan->stages = 4;
       plan->smem = smem;
       plan->grid = (int)std::min<int64_t>(tiles, (int64_t)sms * per_sm);
       // row tiles: a tile lies inside one image row and 64 pixels touch <= 6 low-res columns
-      plan->rowtile = (a.z != nullptr && a.W % 512 == 0 && a.seen_scale >= 16) ? 1 : 0;
+      plan->rowtile = (a.z != nullptr && a.W % 512 == 0 && a.seen_scale >= 16 && a.w % 4 == 0 &&
+                       (reinterpret_cast<uintptr_t>(a.z) & 15) == 0)
+                          ? 1
+                          : 0;
       return true;
     }
   }
@@ -694,6 +748,13 @@ int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_
   p.sy = a->z ? ac_scale(a->h, a->H) : 0.f;
   p.sx = a->z ? ac_scale(a->w, a->W) : 0.f;
   p.partials = reinterpret_cast<double*>(workspace);
+  p.use_tmap = 0;
+  if (plan.fast) {
+    const bool ok_in = make_tile_map(&p.tmap_in, a->logits, a->dtype, a->B, a->K, HW);
+    const bool ok_out = !a->dlogits || make_tile_map(&p.tmap_out, a->dlogits, a->dtype, a->B, a->K, HW);
+    const bool ok_z = !(plan.rowtile && a->z) || make_z_map(&p.tmap_z, a->z, a->B, a->T, a->h, a->w);
+    p.use_tmap = (ok_in && ok_out && ok_z) ? 1 : 0;
+  }
   p.use_bulk = (((HW * es) % 16 == 0) && ((reinterpret_cast<uintptr_t>(a->logits) & 15) == 0) &&
                 (!a->dlogits || (reinterpret_cast<uintptr_t>(a->dlogits) & 15) == 0))
                    ? 1
