@@ -32,6 +32,7 @@ class PixelLossFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, logits, features, head_weight, head_bias, labels, cfg: dict):
+        ctx.set_materialize_grads(False)     # no zero-filled "gradients" for the int64 preds / uint8 mask outputs
         mode = cfg["mode"]
         z = cfg.get("z")
         focal_head = cfg.get("focal_head", -1)
@@ -77,6 +78,8 @@ class PixelLossFunction(torch.autograd.Function):
     def backward(ctx, g, _gp, _gm):
         dlogits, dfeat, dweight, dbias = ctx.grads
         ctx.grads = None
+        if g is None:
+            return None, None, None, None, None, None
         wshape, bshape, wdtype = ctx.shapes
         dlogits = _scaled(dlogits, g)
         dfeat = _scaled(dfeat, g)

@@ -63,16 +63,28 @@ __global__ void __launch_bounds__(256) distill_moments_kernel(const uint8_t* __r
   const int x0 = colstart[j], x1 = colstart[j + 1];
   float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f;
   const uint8_t* mrow = mask ? mask + row * W : nullptr;
-  for (int X = x0; X < x1; ++X) {
-    if (mrow == nullptr || mrow[X]) {
-      const float t = xwt[X] - 0.5f;
-      const float t2 = t * t;
-      m0 += 1.f;
-      m1 += t;
-      m2 += t2;
-      m3 += t2 * t;
-      m4 += t2 * t2;
+  auto add = [&](int X) {
+    const float t = xwt[X] - 0.5f;
+    const float t2 = t * t;
+    m0 += 1.f;
+    m1 += t;
+    m2 += t2;
+    m3 += t2 * t;
+    m4 += t2 * t2;
+  };
+  if (mrow && ((reinterpret_cast<uintptr_t>(mrow + x0) & 7) == 0) && ((x1 - x0) & 7) == 0) {
+    for (int X = x0; X < x1; X += 8) {  // 8 mask bytes per load
+      const uint2 v = *reinterpret_cast<const uint2*>(mrow + X);
+      if ((v.x | v.y) == 0) continue;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if ((v.x >> (8 * k)) & 0xffu) add(X + k);
+        if ((v.y >> (8 * k)) & 0xffu) add(X + 4 + k);
+      }
     }
+  } else {
+    for (int X = x0; X < x1; ++X)
+      if (mrow == nullptr || mrow[X]) add(X);
   }
   float* out = moments + row * 5 * w + j;
   out[0] = m0;
@@ -86,7 +98,7 @@ __global__ void __launch_bounds__(256) distill_moments_kernel(const uint8_t* __r
 #define BACS_DISTILL_RB 4
 #endif
 constexpr int kDistillWarps = 8;
-constexpr int kChanPerWarp = 1;
+constexpr int kChanPerWarp = 2;
 constexpr int kChanPerCta = kDistillWarps * kChanPerWarp;
 
 // Value of a quantity that is linear in the row weight ty:  v(ty) = p + q * ty.
@@ -129,24 +141,25 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
 
 // One warp owns kChanPerWarp channels of one image; lane j owns low-res column(s) j (+32m).
 // The CTA walks the source-row intervals top to bottom; the five mask moments of every
-// row of the interval are staged in shared memory once and reused by all its channels.
+// row of the interval arrive by TMA bulk copy one interval ahead and are shared by all channels.
 //
 // Per (channel, row, cell), with a = value at the cell centre and d = r[j+1]-r[j] of the
-// y-interpolated row (both linear in ty):
+// y-interpolated row (all linear in the row weight ty):
 //   alpha = a_o - a_n, sigma = a_o + a_n, delta = d_o - d_n, eps = d_o + d_n
-//   c0 = alpha*sigma, c1 = 2(alpha*d_o + a_n*delta), c2 = delta*eps     (exactly 0 for old == new)
+//   U(old)^2 - U(new)^2 = (alpha + delta tau)(sigma + eps tau) = c0 + c1 tau + c2 tau^2,
+//   c0 = alpha sigma, c1 = alpha eps + delta sigma, c2 = delta eps            (exactly 0 for old == new)
 //   u = G c (G = Hankel matrix of the moments), S_cell = c.u, dS/dc = 2u
-//   dL/da_n = -2 rs (u0 a_n + u1 d_n) ... accumulated against {1, ty} so that the corner
-//   gradients are assembled once per interval instead of once per row.
+//   dL/da_n = -rs (u0 2a_n + u1 2d_n), dL/dd_n = -rs (u1 2a_n + u2 2d_n), 2a_n = sigma - alpha, 2d_n = eps - delta,
+//   accumulated against {1, ty} so that the corner gradients are assembled once per interval.
 template <typename T, int CPL>
-__global__ void __launch_bounds__(32 * kDistillWarps, 3) distill_kernel(const T* __restrict__ old_att,
+__global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T* __restrict__ old_att,
                                                                       const T* __restrict__ new_att, int A, int h,
                                                                       int w, int H, DistillTables tb,
                                                                       const float* __restrict__ moments, int rows_max,
                                                                       float grad_coef, T* __restrict__ dnew,
                                                                       double* __restrict__ partials) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int b = blockIdx.y, b_img = blockIdx.y;
+  const int b = blockIdx.y;
   const int ch0 = blockIdx.x * kChanPerCta + wid * kChanPerWarp;
   const bool want_grad = dnew != nullptr;
   // dynamic smem: 2 x [rows_max][5][WP] moment buffers (columns zero-padded to WP) | ty[H]
@@ -154,6 +167,8 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 3) distill_kernel(const T*
   __shared__ double red_scratch[32];
   __shared__ uint64_t mom_bar[2];
   constexpr int WP = 32 * CPL;
+  constexpr int NC = kChanPerWarp;
+  constexpr unsigned kFull = 0xffffffffu;
   const size_t mom_stride = (size_t)rows_max * 5 * WP;
   float* s_ty = s_dyn + 2 * mom_stride;
   const bool bulk_ok = (w == WP);  // contiguous rows -> one TMA bulk copy per interval
@@ -164,10 +179,9 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 3) distill_kernel(const T*
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  auto stage_moments = [&](int i, int buf) {
-    // moments of the rows of interval i -> buffer buf
+  auto stage_moments = [&](int i, int buf) {  // moments of the rows of interval i -> buffer buf
     const int Y0 = tb.rowstart[i], nr = tb.rowstart[i + 1] - Y0;
-    const float* src = moments + ((int64_t)b_img * H + Y0) * 5 * w;
+    const float* src = moments + ((int64_t)b * H + Y0) * 5 * w;
     float* dst = s_dyn + buf * mom_stride;
     if (bulk_ok) {
       if (threadIdx.x == 0) dist_bulk_load(dst, src, (uint32_t)(nr * 5 * w * sizeof(float)), &mom_bar[buf]);
@@ -179,41 +193,40 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 3) distill_kernel(const T*
       }
     }
   };
-  constexpr int NC = kChanPerWarp;
 
-  // corner values of the current interval's upper source row (columns j and j+1)
-  float o_prev[NC][CPL], o_prev1[NC][CPL], n_prev[NC][CPL], n_prev1[NC][CPL];
+  // attention values of this lane's column(s): upper source row of the current interval (prev) and
+  // the row after it (nxt, fetched one interval ahead); the right neighbour comes by shuffle
+  float o_prev[NC][CPL], n_prev[NC][CPL], o_nxt[NC][CPL], n_nxt[NC][CPL];
   float carry[NC][CPL];  // gradient already collected for the upper row by the interval above
   float loss_acc = 0.f;
-
-  auto load_row = [&](const T* base, int ch, int row, float* v, float* v1) {
+  auto load_row = [&](const T* base, int ch, int row, float* v) {
 #pragma unroll
     for (int m = 0; m < CPL; ++m) {
       const int j = lane + 32 * m;
-      v[m] = v1[m] = 0.f;
-      if (j < w && ch < A) {
-        const T* p = base + (((int64_t)b * A + ch) * h + row) * w;
-        v[m] = DT<T>::to_f(p[j]);
-        v1[m] = DT<T>::to_f(p[min(j + 1, w - 1)]);
-      }
+      v[m] = (j < w && ch < A) ? DT<T>::to_f(base[(((int64_t)b * A + ch) * h + row) * w + j]) : 0.f;
+    }
+  };
+  // value of column j+1 (the last column is its own right neighbour)
+  auto right = [&](const float* v, float* v1) {
+#pragma unroll
+    for (int m = 0; m < CPL; ++m) {
+      const float dn = __shfl_down_sync(kFull, v[m], 1);
+      const float wrap = __shfl_sync(kFull, m + 1 < CPL ? v[m + 1 < CPL ? m + 1 : m] : 0.f, 0);
+      const int j = lane + 32 * m;
+      v1[m] = (j >= w - 1) ? v[m] : (lane == 31 ? wrap : dn);
     }
   };
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    load_row(old_att, ch0 + c, 0, o_prev[c], o_prev1[c]);
-    load_row(new_att, ch0 + c, 0, n_prev[c], n_prev1[c]);
+    load_row(old_att, ch0 + c, 0, o_prev[c]);
+    load_row(new_att, ch0 + c, 0, n_prev[c]);
+    load_row(old_att, ch0 + c, min(1, h - 1), o_nxt[c]);
+    load_row(new_att, ch0 + c, min(1, h - 1), n_nxt[c]);
 #pragma unroll
     for (int m = 0; m < CPL; ++m) carry[c][m] = 0.f;
   }
-
   stage_moments(0, 0);
-  // corner rows of the NEXT interval are fetched one interval ahead (latency hidden by the row loop)
-  float o_nxt[NC][CPL], o_nxt1[NC][CPL], n_nxt[NC][CPL], n_nxt1[NC][CPL];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    load_row(old_att, ch0 + c, min(1, h - 1), o_nxt[c], o_nxt1[c]);
-    load_row(new_att, ch0 + c, min(1, h - 1), n_nxt[c], n_nxt1[c]);
-  }
+
   for (int i = 0; i < h; ++i) {
     const int Y0 = tb.rowstart[i], Y1 = tb.rowstart[i + 1];
     const int nrows = Y1 - Y0;
@@ -226,54 +239,47 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 3) distill_kernel(const T*
     if (bulk_ok) dist_mbar_wait(&mom_bar[buf], (uint32_t)((i >> 1) & 1));
     else if (i == 0) __syncthreads();
 
-    float o_cur[NC][CPL], o_cur1[NC][CPL], n_cur[NC][CPL], n_cur1[NC][CPL];
-    Lin alpha[NC][CPL], sigma[NC][CPL], delta[NC][CPL], eps[NC][CPL], an[NC][CPL], dn[NC][CPL], dold[NC][CPL];
+    Lin alpha[NC][CPL], sigma[NC][CPL], delta[NC][CPL], eps[NC][CPL];
     float GA0[NC][CPL], GA1[NC][CPL], GD0[NC][CPL], GD1[NC][CPL];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      if (row1 != i) {
+      float o_cur[CPL], n_cur[CPL], o_p1[CPL], n_p1[CPL], o_c1[CPL], n_c1[CPL];
 #pragma unroll
-        for (int m = 0; m < CPL; ++m) {
-          o_cur[c][m] = o_nxt[c][m]; o_cur1[c][m] = o_nxt1[c][m];
-          n_cur[c][m] = n_nxt[c][m]; n_cur1[c][m] = n_nxt1[c][m];
-        }
-        if (i + 2 < h) {
-          load_row(old_att, ch0 + c, i + 2, o_nxt[c], o_nxt1[c]);
-          load_row(new_att, ch0 + c, i + 2, n_nxt[c], n_nxt1[c]);
-        }
-      } else {
-#pragma unroll
-        for (int m = 0; m < CPL; ++m) {
-          o_cur[c][m] = o_prev[c][m]; o_cur1[c][m] = o_prev1[c][m];
-          n_cur[c][m] = n_prev[c][m]; n_cur1[c][m] = n_prev1[c][m];
-        }
+      for (int m = 0; m < CPL; ++m) {
+        o_cur[m] = row1 != i ? o_nxt[c][m] : o_prev[c][m];
+        n_cur[m] = row1 != i ? n_nxt[c][m] : n_prev[c][m];
       }
+      if (i + 2 < h) {  // prefetch the row of the interval after the next one
+        load_row(old_att, ch0 + c, i + 2, o_nxt[c]);
+        load_row(new_att, ch0 + c, i + 2, n_nxt[c]);
+      }
+      right(o_prev[c], o_p1);
+      right(n_prev[c], n_p1);
+      right(o_cur, o_c1);
+      right(n_cur, n_c1);
 #pragma unroll
       for (int m = 0; m < CPL; ++m) {
         // values at ty = 0 (upper source row) and ty = 1 (lower source row)
-        const float ao0 = 0.5f * (o_prev[c][m] + o_prev1[c][m]), ao1 = 0.5f * (o_cur[c][m] + o_cur1[c][m]);
-        const float an0 = 0.5f * (n_prev[c][m] + n_prev1[c][m]), an1 = 0.5f * (n_cur[c][m] + n_cur1[c][m]);
-        const float do0 = o_prev1[c][m] - o_prev[c][m], do1 = o_cur1[c][m] - o_cur[c][m];
-        const float dn0 = n_prev1[c][m] - n_prev[c][m], dn1 = n_cur1[c][m] - n_cur[c][m];
+        const float ao0 = 0.5f * (o_prev[c][m] + o_p1[m]), ao1 = 0.5f * (o_cur[m] + o_c1[m]);
+        const float an0 = 0.5f * (n_prev[c][m] + n_p1[m]), an1 = 0.5f * (n_cur[m] + n_c1[m]);
+        const float do0 = o_p1[m] - o_prev[c][m], do1 = o_c1[m] - o_cur[m];
+        const float dn0 = n_p1[m] - n_prev[c][m], dn1 = n_c1[m] - n_cur[m];
         alpha[c][m] = lin(ao0 - an0, ao1 - an1);
         sigma[c][m] = lin(ao0 + an0, ao1 + an1);
         delta[c][m] = lin(do0 - dn0, do1 - dn1);
         eps[c][m] = lin(do0 + dn0, do1 + dn1);
-        an[c][m] = lin(an0, an1);
-        dn[c][m] = lin(dn0, dn1);
-        dold[c][m] = lin(do0, do1);
         GA0[c][m] = GA1[c][m] = GD0[c][m] = GD1[c][m] = 0.f;
+        o_prev[c][m] = o_cur[m];
+        n_prev[c][m] = n_cur[m];
       }
     }
 
-    // rows are processed RB at a time so that RB independent dependency chains (shared-memory
-    // loads -> FMAs -> 5-step shuffle reduction -> rsqrt) are in flight per warp
     // rows are processed RB at a time (RB independent dependency chains per warp: shared-memory
     // loads -> FMAs -> 5-step shuffle reduction -> rsqrt); a 1-row tail handles odd counts
     auto process_rows = [&](auto rb_tag, const float* mrow, const float* tyrow) {
       constexpr int RB = decltype(rb_tag)::value;
       float ty[RB];
-      float u0[RB][NC][CPL], u1[RB][NC][CPL], u2[RB][NC][CPL], va[RB][NC][CPL], vd[RB][NC][CPL], S[RB][NC];
+      float u0[RB][NC][CPL], u1[RB][NC][CPL], u2[RB][NC][CPL], va2[RB][NC][CPL], vd2[RB][NC][CPL], S[RB][NC];
 #pragma unroll
       for (int q = 0; q < RB; ++q) {
         ty[q] = tyrow[q];
@@ -291,12 +297,12 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 3) distill_kernel(const T*
         for (int c = 0; c < NC; ++c) {
 #pragma unroll
           for (int m = 0; m < CPL; ++m) {
-            const float al = alpha[c][m].at(ty[q]), sg = sigma[c][m].at(ty[q]), de = delta[c][m].at(ty[q]);
-            const float ep = eps[c][m].at(ty[q]), d_o = dold[c][m].at(ty[q]);
-            va[q][c][m] = an[c][m].at(ty[q]);
-            vd[q][c][m] = dn[c][m].at(ty[q]);
+            const float al = alpha[c][m].at(ty[q]), sg = sigma[c][m].at(ty[q]);
+            const float de = delta[c][m].at(ty[q]), ep = eps[c][m].at(ty[q]);
+            va2[q][c][m] = sg - al;  // 2 a_n
+            vd2[q][c][m] = ep - de;  // 2 d_n
             const float c0 = al * sg;
-            const float c1 = 2.f * fmaf(al, d_o, va[q][c][m] * de);
+            const float c1 = fmaf(al, ep, de * sg);
             const float c2 = de * ep;
             u0[q][c][m] = fmaf(c2, M2[m], fmaf(c1, M1[m], c0 * M0[m]));
             u1[q][c][m] = fmaf(c2, M3[m], fmaf(c1, M2[m], c0 * M1[m]));
@@ -311,7 +317,7 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 3) distill_kernel(const T*
 #pragma unroll
         for (int q = 0; q < RB; ++q)
 #pragma unroll
-          for (int c = 0; c < NC; ++c) S[q][c] += __shfl_xor_sync(0xffffffffu, S[q][c], o);
+          for (int c = 0; c < NC; ++c) S[q][c] += __shfl_xor_sync(kFull, S[q][c], o);
       }
 #pragma unroll
       for (int q = 0; q < RB; ++q) {
@@ -323,9 +329,8 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 3) distill_kernel(const T*
           if (want_grad) {
 #pragma unroll
             for (int m = 0; m < CPL; ++m) {
-              // dL/dc = rs * u ;  d/da_n = -2 (g0 a_n + g1 d_n) ; d/dd_n = -2 (g1 a_n + g2 d_n)
-              const float gA = rs * fmaf(u1[q][c][m], vd[q][c][m], u0[q][c][m] * va[q][c][m]);
-              const float gD = rs * fmaf(u2[q][c][m], vd[q][c][m], u1[q][c][m] * va[q][c][m]);
+              const float gA = rs * fmaf(u1[q][c][m], vd2[q][c][m], u0[q][c][m] * va2[q][c][m]);
+              const float gD = rs * fmaf(u2[q][c][m], vd2[q][c][m], u1[q][c][m] * va2[q][c][m]);
               GA0[c][m] += gA;
               GA1[c][m] = fmaf(gA, ty[q], GA1[c][m]);
               GD0[c][m] += gD;
@@ -350,12 +355,12 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 3) distill_kernel(const T*
       for (int c = 0; c < NC; ++c) {
         const int ch = ch0 + c;
         // a_n(ty) = an0 + (an1-an0) ty, d_n likewise; an0 = (n0[j]+n0[j+1])/2, dn0 = n0[j+1]-n0[j]
-        // (index 0 = upper source row, 1 = lower).  The factor -2 of gA / gD is applied here.
+        // (index 0 = upper source row, 1 = lower).  GA / GD were accumulated with 2a_n, 2d_n: factor -1.
         float g0[CPL], g1[CPL], g0n[CPL], g1n[CPL];
 #pragma unroll
         for (int m = 0; m < CPL; ++m) {
-          const float dA0 = -2.f * (GA0[c][m] - GA1[c][m]), dA1 = -2.f * GA1[c][m];  // d/d an0, d/d an1
-          const float dD0 = -2.f * (GD0[c][m] - GD1[c][m]), dD1 = -2.f * GD1[c][m];
+          const float dA0 = -(GA0[c][m] - GA1[c][m]), dA1 = -GA1[c][m];  // d/d an(ty=0), d/d an(ty=1)
+          const float dD0 = -(GD0[c][m] - GD1[c][m]), dD1 = -GD1[c][m];
           g0[m] = 0.5f * dA0 - dD0;   // upper row, column j
           g0n[m] = 0.5f * dA0 + dD0;  // upper row, column j+1
           g1[m] = 0.5f * dA1 - dD1;   // lower row, column j
@@ -365,10 +370,10 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 3) distill_kernel(const T*
         for (int m = 0; m < CPL; ++m) {
           const int j = lane + 32 * m;
           // lane 0 of group m takes the value of lane 31 of group m-1 (all lanes run both shuffles)
-          const float wrap0 = __shfl_sync(0xffffffffu, m > 0 ? g0n[m > 0 ? m - 1 : 0] : 0.f, 31);
-          const float wrap1 = __shfl_sync(0xffffffffu, m > 0 ? g1n[m > 0 ? m - 1 : 0] : 0.f, 31);
-          const float sh0 = __shfl_up_sync(0xffffffffu, g0n[m], 1);
-          const float sh1 = __shfl_up_sync(0xffffffffu, g1n[m], 1);
+          const float wrap0 = __shfl_sync(kFull, m > 0 ? g0n[m > 0 ? m - 1 : 0] : 0.f, 31);
+          const float wrap1 = __shfl_sync(kFull, m > 0 ? g1n[m > 0 ? m - 1 : 0] : 0.f, 31);
+          const float sh0 = __shfl_up_sync(kFull, g0n[m], 1);
+          const float sh1 = __shfl_up_sync(kFull, g1n[m], 1);
           const float up0 = lane == 0 ? wrap0 : sh0;
           const float up1 = lane == 0 ? wrap1 : sh1;
           if (j > 0 && j < w) {
@@ -388,14 +393,6 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 3) distill_kernel(const T*
           if (j < w && ch < A) dnew[(((int64_t)b * A + ch) * h + i) * w + j] = DT<T>::from_f(grad_coef * fin);
           carry[c][m] = g1[m];
         }
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-#pragma unroll
-      for (int m = 0; m < CPL; ++m) {
-        o_prev[c][m] = o_cur[c][m]; o_prev1[c][m] = o_cur1[c][m];
-        n_prev[c][m] = n_cur[c][m]; n_prev1[c][m] = n_cur1[c][m];
       }
     }
   }

@@ -11,16 +11,24 @@ namespace bacs {
 // `.view(D, -1)` cuts that sequence into D rows of N_g elements, so the run spans at most
 // two rows: r0 = base / N_g gets the elements with rank < split, r0 + 1 the rest, where
 // split = (r0 + 1) * N_g - base.  Per-channel mode is the same code with split = n_bg.
-template <typename T, int TMAX>
-__global__ void __launch_bounds__(256) proto_accumulate_kernel(const T* __restrict__ feat, int B, int D, int hw,
-                                                               const int8_t* __restrict__ task,
-                                                               const int32_t* __restrict__ rank,
-                                                               const int32_t* __restrict__ n_bt, int Tn, int mode,
-                                                               float* __restrict__ partial /* [B,D,Tn,2] */) {
+// Each lane accumulates into its own column of a warp-private shared-memory table
+// acc[task][low/high][lane] (conflict-free, no atomics): a pixel touches exactly one entry, so
+// the cost per element does not grow with the number of tasks.
+constexpr int kAccWarps = 8;
+template <typename T>
+__global__ void __launch_bounds__(32 * kAccWarps) proto_accumulate_kernel(const T* __restrict__ feat, int B, int D,
+                                                                          int hw, const int8_t* __restrict__ task,
+                                                                          const int32_t* __restrict__ rank,
+                                                                          const int32_t* __restrict__ n_bt, int Tn,
+                                                                          int mode,
+                                                                          float* __restrict__ partial /* [B,D,Tn,2] */) {
+  extern __shared__ float s_acc[];  // [warp][Tn][2][32]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int b = blockIdx.y;
-  const int c = blockIdx.x * (blockDim.x >> 5) + wid;
+  const int c = blockIdx.x * kAccWarps + wid;
   if (c >= D) return;
+  float* acc = s_acc + (size_t)wid * Tn * 64;
+  for (int i = lane; i < Tn * 64; i += 32) acc[i] = 0.f;
   // lane g holds the split point of task g
   int split = 0x7fffffff;
   if (mode == 0 && lane < Tn) {
@@ -38,9 +46,7 @@ __global__ void __launch_bounds__(256) proto_accumulate_kernel(const T* __restri
       split = sp > 0x7fffffffLL ? 0x7fffffff : (int)sp;
     }
   }
-  float lo[TMAX], hi[TMAX];
-#pragma unroll
-  for (int g = 0; g < TMAX; ++g) lo[g] = hi[g] = 0.f;
+  __syncwarp();
   const T* row = feat + ((int64_t)b * D + c) * hw;
   const int8_t* tk = task + (int64_t)b * hw;
   const int32_t* rk = rank + (int64_t)b * hw;
@@ -58,26 +64,14 @@ __global__ void __launch_bounds__(256) proto_accumulate_kernel(const T* __restri
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int sp = __shfl_sync(0xffffffffu, split, t[u] < 0 ? 0 : t[u]);
-      const bool low = k[u] < sp;
-#pragma unroll
-      for (int g = 0; g < TMAX; ++g) {
-        const float m = (t[u] == g) ? v[u] : 0.f;
-        lo[g] += low ? m : 0.f;
-        hi[g] += low ? 0.f : m;
-      }
+      if (t[u] >= 0) acc[(t[u] * 2 + (k[u] < sp ? 0 : 1)) * 32 + lane] += v[u];
     }
   }
+  __syncwarp();
   float* out = partial + (((int64_t)b * D + c) * Tn) * 2;
-#pragma unroll
-  for (int g = 0; g < TMAX; ++g) {
-    if (g < Tn) {
-      const float a = warp_sum(lo[g]);
-      const float h2 = warp_sum(hi[g]);
-      if (lane == 0) {
-        out[g * 2 + 0] = a;
-        out[g * 2 + 1] = h2;
-      }
-    }
+  for (int e = 0; e < Tn * 2; ++e) {
+    const float r = warp_sum(acc[e * 32 + lane]);
+    if (lane == 0) out[e] = r;
   }
 }
 
@@ -85,16 +79,20 @@ __global__ void __launch_bounds__(256) proto_accumulate_kernel(const T* __restri
 // Image b's masked elements occupy flat positions [D*pre_b, D*(pre_b+n_b)), i.e. rows
 // lo_b .. hi_b of the D x N_g view; row r only looks at images with lo_b <= r <= hi_b + 1.
 constexpr int kFinMaxB = 1024;
-constexpr int kFinRows = 64;  // output rows per block
-__global__ void __launch_bounds__(kFinRows) proto_finalize_kernel(const float* __restrict__ partial, int B, int D,
-                                                                  const int32_t* __restrict__ n_bt, int Tn, int mode,
-                                                                  double* __restrict__ sums,
-                                                                  double* __restrict__ counts) {
+constexpr int kFinRows = 32;   // output rows per block
+constexpr int kFinLanes = 8;   // images are strided over this many threads per row
+__global__ void __launch_bounds__(kFinRows* kFinLanes) proto_finalize_kernel(const float* __restrict__ partial, int B,
+                                                                            int D, const int32_t* __restrict__ n_bt,
+                                                                            int Tn, int mode,
+                                                                            double* __restrict__ sums,
+                                                                            double* __restrict__ counts) {
   __shared__ long long s_pre[kFinMaxB];
   __shared__ int s_nb[kFinMaxB], s_lo[kFinMaxB], s_hi[kFinMaxB];
   __shared__ long long s_tot;
+  __shared__ double s_red[kFinLanes][kFinRows];
   const int g = blockIdx.x;
-  if (threadIdx.x == 0) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
     long long run = 0;
     for (int bb = 0; bb < B; ++bb) {
       const int n = n_bt[bb * Tn + g];
@@ -108,39 +106,45 @@ __global__ void __launch_bounds__(kFinRows) proto_finalize_kernel(const float* _
   __syncthreads();
   const long long tot = s_tot;
   if (mode == 0 && tot > 0)
-    for (int bb = threadIdx.x; bb < B; bb += blockDim.x) {
+    for (int bb = tid; bb < B; bb += blockDim.x) {
       s_lo[bb] = (int)(((long long)D * s_pre[bb]) / tot);
       s_hi[bb] = s_nb[bb] > 0 ? (int)(((long long)D * (s_pre[bb] + s_nb[bb]) - 1) / tot) : -2;
     }
   __syncthreads();
-  for (int r = blockIdx.y * kFinRows + threadIdx.x; r < D && r < (blockIdx.y + 1) * kFinRows; r += blockDim.x) {
-    double acc = 0.0;
-    if (tot > 0) {
-      if (mode != 0) {
-        for (int bb = 0; bb < B; ++bb) acc += (double)partial[(((int64_t)bb * D + r) * Tn + g) * 2];
-      } else {
-        for (int bb = 0; bb < B; ++bb) {
-          const long long nb = s_nb[bb];
-          if (nb <= 0 || r < s_lo[bb] || r > s_hi[bb] + 1) continue;
-          // channels c with r0(c) == r   <=>  r*tot <= D*pre + c*nb < (r+1)*tot
-          const long long off = (long long)D * s_pre[bb];
-          auto ceil_div = [](long long a, long long d) { return a <= 0 ? 0LL : (a + d - 1) / d; };
-          long long c_lo = ceil_div((long long)r * tot - off, nb);
-          long long c_hi = ceil_div((long long)(r + 1) * tot - off, nb);
-          if (c_hi > D) c_hi = D;
-          for (long long c = c_lo; c < c_hi; ++c) acc += (double)partial[(((int64_t)bb * D + c) * Tn + g) * 2 + 0];
-          // channels with r0(c) == r - 1 contribute their high part
-          if (r > 0) {
-            long long d_lo = ceil_div((long long)(r - 1) * tot - off, nb);
-            long long d_hi = c_lo;
-            if (d_hi > D) d_hi = D;
-            for (long long c = d_lo; c < d_hi; ++c)
-              acc += (double)partial[(((int64_t)bb * D + c) * Tn + g) * 2 + 1];
-          }
+  const int rl = tid % kFinRows, bl = tid / kFinRows;
+  const int r = blockIdx.y * kFinRows + rl;
+  double acc = 0.0;
+  if (r < D && tot > 0) {
+    if (mode != 0) {
+      for (int bb = bl; bb < B; bb += kFinLanes) acc += (double)partial[(((int64_t)bb * D + r) * Tn + g) * 2];
+    } else {
+      for (int bb = bl; bb < B; bb += kFinLanes) {
+        const long long nb = s_nb[bb];
+        if (nb <= 0 || r < s_lo[bb] || r > s_hi[bb] + 1) continue;
+        // channels c with r0(c) == r   <=>  r*tot <= D*pre + c*nb < (r+1)*tot
+        const long long off = (long long)D * s_pre[bb];
+        auto ceil_div = [](long long a, long long d) { return a <= 0 ? 0LL : (a + d - 1) / d; };
+        long long c_lo = ceil_div((long long)r * tot - off, nb);
+        long long c_hi = ceil_div((long long)(r + 1) * tot - off, nb);
+        if (c_hi > D) c_hi = D;
+        for (long long c = c_lo; c < c_hi; ++c) acc += (double)partial[(((int64_t)bb * D + c) * Tn + g) * 2 + 0];
+        // channels with r0(c) == r - 1 contribute their high part
+        if (r > 0) {
+          long long d_lo = ceil_div((long long)(r - 1) * tot - off, nb);
+          long long d_hi = c_lo;
+          if (d_hi > D) d_hi = D;
+          for (long long c = d_lo; c < d_hi; ++c) acc += (double)partial[(((int64_t)bb * D + c) * Tn + g) * 2 + 1];
         }
       }
     }
-    sums[(int64_t)g * D + r] = acc;
+  }
+  s_red[bl][rl] = acc;
+  __syncthreads();
+  if (bl == 0 && r < D) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < kFinLanes; ++i) t += s_red[i][rl];  // fixed order: deterministic
+    sums[(int64_t)g * D + r] = t;
   }
 }
 
@@ -217,20 +221,15 @@ int bacs_proto_accumulate(const void* features, int dtype, int B, int D, int h, 
   cudaStream_t s = (cudaStream_t)stream;
   float* partial = reinterpret_cast<float*>(workspace);
   const int hw = h * w;
-  dim3 grid((D + 7) / 8, B);
-#define LAUNCH_ACC(TT, TM) \
-  proto_accumulate_kernel<TT, TM><<<grid, 256, 0, s>>>(reinterpret_cast<const TT*>(features), B, D, hw, task, rank, \
-                                                       n_bt, T, mode, partial)
+  dim3 grid((D + kAccWarps - 1) / kAccWarps, B);
+  const size_t acc_smem = (size_t)kAccWarps * T * 64 * sizeof(float);
   BACS_DISPATCH_DTYPE(dtype, TT, {
-    if (T <= 4) LAUNCH_ACC(TT, 4);
-    else if (T <= 8) LAUNCH_ACC(TT, 8);
-    else if (T <= 16) LAUNCH_ACC(TT, 16);
-    else LAUNCH_ACC(TT, 32);
+    proto_accumulate_kernel<TT><<<grid, 32 * kAccWarps, acc_smem, s>>>(reinterpret_cast<const TT*>(features), B, D, hw,
+                                                                       task, rank, n_bt, T, mode, partial);
   });
-#undef LAUNCH_ACC
   BACS_CHECK_LAUNCH("bacs_proto_accumulate");
-  proto_finalize_kernel<<<dim3(T, (D + kFinRows - 1) / kFinRows), kFinRows, 0, s>>>(partial, B, D, n_bt, T, mode, sums,
-                                                                                   counts);
+  proto_finalize_kernel<<<dim3(T, (D + kFinRows - 1) / kFinRows), kFinRows * kFinLanes, 0, s>>>(partial, B, D, n_bt, T,
+                                                                                                 mode, sums, counts);
   BACS_CHECK_LAUNCH("bacs_proto_accumulate(finalize)");
   return BACS_OK;
 }

@@ -8,7 +8,9 @@
 namespace bacs {
 
 constexpr int kSeenWarps = 8;
+constexpr int kSeenPix = 2;  // pixels per thread: the per-channel weights are fetched once for all of them
 
+// block = 32 lanes x 8 channel groups; a block covers 128 consecutive pixels of one image
 template <typename T, int TMAX>
 __global__ void __launch_bounds__(32 * kSeenWarps) seen_logits_kernel(const T* __restrict__ feat, int D, int hw,
                                                                        const float* __restrict__ proto,
@@ -16,59 +18,77 @@ __global__ void __launch_bounds__(32 * kSeenWarps) seen_logits_kernel(const T* _
                                                                        const float* __restrict__ bias, int Tn,
                                                                        int chunk, float* __restrict__ z) {
   extern __shared__ float smem[];
-  float* s_sp = smem;                 // [Tn, chunk] sigmoid(proto)
-  float* s_w = smem + Tn * chunk;     // [Tn, chunk]
+  float* s_sp = smem;              // [chunk][Tn] sigmoid(proto)   (head index fastest: one row per channel)
+  float* s_w = smem + Tn * chunk;  // [chunk][Tn]
   const int lane = threadIdx.x, cg = threadIdx.y;
   const int b = blockIdx.y;
-  const int q = blockIdx.x * 32 + lane;
-  const bool live = q < hw;
+  const int q0 = blockIdx.x * (32 * kSeenPix) + lane;
   const int tid = cg * 32 + lane;
-  float acc[TMAX];
+  float acc[kSeenPix][TMAX];
 #pragma unroll
-  for (int t = 0; t < TMAX; ++t) acc[t] = 0.f;
-  const T* base = feat + (int64_t)b * D * hw + (live ? q : 0);
+  for (int i = 0; i < kSeenPix; ++i)
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) acc[i][t] = 0.f;
+  const T* base = feat + (int64_t)b * D * hw;
   for (int c0 = 0; c0 < D; c0 += chunk) {
     const int cn = min(chunk, D - c0);
     __syncthreads();
     for (int i = tid; i < Tn * cn; i += 32 * kSeenWarps) {
       const int t = i / cn, c = i - t * cn;
-      s_sp[t * chunk + c] = sigmoid_fast(proto[t * D + c0 + c]);
-      s_w[t * chunk + c] = weight[t * D + c0 + c];
+      s_sp[c * Tn + t] = sigmoid_fast(proto[t * D + c0 + c]);
+      s_w[c * Tn + t] = weight[t * D + c0 + c];
     }
     __syncthreads();
-    // warp cg handles channels cg, cg + W, ... of the chunk; 8 independent loads in flight per thread
-    constexpr int U = 8;
-    for (int c = cg; c < cn; c += kSeenWarps * U) {
-      float x[U];
+    // warp cg handles channels cg, cg + 8, ... of the chunk; two channels (8 loads) in flight per thread
+    for (int c = cg; c < cn; c += 2 * kSeenWarps) {
+      float x[2][kSeenPix];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const int cc = c + u * kSeenWarps;
-        x[u] = (live && cc < cn) ? DT<T>::to_f(base[(int64_t)(c0 + cc) * hw]) : 0.f;
+#pragma unroll
+        for (int i = 0; i < kSeenPix; ++i) {
+          const int q = q0 + 32 * i;
+          x[u][i] = (cc < cn && q < hw) ? DT<T>::to_f(base[(int64_t)(c0 + cc) * hw + q]) : 0.f;
+        }
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const int cc = c + u * kSeenWarps;
         if (cc < cn) {
-          const float sx = sigmoid_fast(x[u]);
+          float sx[kSeenPix];
+#pragma unroll
+          for (int i = 0; i < kSeenPix; ++i) sx[i] = sigmoid_fast(x[u][i]);
 #pragma unroll
           for (int t = 0; t < TMAX; ++t)
-            if (t < Tn) acc[t] = fmaf(s_w[t * chunk + cc], fabsf(sx - s_sp[t * chunk + cc]), acc[t]);
+            if (t < Tn) {
+              const float wv = s_w[cc * Tn + t], sp = s_sp[cc * Tn + t];
+#pragma unroll
+              for (int i = 0; i < kSeenPix; ++i) acc[i][t] = fmaf(wv, fabsf(sx[i] - sp), acc[i][t]);
+            }
         }
       }
     }
   }
   __syncthreads();
-  // cross-warp reduction through shared memory: red[cg][t][lane]
+  // cross-warp reduction through shared memory: red[cg][t][pixel slot]
   float* red = smem;
+  constexpr int PS = 32 * kSeenPix;
 #pragma unroll
   for (int t = 0; t < TMAX; ++t)
-    if (t < Tn) red[(cg * Tn + t) * 32 + lane] = acc[t];
+    if (t < Tn) {
+#pragma unroll
+      for (int i = 0; i < kSeenPix; ++i) red[(cg * Tn + t) * PS + 32 * i + lane] = acc[i][t];
+    }
   __syncthreads();
   for (int t = cg; t < Tn; t += kSeenWarps) {
-    float s = bias[t];
 #pragma unroll
-    for (int g = 0; g < kSeenWarps; ++g) s += red[(g * Tn + t) * 32 + lane];
-    if (live) z[((int64_t)b * Tn + t) * hw + q] = s;
+    for (int i = 0; i < kSeenPix; ++i) {
+      float s = bias[t];
+#pragma unroll
+      for (int g = 0; g < kSeenWarps; ++g) s += red[(g * Tn + t) * PS + 32 * i + lane];
+      const int q = q0 + 32 * i;
+      if (q < hw) z[((int64_t)b * Tn + t) * hw + q] = s;
+    }
   }
 }
 
@@ -96,7 +116,7 @@ __global__ void __launch_bounds__(256) seen_upsample_kernel(const float* __restr
 
 // One block per channel: dW[c] = s * sum_{b,q} gz * |sig(f) - sig(p)|, optional dfeat.
 template <typename T>
-__global__ void __launch_bounds__(256) seen_head_backward_kernel(const T* __restrict__ feat, int B, int D, int hw,
+__global__ void __launch_bounds__(512) seen_head_backward_kernel(const T* __restrict__ feat, int B, int D, int hw,
                                                                  const float* __restrict__ proto_t,
                                                                  const float* __restrict__ weight_t,
                                                                  const float* __restrict__ gz,
@@ -116,30 +136,36 @@ __global__ void __launch_bounds__(256) seen_head_backward_kernel(const T* __rest
   const float sp = sigmoid_fast(proto_t[c]);
   const float wc = weight_t[c];
   float acc = 0.f;
+  // threads are split over images (ib) and pixels (iq) so that no index needs a division
   constexpr int U = 4;
-  const int total = B * hw;  // element i -> image i / hw, pixel i % hw; rows of one channel are hw apart by D*hw
-  for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * U) {
-    float x[U], gq[U];
-    int64_t off[U];
+  const int tq = min((int)blockDim.x, ((hw + U - 1) / U + 31) / 32 * 32);  // threads along the pixel axis
+  const int nb_par = max(1, (int)blockDim.x / tq);                          // images processed side by side
+  const int ib = threadIdx.x / tq, iq = threadIdx.x - ib * tq;
+  if (ib < nb_par) {
+    for (int b = ib; b < B; b += nb_par) {
+      const T* row = feat + ((int64_t)b * D + c) * hw;
+      const float* g = gz + (int64_t)b * hw;
+      T* drow = dfeat ? dfeat + ((int64_t)b * D + c) * hw : nullptr;
+      for (int q0 = iq; q0 < hw; q0 += tq * U) {
+        float x[U], gq[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * blockDim.x;
-      const int b = i / hw, q = i - b * hw;
-      off[u] = ((int64_t)b * D + c) * hw + q;
-      const bool ok = i < total;
-      x[u] = ok ? DT<T>::to_f(feat[off[u]]) : 0.f;
-      gq[u] = ok ? gz[i] : 0.f;
-    }
+        for (int u = 0; u < U; ++u) {
+          const int q = q0 + u * tq;
+          x[u] = q < hw ? DT<T>::to_f(row[q]) : 0.f;
+          gq[u] = q < hw ? g[q] : 0.f;
+        }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * blockDim.x;
-      if (i < total) {
-        const float sx = sigmoid_fast(x[u]);
-        const float d = sx - sp;
-        acc = fmaf(gq[u], fabsf(d), acc);
-        if (dfeat) {
-          const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-          dfeat[off[u]] = DT<T>::from_f(scale * gq[u] * wc * sg * sx * (1.f - sx));
+        for (int u = 0; u < U; ++u) {
+          const int q = q0 + u * tq;
+          if (q < hw) {
+            const float sx = sigmoid_fast(x[u]);
+            const float d = sx - sp;
+            acc = fmaf(gq[u], fabsf(d), acc);
+            if (drow) {
+              const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+              drow[q] = DT<T>::from_f(scale * gq[u] * wc * sg * sx * (1.f - sx));
+            }
+          }
         }
       }
     }
@@ -178,13 +204,22 @@ int bacs_seen_logits(const void* features, int dtype, int B, int D, int h, int w
   chunk = chunk / kSeenWarps * kSeenWarps;
   if (chunk > D) chunk = (D + kSeenWarps - 1) / kSeenWarps * kSeenWarps;
   size_t smem = (size_t)2 * T * chunk * sizeof(float);
-  const size_t red = (size_t)kSeenWarps * T * 32 * sizeof(float);
+  const size_t red = (size_t)kSeenWarps * T * 32 * kSeenPix * sizeof(float);
   if (smem < red) smem = red;
-  dim3 grid((hw + 31) / 32, B), block(32, kSeenWarps);
+  dim3 grid((hw + 32 * kSeenPix - 1) / (32 * kSeenPix), B), block(32, kSeenWarps);
   cudaStream_t s = (cudaStream_t)stream;
-#define LAUNCH_Z(TT, TM) \
-  seen_logits_kernel<TT, TM><<<grid, block, smem, s>>>(reinterpret_cast<const TT*>(features), D, hw, proto, weight, \
-                                                       bias, T, chunk, z)
+#define LAUNCH_Z(TT, TM)                                                                                          \
+  do {                                                                                                            \
+    auto kern = seen_logits_kernel<TT, TM>;                                                                       \
+    if (smem > 48 * 1024) {                                                                                       \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+      if (e != cudaSuccess) {                                                                                     \
+        set_error("bacs_seen_logits: shared memory opt-in failed: %s", cudaGetErrorString(e));                   \
+        return BACS_ERR_CUDA;                                                                                     \
+      }                                                                                                           \
+    }                                                                                                             \
+    kern<<<grid, block, smem, s>>>(reinterpret_cast<const TT*>(features), D, hw, proto, weight, bias, T, chunk, z); \
+  } while (0)
   BACS_DISPATCH_DTYPE(dtype, TT, {
     if (T <= 4) LAUNCH_Z(TT, 4);
     else if (T <= 8) LAUNCH_Z(TT, 8);
@@ -219,7 +254,7 @@ int bacs_seen_head_backward(const void* features, int dtype, int B, int D, int h
   const int hw = h * w;
   cudaStream_t s = (cudaStream_t)stream;
   BACS_DISPATCH_DTYPE(dtype, TT, {
-    seen_head_backward_kernel<TT><<<D + 1, 256, 0, s>>>(reinterpret_cast<const TT*>(features), B, D, hw, proto_t,
+    seen_head_backward_kernel<TT><<<D + 1, 512, 0, s>>>(reinterpret_cast<const TT*>(features), B, D, hw, proto_t,
                                                         weight_t, gz, scale_dev, dweight, dbias,
                                                         reinterpret_cast<TT*>(dfeatures));
   });
