@@ -48,6 +48,7 @@ _SIGNATURES = {
     "bacs_seen_head_backward": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "bacs_focal_scale": (i32, [vp, vp, f32, vp, vp, vp]),
     "bacs_pixel_workspace_bytes": (sz, [C.POINTER(PixelArgs)]),
+    "bacs_pixel_kernel_variant": (i32, [C.POINTER(PixelArgs)]),
     "bacs_pixel_loss": (i32, [C.POINTER(PixelArgs), vp, sz, vp]),
     "bacs_distill_workspace_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
     "bacs_teacher_distill": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, f32, vp, vp, vp, sz, vp]),

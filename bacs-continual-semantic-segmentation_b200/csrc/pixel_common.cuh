@@ -165,6 +165,36 @@ struct PixCoef {
   float cg0, cg1, cg2, d0, dy;
 };
 
+// Binary focal loss of one seen-head logit Z with target t (smp FocalLoss(mode="binary"), base_loss.py:255-272):
+//   bce = softplus(Z) - t Z,  pt = exp(-bce) = sigmoid(+-Z),  term = (1-pt)^g * bce [* alpha weight]; dterm = d term / dZ
+__device__ __forceinline__ void focal_term(const bacs_pixel_args& a, float Z, float t, float& term, float& dterm) {
+  const float e = __expf(-fabsf(Z));
+  const float inv = __fdividef(1.f, 1.f + e);
+  const float hi = inv, lo = e * inv;                        // sigmoid(|Z|), sigmoid(-|Z|)
+  const float sig = Z >= 0.f ? hi : lo;                      // sigmoid(Z)
+  const float nsig = Z >= 0.f ? lo : hi;                     // 1 - sigmoid(Z) without cancellation
+  const float pt = (t != 0.f) ? sig : nsig;
+  const float om = (t != 0.f) ? nsig : sig;                  // 1 - pt
+  const float dbce = (t != 0.f) ? -nsig : sig;               // sigmoid(Z) - t
+  const float bce = fmaxf(Z, 0.f) - Z * t + __logf(1.f + e);
+  if (a.focal_gamma == 2.f) {
+    term = om * om * bce;
+    dterm = dbce * (om * om + 2.f * om * pt * bce);
+  } else if (a.focal_gamma == 0.f) {
+    term = bce;
+    dterm = dbce;
+  } else {
+    const float pg = powf(om, a.focal_gamma);
+    term = pg * bce;
+    dterm = dbce * (pg + a.focal_gamma * powf(om, a.focal_gamma - 1.f) * pt * bce);
+  }
+  if (a.focal_alpha >= 0.f) {
+    const float aw = a.focal_alpha * t + (1.f - a.focal_alpha) * (1.f - t);
+    term *= aw;
+    dterm *= aw;
+  }
+}
+
 // Everything that depends on the softmax statistics of ONE pixel (not on the channel loop).
 __device__ __forceinline__ void pixel_terms(const bacs_pixel_args& a, float inv_n, float s_norm, int old_cl, int y,
                                             bool is_ign, float mx, float S, float S_old, float e0, float x0, float xy,
@@ -251,36 +281,10 @@ __device__ __forceinline__ void pixel_terms(const bacs_pixel_args& a, float inv_
     if (m) acc[BACS_ACC_DISTILL_PIX] += 1.f;
   }
 
-  // seen-detector focal loss of head `focal_head` (binary, target = foreground):
-  //   bce = softplus(Z) - t Z,  pt = exp(-bce) = sigmoid(+-Z),  term = (1-pt)^g * bce
+  // seen-detector focal loss of head `focal_head` (binary, target = foreground)
   if (a.gz && !is_ign) {
-    const float Z = zfoc;
-    const float t = (valid && y == 0) ? 0.f : 1.f;
-    const float e = __expf(-fabsf(Z));
-    const float inv = __fdividef(1.f, 1.f + e);
-    const float hi = inv, lo = e * inv;                        // sigmoid(|Z|), sigmoid(-|Z|)
-    const float sig = Z >= 0.f ? hi : lo;                      // sigmoid(Z)
-    const float nsig = Z >= 0.f ? lo : hi;                     // 1 - sigmoid(Z) without cancellation
-    const float pt = (t != 0.f) ? sig : nsig;
-    const float om = (t != 0.f) ? nsig : sig;                  // 1 - pt
-    const float bce = fmaxf(Z, 0.f) - Z * t + __logf(1.f + e);
     float term, dterm;
-    if (a.focal_gamma == 2.f) {
-      term = om * om * bce;
-      dterm = (sig - t) * (om * om + 2.f * om * pt * bce);
-    } else if (a.focal_gamma == 0.f) {
-      term = bce;
-      dterm = sig - t;
-    } else {
-      const float pg = powf(om, a.focal_gamma);
-      term = pg * bce;
-      dterm = (sig - t) * (pg + a.focal_gamma * powf(om, a.focal_gamma - 1.f) * pt * bce);
-    }
-    if (a.focal_alpha >= 0.f) {
-      const float aw = a.focal_alpha * t + (1.f - a.focal_alpha) * (1.f - t);
-      term *= aw;
-      dterm *= aw;
-    }
+    focal_term(a, zfoc, (valid && y == 0) ? 0.f : 1.f, term, dterm);
     acc[BACS_ACC_FOCAL] += term;
     gfoc = dterm;
   }
@@ -296,5 +300,9 @@ struct PixelPlan {
 int launch_pixel_fast_f32(const PixelParams& p, const PixelPlan& plan, cudaStream_t s);
 int launch_pixel_fast_bf16(const PixelParams& p, const PixelPlan& plan, cudaStream_t s);
 int launch_pixel_fast_f16(const PixelParams& p, const PixelPlan& plan, cudaStream_t s);
+// launchers of the training-step specialisation (pixel_wce.cuh)
+int launch_pixel_wce_f32(const PixelParams& p, const PixelPlan& plan, cudaStream_t s);
+int launch_pixel_wce_bf16(const PixelParams& p, const PixelPlan& plan, cudaStream_t s);
+int launch_pixel_wce_f16(const PixelParams& p, const PixelPlan& plan, cudaStream_t s);
 
 }  // namespace bacs

@@ -637,9 +637,9 @@ static bool make_plan(const bacs_pixel_args& a, PixelPlan* plan) {
         kreg = kregs[i];
         break;
       }
-    // 4 stages of {kreg logit rows, 512 int64 labels} + one [T][8] seen-logit strip per warp
+    // 4 stages of {kreg logit rows, 512 int64 labels, seen-head rows} + one [T][8] float2 strip per warp
     const size_t zrows = a.z ? (((size_t)a.T * 2 * a.w * 4 + 127) & ~(size_t)127) : 0;
-    const size_t smem = (size_t)4 * ((size_t)kreg * 512 * es + 4096 + zrows) + (a.z ? (size_t)8 * a.T * 8 * 4 : 0) + 64;
+    const size_t smem = (size_t)4 * ((size_t)kreg * 512 * es + 4096 + zrows) + (a.z ? (size_t)8 * a.T * 8 * 8 : 0) + 64;
     if (smem + 1024 <= cap) {
       // 228 KB of shared memory per SM, 1 KB reserved per resident CTA, < 0.5 KB static
       const int per_sm = (2 * (smem + 1024 + 512) <= (size_t)228 * 1024) ? 2 : 1;
@@ -701,6 +701,17 @@ size_t bacs_pixel_workspace_bytes(const bacs_pixel_args* a) {
   const int64_t tiles = (HW + plan.P - 1) / plan.P * a->B;
   const int64_t n_part = a->mode == BACS_PIX_SCORE ? tiles : plan.grid;
   return align_up((size_t)n_part * BACS_NACC * sizeof(double), 256);
+}
+
+static bool wce_eligible(const bacs_pixel_args& a, const PixelPlan& plan) {
+  return plan.fast && plan.rowtile && a.mode == BACS_PIX_WEIGHTED_CE && !a.seen_max && a.z && encode_tiled_fn() != nullptr &&
+         a.w <= 256 && a.T <= 256 && a.K <= 256;
+}
+
+int bacs_pixel_kernel_variant(const bacs_pixel_args* a) {
+  PixelPlan plan;
+  if (!a || !make_plan(*a, &plan)) return -1;
+  return wce_eligible(*a, plan) ? 2 : (plan.fast ? 1 : 0);
 }
 
 int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_bytes, bacs_stream_t stream) {
@@ -778,7 +789,16 @@ int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_
     if (plan.rowtile) LAUNCH_PIX(TT, PPT, 0, true); \
     else LAUNCH_PIX(TT, PPT, 0, false);             \
   } while (0)
-  if (plan.fast) {
+  const bool wce = p.use_tmap && wce_eligible(*a, plan);
+  if (wce) {  // the training step's kernel
+    int rc;
+    switch (a->dtype) {
+      case BACS_F32: rc = launch_pixel_wce_f32(p, plan, s); break;
+      case BACS_BF16: rc = launch_pixel_wce_bf16(p, plan, s); break;
+      default: rc = launch_pixel_wce_f16(p, plan, s); break;
+    }
+    if (rc != BACS_OK) return rc;
+  } else if (plan.fast) {
     int rc;
     switch (a->dtype) {
       case BACS_F32: rc = launch_pixel_fast_f32(p, plan, s); break;

@@ -241,6 +241,7 @@ def pixel_loss(logits: torch.Tensor, labels: torch.Tensor, mode: int, *, want_gr
     ws = _ws(nbytes, dev)
     check(lib.bacs_pixel_loss(C.byref(a), ws.data_ptr(), ws.numel(), _stream()), "bacs_pixel_loss")
     out["hist"] = hist
+    out["variant"] = lib.bacs_pixel_kernel_variant(C.byref(a))
     return out
 
 

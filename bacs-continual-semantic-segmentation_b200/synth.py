@@ -58,6 +58,15 @@ CONFIGS = {
     "tiny": StepConfig("tiny", B=2, K=7, old_cl=5, T=3, H=64, W=96, D=32, A=16, initial_classes=3,
                        increment=2, Br=2),
     "small": StepConfig("small", B=3, K=21, old_cl=20, T=6, H=128, W=160, D=64, A=32, Br=3),
+    # 512-pixel row tiles (the training-step kernel): whole rows, two tiles per row, padded class counts
+    "row512": StepConfig("row512", B=2, K=21, old_cl=20, T=6, H=48, W=512, D=32, A=16, Br=2),
+    "row1024": StepConfig("row1024", B=1, K=20, old_cl=18, T=3, H=32, W=1024, D=32, A=16, initial_classes=15,
+                          increment=2),
+    "row512_k17": StepConfig("row512_k17", B=2, K=17, old_cl=16, T=2, H=32, W=512, D=32, A=16),
+    "row512_k11": StepConfig("row512_k11", B=1, K=11, old_cl=6, T=11, H=32, W=512, D=32, A=16, initial_classes=6,
+                             increment=5),
+    "row512_k7": StepConfig("row512_k7", B=1, K=7, old_cl=5, T=3, H=32, W=512, D=32, A=16, initial_classes=3,
+                            increment=2),
 }
 
 

@@ -227,6 +227,62 @@ def test_pixel_weighted_ce(ops, synth, name, dtype, ukd):
     assert int(acc[_cabi.ACC_INVALID]) == 0
 
 
+@pytest.mark.parametrize("name,dtype,ukd", [
+    ("row512", torch.float32, True), ("row512", torch.bfloat16, True), ("row512", torch.float16, False),
+    ("row1024", torch.bfloat16, True), ("row1024", torch.float32, False), ("row512_k17", torch.bfloat16, True),
+    ("row512_k17", torch.float32, True), ("row512_k11", torch.bfloat16, False), ("row512_k11", torch.float32, True),
+    ("row512_k7", torch.bfloat16, True), ("row512_k7", torch.float32, True)])
+def test_pixel_training_step_kernel(ops, synth, name, dtype, ukd):
+    """512-pixel row tiles take the specialised training-step kernel: weighted CE + focal term of one head +
+    distill mask + arg-max + both gradients in one launch, incl. padded class counts and invalid labels."""
+    from bacs_b200 import _cabi
+    cfg = synth.CONFIGS[name]
+    inp = synth.make_step_inputs(cfg, seed=5, dtype=dtype)
+    g = torch.Generator().manual_seed(3)
+    mask = synth.make_labels(cfg, g, classes=list(range(1, cfg.K)))
+    mask[0, 9, 40:47] = cfg.K + 3                       # outside [0,K), not ignore: counted, treated as ignore
+    t = cfg.T - 1
+    z = _seen_z(inp).clone().requires_grad_(True)
+    up = O.bilinear_upsample(z, (cfg.H, cfg.W), True)
+    smax = torch.sigmoid(up).max(1)[0].detach()
+    x = inp.logits.float().clone().requires_grad_(True)
+    clean = torch.where(mask > 255, torch.full_like(mask, 255), mask)
+    clean = torch.where((clean >= cfg.K) & (clean != 255), torch.full_like(mask, 255), clean)
+    want = O.weighted_ce(x, clean, smax, cfg.old_cl, 2.0, 0.5, ukd)
+    want.backward()
+    kept = int((clean != 255).sum())
+    want_f = O.focal_seen_loss(up[:, t:t + 1], clean, 2.0, 0.25)
+    want_f.backward()
+    scale = 1024.0 if dtype == torch.float16 else 1.0
+    out = ops.pixel_loss(inp.logits.cuda(), mask.cuda(), _cabi.PIX_WEIGHTED_CE, want_grad=True, z=z.detach().cuda(),
+                         want_distill_mask=True, old_cl=cfg.old_cl, ukd=ukd, grad_scale=scale, focal_head=t,
+                         focal_alpha=0.25)
+    assert out["variant"] == 2, "expected the training-step kernel"
+    N = cfg.B * cfg.H * cfg.W
+    acc = out["acc"].cpu()
+    close(acc[_cabi.ACC_LOSS] / N, want, what="loss")
+    close(acc[_cabi.ACC_FOCAL] / kept, want_f, what="focal loss")
+    close(out["gz"] / kept, z.grad[:, t], atol=2e-5 * float(z.grad.abs().max()), what="gz")
+    assert torch.equal(out["preds"].cpu(), O.argmax_first(inp.logits.float()))
+    want_g = (x.grad * scale).to(dtype).float()
+    tol = RTOL if dtype == torch.float32 else 2.0 ** (-7 if dtype == torch.bfloat16 else -10)
+    close(out["dlogits"].float(), want_g, atol=tol * float(want_g.abs().max()), what="dlogits")
+    want_m = (clean == 0) & (smax > 0.5)
+    diff = out["distill_mask"].cpu().bool() != want_m
+    assert int((diff & ((smax - 0.5).abs() > 1e-6)).sum()) == 0
+    assert int(diff.sum()) <= 2
+    assert int(acc[_cabi.ACC_KEPT]) == kept
+    assert int(acc[_cabi.ACC_VALID]) == kept
+    assert int(acc[_cabi.ACC_BG]) == int((clean == 0).sum())
+    assert int(acc[_cabi.ACC_INVALID]) == 7
+    assert int(acc[_cabi.ACC_DISTILL_PIX]) == int(out["distill_mask"].sum())
+    # forward only (evaluation): same loss, no gradient tensors
+    out2 = ops.pixel_loss(inp.logits.cuda(), mask.cuda(), _cabi.PIX_WEIGHTED_CE, want_grad=False, z=z.detach().cuda(),
+                          old_cl=cfg.old_cl, ukd=ukd)
+    close(out2["acc"][_cabi.ACC_LOSS] / N, want, what="loss (no grad)")
+    assert torch.equal(out2["preds"], out["preds"])
+
+
 def test_pixel_focal_term(ops, synth):
     from bacs_b200 import _cabi
     cfg = synth.CONFIGS["tiny"]
