@@ -66,7 +66,8 @@ template <> struct NegInf<__half> {
 
 // Shared memory (dynamic): 4 stages of { [2][KREG][256] logits, 512 int64 labels, [T][2][w] seen-head rows }
 // followed by one warp-private [T][8] strip of float2 per warp.
-template <typename T, int KREG>
+// STD: the reference's hyper-parameters (gamma = focal gamma = 2, no alpha weighting, ukd) folded at compile time.
+template <typename T, int KREG, bool STD>
 __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid_constant__ PixelParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar_full[4];
@@ -97,29 +98,31 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(&bar_full[s], 1);             // the issuing lane's expect-tx arrival
+      mbar_init(&bar_full[s], 1);             // the loading lane's expect-tx arrival
       mbar_init(&bar_done[s], kFastThreads);  // every thread, after its gradient rows are written
     }
     fence_mbar_init();
   }
   __syncthreads();
 
-  // tile geometry is advanced incrementally (no integer divisions in the loop)
-  const int step_b = grid / tpi, step_t = grid - step_b * tpi;
-  int tb = (int)blockIdx.x / tpi, tt = (int)blockIdx.x - tb * tpi;
-  auto advance = [&](int& b, int& t) {
-    b += step_b;
-    t += step_t;
-    if (t >= tpi) {
-      t -= tpi;
-      ++b;
-    }
-  };
   const int tiles_per_row = a.W / P;
+  const bool tpr1 = tiles_per_row == 1;
   const int tpr_shift = (tiles_per_row & (tiles_per_row - 1)) == 0 ? __ffs(tiles_per_row) - 1 : -1;
-  auto row_of_tile = [&](int t) { return tpr_shift >= 0 ? (t >> tpr_shift) : t / tiles_per_row; };
+  auto row_of_tile = [&](int t) { return tpr1 ? t : (tpr_shift >= 0 ? (t >> tpr_shift) : t / tiles_per_row); };
+  // ---- TMA traffic.  Tile k of this CTA is OWNED by warp k % 8: its elected lane writes the gradient rows
+  // back one iteration later (once every thread has arrived on bar_done) and, one iteration after that --
+  // when its own store has drained the stage -- refills the stage with tile k + 4.  Every warp carries an
+  // eighth of the issue work, none is a straggler, and a lane only ever waits on bulk groups it committed.
+  auto tile_coords = [&](int k, int& b, int& t) {
+    const int g = (int)blockIdx.x + k * grid;
+    b = g / tpi;
+    t = g - b * tpi;
+  };
   const uint32_t tx_bytes = (uint32_t)K * (uint32_t)(P * sizeof(T)) + kLabelBytes + zrow_bytes;
-  auto issue_load = [&](int b, int t, int s) {
+  auto issue_load = [&](int k) {
+    int b, t;
+    tile_coords(k, b, t);
+    const int s = k & (S - 1);
     mbar_expect_tx(&bar_full[s], tx_bytes);
     T* dst = stage_tile(s);
     const Lerp ly = lerp_align_corners(row_of_tile(t), a.h, p.sy);
@@ -129,31 +132,30 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
     bulk_g2s(const_cast<int64_t*>(stage_labels(s)), a.labels + (int64_t)b * HW + (int64_t)t * P, kLabelBytes,
              &bar_full[s]);
   };
-  auto issue_store = [&](int b, int t, int s) {
-    const T* src = stage_tile(s);
+  auto issue_store = [&](int k) {
+    int b, t;
+    tile_coords(k, b, t);
+    const T* src = stage_tile(k & (S - 1));
     tma_store_3d(&p.tmap_out, t * P, 0, b, src);
     tma_store_3d(&p.tmap_out, t * P + kBox, 0, b, src + (size_t)KREG * kBox);
     bulk_commit();
   };
-  int pb = tb, pt = tt;  // load cursor (tile k + 2)
-  int sb = tb, st = tt;  // store cursor (tile k - 1)
-  bool issuer = false;   // one elected lane of warp 0 (always the same: bulk groups are per thread)
-  if (wid == 0) issuer = elect_one();
-  if (issuer) {
-    for (int k = 0; k < 2 && k < my_tiles; ++k) {
-      issue_load(pb, pt, k);
-      advance(pb, pt);
-    }
+  if (wid == 0 && elect_one()) {
+    for (int k = 0; k < 2 && k < my_tiles; ++k) issue_load(k);
   }
+
+  // tile geometry of the compute loop is advanced incrementally (no integer divisions)
+  const int step_b = grid / tpi, step_t = grid - step_b * tpi;
+  int tb = (int)blockIdx.x / tpi, tt = (int)blockIdx.x - tb * tpi;
 
   const int px0 = tid * 2;
   const int old_cl = min(max(a.old_cl, 1), K);
-  const float u = a.ukd ? 1.f : 0.f;
+  const float u = (STD || a.ukd) ? 1.f : 0.f;
   const float gs_bacs = p.inv_n * a.grad_scale;
   const bool want_grad = a.dlogits != nullptr;
   const bool want_focal = a.gz != nullptr;
   float acc_loss = 0.f, acc_focal = 0.f;
-  uint32_t cnt8 = 0;                               // 8-bit fields: valid | invalid << 8 | bg << 16 | distill << 24
+  uint32_t cnt8 = 0;  // 8-bit fields: valid | invalid << 8 | bg << 16 | distill << 24
   uint32_t n_valid = 0, n_invalid = 0, n_bg = 0, n_dist = 0;
   auto flush_counts = [&]() {
     n_valid += cnt8 & 0xffu;
@@ -182,22 +184,28 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
     gd[0] = ci[0] - g0;
     gd[1] = ci[1] - g0;
   };
-  if (tiles_per_row == 1) set_x(wid * 64);
+  if (tpr1) set_x(wid * 64);
 
   for (int k = 0; k < my_tiles; ++k) {
     const int b = tb, t_in = tt;
-    advance(tb, tt);
+    tb += step_b;
+    tt += step_t;
+    if (tt >= tpi) {
+      tt -= tpi;
+      ++tb;
+    }
     const int s = k & (S - 1);
     T* tile = stage_tile(s);
     const int Yrow = row_of_tile(t_in);
     const Lerp ly_row = lerp_align_corners(Yrow, a.h, p.sy);
-    if (tiles_per_row != 1) set_x((t_in - Yrow * tiles_per_row) * P + wid * 64);
+    if (!tpr1) set_x((t_in - Yrow * tiles_per_row) * P + wid * 64);
 
     // ---- wait for the tile (logit rows + labels + seen-head rows) -------------------------------
     mbar_wait_sleepy(&bar_full[s], (uint32_t)((k >> 2) & 1));
     const longlong2 lab = *reinterpret_cast<const longlong2*>(stage_labels(s) + px0);
 
-    // ---- seen heads of this warp's 64 pixels: y-interpolated strip of (z[c], z[c+1]) pairs ------
+    // ---- seen heads of this warp's 64 pixels: y-interpolated strip, stored per low-res column c as
+    //      (z[c], z[c+1] - z[c]) so that the x-interpolation of a pixel is one LDS.64 + one FFMA ------
     {
       const float* zs = stage_zrows(s);
       const float wy1 = ly_row.w1, wy0 = 1.f - wy1;
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
         const float* zt = zs + (size_t)min(t, TH - 1) * 2 * a.w + col;
         const float v = __fadd_rn(__fmul_rn(wy0, zt[0]), __fmul_rn(wy1, zt[r1]));
         const float vn = __shfl_down_sync(0xffffffffu, v, 1);  // column c+1 (garbage for c == 7: never read)
-        if (t < TH) strip[t * kZCols + c] = make_float2(v, vn);
+        if (t < TH) strip[t * kZCols + c] = make_float2(v, vn - v);
       }
       __syncwarp();
     }
@@ -226,27 +234,29 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
     }
 
     // ---- seen probability (max over heads of the up-sampled logits) and the focal head's logit ----
-    float seen[2], zfoc[2];
+    float seen[2], zfoc[2] = {0.f, 0.f};
+    {
+      const float2* sp0 = strip + ci[0];
+      const float2* sp1 = strip + ci[1];
+      float zm0 = -INFINITY, zm1 = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const float2* sp = strip + ci[j];
-      const float w1 = wx1[j], w0 = 1.f - w1;
-      float zmax = -INFINITY;
-#pragma unroll
-      for (int t = 0; t < 16; ++t) {
+      for (int t = 0; t < 12; ++t) {
         if (t >= TH) break;
-        const float2 v = sp[t * kZCols];
-        zmax = fmaxf(zmax, __fadd_rn(__fmul_rn(w0, v.x), __fmul_rn(w1, v.y)));
+        const float2 v0 = sp0[t * kZCols], v1 = sp1[t * kZCols];
+        zm0 = fmaxf(zm0, fmaf(wx1[0], v0.y, v0.x));
+        zm1 = fmaxf(zm1, fmaf(wx1[1], v1.y, v1.x));
       }
-      for (int t = 16; t < TH; ++t) {
-        const float2 v = sp[t * kZCols];
-        zmax = fmaxf(zmax, __fadd_rn(__fmul_rn(w0, v.x), __fmul_rn(w1, v.y)));
+      for (int t = 12; t < TH; ++t) {
+        const float2 v0 = sp0[t * kZCols], v1 = sp1[t * kZCols];
+        zm0 = fmaxf(zm0, fmaf(wx1[0], v0.y, v0.x));
+        zm1 = fmaxf(zm1, fmaf(wx1[1], v1.y, v1.x));
       }
-      seen[j] = sigmoid_fast(zmax);
-      zfoc[j] = 0.f;
+      seen[0] = rcp_fast(1.f + ex2_fast(-kLog2e * zm0));
+      seen[1] = rcp_fast(1.f + ex2_fast(-kLog2e * zm1));
       if (want_focal) {
-        const float2 v = sp[a.focal_head * kZCols];
-        zfoc[j] = __fadd_rn(__fmul_rn(w0, v.x), __fmul_rn(w1, v.y));
+        const float2 v0 = sp0[a.focal_head * kZCols], v1 = sp1[a.focal_head * kZCols];
+        zfoc[0] = fmaf(wx1[0], v0.y, v0.x);
+        zfoc[1] = fmaf(wx1[1], v1.y, v1.x);
       }
     }
 
@@ -320,12 +330,12 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
       const float lS = lg2_fast(Sa), iS = rcp_fast(Sa);
       const float lF = lg2_fast(Sfg), iF = rcp_fast(Sfg);
       float lO = 0.f, iO = 0.f;
-      if (a.ukd) {  // uniform
+      if (STD || a.ukd) {  // uniform
         lO = lg2_fast(So);
         iO = rcp_fast(So);
       }
       const float sm = seen[j] > a.threshold ? 1.f : seen[j];
-      const float mod = pow_gamma(1.f - sm, a.gamma);
+      const float mod = STD ? (1.f - sm) * (1.f - sm) : pow_gamma(1.f - sm, a.gamma);
       const float m = isbg ? mod : 1.f;
       const float uo = isnew ? 0.f : u;
       const float a1 = m + (isnew ? 1.f : uo);
@@ -347,7 +357,23 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
       gfoc[j] = 0.f;
       if (want_focal) {  // uniform
         float term, dterm;
-        focal_term(a, zfoc[j], isbg ? 0.f : 1.f, term, dterm);
+        if (STD) {
+          // binary focal loss, gamma = 2, target t = foreground: bce = softplus(Z) - t Z, pt = exp(-bce)
+          const float Z = zfoc[j];
+          const float e = ex2_fast(-kLog2e * fabsf(Z));
+          const float d = 1.f + e;
+          const float hi = rcp_fast(d), lo = e * hi;      // sigmoid(|Z|), sigmoid(-|Z|)
+          const float l1p = kLn2 * lg2_fast(d);
+          const bool pos = Z >= 0.f;
+          const float sig = pos ? hi : lo, nsig = pos ? lo : hi;
+          const float pt = isbg ? nsig : sig, om = isbg ? sig : nsig;
+          const float bce = fmaxf(Z, 0.f) - (isbg ? 0.f : Z) + l1p;
+          const float om2 = om * om;
+          term = om2 * bce;
+          dterm = (isbg ? sig : -nsig) * fmaf(2.f * om * pt, bce, om2);
+        } else {
+          focal_term(a, zfoc[j], isbg ? 0.f : 1.f, term, dterm);
+        }
         acc_focal += valid ? term : 0.f;
         gfoc[j] = valid ? dterm : 0.f;
       }
@@ -393,23 +419,22 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
     }
     mbar_arrive(&bar_done[s]);
 
-    // ---- issuing lane: write tile k-1 back, refill the stage of tile k-2 with tile k+2 (both
-    //      conditions were met a whole tile ago, so nothing here blocks) ---------------------------------
-    if (issuer) {
-      if (k >= 1) {
-        mbar_wait(&bar_done[(k - 1) & (S - 1)], (uint32_t)(((k - 1) >> 2) & 1));
-        if (want_grad) {
-          issue_store(sb, st, (k - 1) & (S - 1));
-          advance(sb, st);
-          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        }
+    // ---- tile owners: write tile k-1 back; refill the stage of tile k-2 with tile k+2 ------------------
+    if (k >= 1 && wid == ((k - 1) & 7)) {
+      if (elect_one()) {
+        mbar_wait(&bar_done[(k - 1) & (S - 1)], (uint32_t)(((k - 1) >> 2) & 1));  // gradients of tile k-1 written
+        if (want_grad) issue_store(k - 1);
       }
-      if (k + 2 < my_tiles) {
-        issue_load(pb, pt, (k + 2) & (S - 1));
-        advance(pb, pt);
-      }
+      __syncwarp();
     }
-    __syncwarp();
+    if (wid == ((k + 6) & 7)) {
+      if (elect_one()) {
+        // this lane waited for bar_done of tile k-2 one iteration ago; its store has had a tile to drain
+        if (want_grad) bulk_wait_read0();
+        if (k + 2 < my_tiles) issue_load(k + 2);
+      }
+      __syncwarp();
+    }
 
     // ---- arg-max / mask stores -------------------------------------------------------------------------
     const int64_t pix = (int64_t)b * HW + (int64_t)t_in * P + px0;
@@ -450,11 +475,16 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
     }
     if ((k & 63) == 63) flush_counts();
   }
-  if (issuer && my_tiles > 0) {  // the last tile's gradient rows
+  if (my_tiles > 0) {  // the last tile's gradient rows; every lane that committed bulk stores drains them
     const int kl = my_tiles - 1;
-    mbar_wait(&bar_done[kl & (S - 1)], (uint32_t)((kl >> 2) & 1));
-    if (want_grad) issue_store(sb, st, kl & (S - 1));
-    bulk_wait_all();
+    if (elect_one()) {
+      if (wid == (kl & 7)) {
+        mbar_wait(&bar_done[kl & (S - 1)], (uint32_t)((kl >> 2) & 1));
+        if (want_grad) issue_store(kl);
+      }
+      bulk_wait_all();
+    }
+    __syncwarp();
   }
 
   flush_counts();
@@ -482,7 +512,9 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
 
 template <typename T, int KREG>
 static int launch_wce_one(const PixelParams& p, const PixelPlan& plan, cudaStream_t s) {
-  auto kern = pixel_wce_kernel<T, KREG>;
+  const bacs_pixel_args& a = p.a;
+  const bool std_hp = a.gamma == 2.f && a.ukd && (!a.gz || (a.focal_gamma == 2.f && a.focal_alpha < 0.f));
+  auto kern = std_hp ? pixel_wce_kernel<T, KREG, true> : pixel_wce_kernel<T, KREG, false>;
   if (plan.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) {
