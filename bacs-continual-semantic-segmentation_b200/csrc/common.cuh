@@ -88,6 +88,50 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
   return r;
 }
 
+
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two fp32 results per issued instruction) ----
+// ptxas folds f2b() broadcasts and half swaps into operand modifiers (.F32, .LO_HI), so pairs built
+// from one scalar cost no extra register or move.
+struct F2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ F2 f2(float lo, float hi) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ F2 f2b(float x) { return f2(x, x); }
+__device__ __forceinline__ float f2lo(F2 a) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+  return lo;
+}
+__device__ __forceinline__ float f2hi(F2 a) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+  return hi;
+}
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
+  F2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) {
+  F2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ F2 add2(F2 a, F2 b) {
+  F2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ F2 sub2(F2 a, F2 b) {
+  F2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+
 // fast sigmoid (ex2.approx + rcp.approx, ~2 ulp): used on the bulk feature data
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 // accurate sigmoid (used where a threshold decision depends on it)

@@ -13,6 +13,7 @@
 // This is algebraically identical to the reference and cuts the work per (channel,row) from
 // W pixel evaluations to w cell evaluations (16x fewer for the stride-16 networks).  The
 // centring of tau keeps the fp32 error at the level of the direct evaluation.
+#include <algorithm>
 #include <type_traits>
 
 #include "common.cuh"
@@ -108,8 +109,11 @@ struct Lin {
 };
 __device__ __forceinline__ Lin lin(float v0, float v1) { return Lin{v0, v1 - v0}; }  // v0 at ty=0, v1 at ty=1
 
-__device__ __forceinline__ void dist_mbar_init(uint64_t* bar) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)));
+__device__ __forceinline__ void dist_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void dist_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
 __device__ __forceinline__ void dist_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   const uint32_t b32 = (uint32_t)__cvta_generic_to_shared(bar);
@@ -157,30 +161,42 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T*
                                                                       int w, int H, DistillTables tb,
                                                                       const float* __restrict__ moments, int rows_max,
                                                                       float grad_coef, T* __restrict__ dnew,
-                                                                      double* __restrict__ partials) {
+                                                                      double* __restrict__ partials, int n_groups,
+                                                                      int total_units) {
+  // Work unit = (image b, group of kChanPerCta channels, source-row interval i), flattened in that order.
+  // Every persistent CTA takes one contiguous, equally long range of units, so the SMs stay evenly loaded
+  // whatever B*A is.  A range that starts inside an image first replays the interval above it ("halo") to
+  // obtain the gradient that interval sends down to the range's first source row.
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int b = blockIdx.y;
-  const int ch0 = blockIdx.x * kChanPerCta + wid * kChanPerWarp;
   const bool want_grad = dnew != nullptr;
-  // dynamic smem: 2 x [rows_max][5][WP] moment buffers (columns zero-padded to WP) | ty[H]
+  const int u0 = (int)((int64_t)blockIdx.x * total_units / gridDim.x);
+  const int u1 = (int)((int64_t)(blockIdx.x + 1) * total_units / gridDim.x);
+  const int ustart = u0 - ((want_grad && (u0 % h) != 0) ? 1 : 0);
+  // dynamic smem: 3 x [rows_max][5][WP] moment buffers (columns zero-padded to WP) | ty[H] | rowstart[h+1]
   extern __shared__ __align__(16) float s_dyn[];
   __shared__ double red_scratch[32];
-  __shared__ uint64_t mom_bar[2];
+  __shared__ uint64_t mom_bar[3];   // moments of an interval have landed (TMA expect-tx)
+  __shared__ uint64_t free_bar[3];  // all warps are done with the buffer
   constexpr int WP = 32 * CPL;
   constexpr int NC = kChanPerWarp;
   constexpr unsigned kFull = 0xffffffffu;
   const size_t mom_stride = (size_t)rows_max * 5 * WP;
-  float* s_ty = s_dyn + 2 * mom_stride;
+  float* s_ty = s_dyn + 3 * mom_stride;
+  int* s_rowstart = reinterpret_cast<int*>(s_ty + H);
   const bool bulk_ok = (w == WP);  // contiguous rows -> one TMA bulk copy per interval
   for (int k = threadIdx.x; k < H; k += blockDim.x) s_ty[k] = tb.ywt[k];
+  for (int k = threadIdx.x; k <= h; k += blockDim.x) s_rowstart[k] = tb.rowstart[k];
   if (threadIdx.x == 0) {
-    dist_mbar_init(&mom_bar[0]);
-    dist_mbar_init(&mom_bar[1]);
+    for (int k = 0; k < 3; ++k) {
+      dist_mbar_init(&mom_bar[k], 1);
+      dist_mbar_init(&free_bar[k], kDistillWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  auto stage_moments = [&](int i, int buf) {  // moments of the rows of interval i -> buffer buf
-    const int Y0 = tb.rowstart[i], nr = tb.rowstart[i + 1] - Y0;
+  auto stage_moments = [&](int un, int buf) {  // moments of the rows of unit un -> buffer buf
+    const int g = un / h, i = un - g * h, b = g / n_groups;
+    const int Y0 = s_rowstart[i], nr = s_rowstart[i + 1] - Y0;
     const float* src = moments + ((int64_t)b * H + Y0) * 5 * w;
     float* dst = s_dyn + buf * mom_stride;
     if (bulk_ok) {
@@ -194,16 +210,18 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T*
     }
   };
 
-  // attention values of this lane's column(s): upper source row of the current interval (prev) and
-  // the row after it (nxt, fetched one interval ahead); the right neighbour comes by shuffle
-  float o_prev[NC][CPL], n_prev[NC][CPL], o_nxt[NC][CPL], n_nxt[NC][CPL];
+  // attention values of this lane's column(s): upper source row of the current interval (prev) and, still in
+  // storage precision, the row after it (nxt): it is fetched one interval ahead and only converted when it
+  // becomes the current row, so the loads have a whole interval to land.  The right neighbour comes by shuffle.
+  float o_prev[NC][CPL], n_prev[NC][CPL];
+  T o_nxt[NC][CPL], n_nxt[NC][CPL];
   float carry[NC][CPL];  // gradient already collected for the upper row by the interval above
   float loss_acc = 0.f;
-  auto load_row = [&](const T* base, int ch, int row, float* v) {
+  auto load_row = [&](const T* base, int b, int ch, int row, T* v) {
 #pragma unroll
     for (int m = 0; m < CPL; ++m) {
       const int j = lane + 32 * m;
-      v[m] = (j < w && ch < A) ? DT<T>::to_f(base[(((int64_t)b * A + ch) * h + row) * w + j]) : 0.f;
+      v[m] = (j < w && ch < A) ? base[(((int64_t)b * A + ch) * h + row) * w + j] : DT<T>::from_f(0.f);
     }
   };
   // value of column j+1 (the last column is its own right neighbour)
@@ -216,28 +234,47 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T*
       v1[m] = (j >= w - 1) ? v[m] : (lane == 31 ? wrap : dn);
     }
   };
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    load_row(old_att, ch0 + c, 0, o_prev[c]);
-    load_row(new_att, ch0 + c, 0, n_prev[c]);
-    load_row(old_att, ch0 + c, min(1, h - 1), o_nxt[c]);
-    load_row(new_att, ch0 + c, min(1, h - 1), n_nxt[c]);
-#pragma unroll
-    for (int m = 0; m < CPL; ++m) carry[c][m] = 0.f;
-  }
-  stage_moments(0, 0);
+  if (u0 < u1) stage_moments(ustart, 0);
+  if (!bulk_ok) __syncthreads();
 
-  for (int i = 0; i < h; ++i) {
-    const int Y0 = tb.rowstart[i], Y1 = tb.rowstart[i + 1];
+  for (int un = ustart, k = 0; un < u1; ++un, ++k) {
+    const int g = un / h, i = un - g * h;
+    const int b = g / n_groups;
+    const int ch0 = (g - b * n_groups) * kChanPerCta + wid * kChanPerWarp;
+    const bool halo = un < u0;  // replayed for the gradient it sends down only: no loss, no dnew row
+    const int Y0 = s_rowstart[i], Y1 = s_rowstart[i + 1];
     const int nrows = Y1 - Y0;
     const int row1 = min(i + 1, h - 1);
-    const int buf = i & 1;
+    const int buf = k % 3;
     const float* s_mom = s_dyn + buf * mom_stride;
-    // every warp is done with buffer buf^1 (interval i-1): refill it with interval i+1
-    __syncthreads();
-    if (i + 1 < h) stage_moments(i + 1, buf ^ 1);
-    if (bulk_ok) dist_mbar_wait(&mom_bar[buf], (uint32_t)((i >> 1) & 1));
-    else if (i == 0) __syncthreads();
+    const float loss_before = loss_acc;
+    // Unit k+1 goes into the buffer unit k-2 used: its readers had a whole unit to finish, so the staging
+    // thread practically never waits and no CTA-wide barrier is needed.
+    if (bulk_ok) {
+      if (threadIdx.x == 0 && un + 1 < u1) {
+        if (k >= 2) dist_mbar_wait(&free_bar[(k + 1) % 3], (uint32_t)(((k - 2) / 3) & 1));
+        stage_moments(un + 1, (k + 1) % 3);
+      }
+      __syncwarp();
+      dist_mbar_wait(&mom_bar[buf], (uint32_t)((k / 3) & 1));
+    } else {
+      if (un + 1 < u1) stage_moments(un + 1, (k + 1) % 3);  // for the NEXT unit; published by the barrier below
+    }
+    if (k == 0 || i == 0) {  // first unit of a (image, channel group) segment: fetch its two source rows
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        load_row(old_att, b, ch0 + c, i, o_nxt[c]);
+        load_row(new_att, b, ch0 + c, i, n_nxt[c]);
+#pragma unroll
+        for (int m = 0; m < CPL; ++m) {
+          o_prev[c][m] = DT<T>::to_f(o_nxt[c][m]);
+          n_prev[c][m] = DT<T>::to_f(n_nxt[c][m]);
+          carry[c][m] = 0.f;
+        }
+        load_row(old_att, b, ch0 + c, row1, o_nxt[c]);
+        load_row(new_att, b, ch0 + c, row1, n_nxt[c]);
+      }
+    }
 
     Lin alpha[NC][CPL], sigma[NC][CPL], delta[NC][CPL], eps[NC][CPL];
     float GA0[NC][CPL], GA1[NC][CPL], GD0[NC][CPL], GD1[NC][CPL];
@@ -246,12 +283,12 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T*
       float o_cur[CPL], n_cur[CPL], o_p1[CPL], n_p1[CPL], o_c1[CPL], n_c1[CPL];
 #pragma unroll
       for (int m = 0; m < CPL; ++m) {
-        o_cur[m] = row1 != i ? o_nxt[c][m] : o_prev[c][m];
-        n_cur[m] = row1 != i ? n_nxt[c][m] : n_prev[c][m];
+        o_cur[m] = row1 != i ? DT<T>::to_f(o_nxt[c][m]) : o_prev[c][m];
+        n_cur[m] = row1 != i ? DT<T>::to_f(n_nxt[c][m]) : n_prev[c][m];
       }
       if (i + 2 < h) {  // prefetch the row of the interval after the next one
-        load_row(old_att, ch0 + c, i + 2, o_nxt[c]);
-        load_row(new_att, ch0 + c, i + 2, n_nxt[c]);
+        load_row(old_att, b, ch0 + c, i + 2, o_nxt[c]);
+        load_row(new_att, b, ch0 + c, i + 2, n_nxt[c]);
       }
       right(o_prev[c], o_p1);
       right(n_prev[c], n_p1);
@@ -274,80 +311,162 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T*
       }
     }
 
-    // rows are processed RB at a time (RB independent dependency chains per warp: shared-memory
-    // loads -> FMAs -> 5-step shuffle reduction -> rsqrt); a 1-row tail handles odd counts
-    auto process_rows = [&](auto rb_tag, const float* mrow, const float* tyrow) {
-      constexpr int RB = decltype(rb_tag)::value;
-      float ty[RB];
-      float u0[RB][NC][CPL], u1[RB][NC][CPL], u2[RB][NC][CPL], va2[RB][NC][CPL], vd2[RB][NC][CPL], S[RB][NC];
+    // Rows are processed four at a time as two PAIRS of adjacent rows: every fp32 operation of a pair is one
+    // packed instruction (FFMA2 / FMUL2 / FADD2), with the channel's coefficients as broadcast operands and
+    // the rows' moments / weights in the two halves.  A 1-row scalar tail handles the remaining rows.
+    F2 GA0p[NC][CPL], GA1p[NC][CPL], GD0p[NC][CPL], GD1p[NC][CPL];  // halves: even / odd row of the pair
 #pragma unroll
-      for (int q = 0; q < RB; ++q) {
-        ty[q] = tyrow[q];
-        const float* mr = mrow + q * 5 * WP;
-        float M0[CPL], M1[CPL], M2[CPL], M3[CPL], M4[CPL];
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int m = 0; m < CPL; ++m) GA0p[c][m] = GA1p[c][m] = GD0p[c][m] = GD1p[c][m] = f2b(0.f);
+    auto process_pairs = [&](const float* mrow, const float* tyrow) {
+      constexpr int RP = 2;
+      F2 ty2[RP];
+      F2 u0[RP][NC][CPL], u1[RP][NC][CPL], u2[RP][NC][CPL], va2[RP][NC][CPL], vd2[RP][NC][CPL], S[RP][NC];
+#pragma unroll
+      for (int q = 0; q < RP; ++q) {
+        ty2[q] = f2(tyrow[2 * q], tyrow[2 * q + 1]);
+        const float* mra = mrow + (2 * q) * 5 * WP;
+        const float* mrb = mra + 5 * WP;
+        F2 M0[CPL], M1[CPL], M2[CPL], M3[CPL], M4[CPL];
 #pragma unroll
         for (int m = 0; m < CPL; ++m) {
-          M0[m] = mr[32 * m];
-          M1[m] = mr[WP + 32 * m];
-          M2[m] = mr[2 * WP + 32 * m];
-          M3[m] = mr[3 * WP + 32 * m];
-          M4[m] = mr[4 * WP + 32 * m];
+          M0[m] = f2(mra[32 * m], mrb[32 * m]);
+          M1[m] = f2(mra[WP + 32 * m], mrb[WP + 32 * m]);
+          M2[m] = f2(mra[2 * WP + 32 * m], mrb[2 * WP + 32 * m]);
+          M3[m] = f2(mra[3 * WP + 32 * m], mrb[3 * WP + 32 * m]);
+          M4[m] = f2(mra[4 * WP + 32 * m], mrb[4 * WP + 32 * m]);
         }
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
 #pragma unroll
           for (int m = 0; m < CPL; ++m) {
-            const float al = alpha[c][m].at(ty[q]), sg = sigma[c][m].at(ty[q]);
-            const float de = delta[c][m].at(ty[q]), ep = eps[c][m].at(ty[q]);
-            va2[q][c][m] = sg - al;  // 2 a_n
-            vd2[q][c][m] = ep - de;  // 2 d_n
-            const float c0 = al * sg;
-            const float c1 = fmaf(al, ep, de * sg);
-            const float c2 = de * ep;
-            u0[q][c][m] = fmaf(c2, M2[m], fmaf(c1, M1[m], c0 * M0[m]));
-            u1[q][c][m] = fmaf(c2, M3[m], fmaf(c1, M2[m], c0 * M1[m]));
-            u2[q][c][m] = fmaf(c2, M4[m], fmaf(c1, M3[m], c0 * M2[m]));
-            const float sc = fmaf(c2, u2[q][c][m], fmaf(c1, u1[q][c][m], c0 * u0[q][c][m]));
-            S[q][c] = m == 0 ? sc : S[q][c] + sc;
+            const F2 al = fma2(f2b(alpha[c][m].q), ty2[q], f2b(alpha[c][m].p));
+            const F2 sg = fma2(f2b(sigma[c][m].q), ty2[q], f2b(sigma[c][m].p));
+            const F2 de = fma2(f2b(delta[c][m].q), ty2[q], f2b(delta[c][m].p));
+            const F2 ep = fma2(f2b(eps[c][m].q), ty2[q], f2b(eps[c][m].p));
+            va2[q][c][m] = sub2(sg, al);  // 2 a_n
+            vd2[q][c][m] = sub2(ep, de);  // 2 d_n
+            const F2 c0 = mul2(al, sg);
+            const F2 c1 = fma2(al, ep, mul2(de, sg));
+            const F2 c2 = mul2(de, ep);
+            u0[q][c][m] = fma2(c2, M2[m], fma2(c1, M1[m], mul2(c0, M0[m])));
+            u1[q][c][m] = fma2(c2, M3[m], fma2(c1, M2[m], mul2(c0, M1[m])));
+            u2[q][c][m] = fma2(c2, M4[m], fma2(c1, M3[m], mul2(c0, M2[m])));
+            const F2 sc = fma2(c2, u2[q][c][m], fma2(c1, u1[q][c][m], mul2(c0, u0[q][c][m])));
+            S[q][c] = m == 0 ? sc : add2(S[q][c], sc);
           }
         }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int q = 0; q < RB; ++q)
+        for (int q = 0; q < RP; ++q)
 #pragma unroll
-          for (int c = 0; c < NC; ++c) S[q][c] += __shfl_xor_sync(kFull, S[q][c], o);
+          for (int c = 0; c < NC; ++c) {
+            F2 other;
+            other.v = __shfl_xor_sync(kFull, S[q][c].v, o);
+            S[q][c] = add2(S[q][c], other);
+          }
       }
 #pragma unroll
-      for (int q = 0; q < RB; ++q) {
+      for (int q = 0; q < RP; ++q) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           // zero (or rounding-negative) row: norm 0 and sub-gradient 0, as torch's norm backward
-          const float rs = S[q][c] > 0.f ? rsqrt_fast(S[q][c]) : 0.f;
-          loss_acc = fmaf(S[q][c], rs, loss_acc);
+          const float sa = f2lo(S[q][c]), sb = f2hi(S[q][c]);
+          const float rsa = sa > 0.f ? rsqrt_fast(sa) : 0.f;
+          const float rsb = sb > 0.f ? rsqrt_fast(sb) : 0.f;
+          loss_acc = fmaf(sa, rsa, loss_acc);
+          loss_acc = fmaf(sb, rsb, loss_acc);
           if (want_grad) {
+            const F2 rs = f2(rsa, rsb);
+            const F2 rst = mul2(rs, ty2[q]);
 #pragma unroll
             for (int m = 0; m < CPL; ++m) {
-              const float gA = rs * fmaf(u1[q][c][m], vd2[q][c][m], u0[q][c][m] * va2[q][c][m]);
-              const float gD = rs * fmaf(u2[q][c][m], vd2[q][c][m], u1[q][c][m] * va2[q][c][m]);
-              GA0[c][m] += gA;
-              GA1[c][m] = fmaf(gA, ty[q], GA1[c][m]);
-              GD0[c][m] += gD;
-              GD1[c][m] = fmaf(gD, ty[q], GD1[c][m]);
+              const F2 xA = fma2(u1[q][c][m], vd2[q][c][m], mul2(u0[q][c][m], va2[q][c][m]));
+              const F2 xD = fma2(u2[q][c][m], vd2[q][c][m], mul2(u1[q][c][m], va2[q][c][m]));
+              GA0p[c][m] = fma2(rs, xA, GA0p[c][m]);
+              GA1p[c][m] = fma2(rst, xA, GA1p[c][m]);
+              GD0p[c][m] = fma2(rs, xD, GD0p[c][m]);
+              GD1p[c][m] = fma2(rst, xD, GD1p[c][m]);
             }
           }
         }
       }
     };
+    auto process_row = [&](const float* mr, float ty) {
+      float M0[CPL], M1[CPL], M2[CPL], M3[CPL], M4[CPL];
+      float u0[NC][CPL], u1[NC][CPL], u2[NC][CPL], va2[NC][CPL], vd2[NC][CPL], S[NC];
+#pragma unroll
+      for (int m = 0; m < CPL; ++m) {
+        M0[m] = mr[32 * m];
+        M1[m] = mr[WP + 32 * m];
+        M2[m] = mr[2 * WP + 32 * m];
+        M3[m] = mr[3 * WP + 32 * m];
+        M4[m] = mr[4 * WP + 32 * m];
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+#pragma unroll
+        for (int m = 0; m < CPL; ++m) {
+          const float al = alpha[c][m].at(ty), sg = sigma[c][m].at(ty);
+          const float de = delta[c][m].at(ty), ep = eps[c][m].at(ty);
+          va2[c][m] = sg - al;
+          vd2[c][m] = ep - de;
+          const float c0 = al * sg;
+          const float c1 = fmaf(al, ep, de * sg);
+          const float c2 = de * ep;
+          u0[c][m] = fmaf(c2, M2[m], fmaf(c1, M1[m], c0 * M0[m]));
+          u1[c][m] = fmaf(c2, M3[m], fmaf(c1, M2[m], c0 * M1[m]));
+          u2[c][m] = fmaf(c2, M4[m], fmaf(c1, M3[m], c0 * M2[m]));
+          const float sc = fmaf(c2, u2[c][m], fmaf(c1, u1[c][m], c0 * u0[c][m]));
+          S[c] = m == 0 ? sc : S[c] + sc;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) S[c] += __shfl_xor_sync(kFull, S[c], o);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const float rs = S[c] > 0.f ? rsqrt_fast(S[c]) : 0.f;
+        loss_acc = fmaf(S[c], rs, loss_acc);
+        if (want_grad) {
+#pragma unroll
+          for (int m = 0; m < CPL; ++m) {
+            const float gA = rs * fmaf(u1[c][m], vd2[c][m], u0[c][m] * va2[c][m]);
+            const float gD = rs * fmaf(u2[c][m], vd2[c][m], u1[c][m] * va2[c][m]);
+            GA0[c][m] += gA;
+            GA1[c][m] = fmaf(gA, ty, GA1[c][m]);
+            GD0[c][m] += gD;
+            GD1[c][m] = fmaf(gD, ty, GD1[c][m]);
+          }
+        }
+      }
+    };
     {
-      constexpr int RBM = BACS_DISTILL_RB;
       const float* mrow = s_mom + lane;  // moments of the current row, this lane's column
       const float* tyrow = s_ty + Y0;
       int r0 = 0;
-      for (; r0 + RBM <= nrows; r0 += RBM, mrow += RBM * 5 * WP, tyrow += RBM)
-        process_rows(std::integral_constant<int, RBM>{}, mrow, tyrow);
-      for (; r0 < nrows; ++r0, mrow += 5 * WP, ++tyrow) process_rows(std::integral_constant<int, 1>{}, mrow, tyrow);
+      for (; r0 + 4 <= nrows; r0 += 4, mrow += 4 * 5 * WP, tyrow += 4) process_pairs(mrow, tyrow);
+      for (; r0 < nrows; ++r0, mrow += 5 * WP, ++tyrow) process_row(mrow, *tyrow);
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int m = 0; m < CPL; ++m) {
+          GA0[c][m] += f2lo(GA0p[c][m]) + f2hi(GA0p[c][m]);
+          GA1[c][m] += f2lo(GA1p[c][m]) + f2hi(GA1p[c][m]);
+          GD0[c][m] += f2lo(GD0p[c][m]) + f2hi(GD0p[c][m]);
+          GD1[c][m] += f2lo(GD1p[c][m]) + f2hi(GD1p[c][m]);
+        }
+    }
+
+    if (bulk_ok) {
+      __syncwarp();
+      if (lane == 0) dist_mbar_arrive(&free_bar[buf]);  // this warp is done with the interval's moments
+    } else {
+      __syncthreads();
     }
 
     if (want_grad) {
@@ -390,16 +509,17 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T*
           const int j = lane + 32 * m;
           float fin = carry[c][m] + g0[m];
           if (row1 == i) fin += g1[m];
-          if (j < w && ch < A) dnew[(((int64_t)b * A + ch) * h + i) * w + j] = DT<T>::from_f(grad_coef * fin);
+          if (!halo && j < w && ch < A) dnew[(((int64_t)b * A + ch) * h + i) * w + j] = DT<T>::from_f(grad_coef * fin);
           carry[c][m] = g1[m];
         }
       }
     }
+    if (halo) loss_acc = loss_before;
   }
   // every lane holds the same loss_acc (the shuffle reduction broadcasts); count it once per warp
   const double mine = (lane == 0) ? (double)loss_acc : 0.0;
   const double tot = block_sum(mine, red_scratch);
-  if (threadIdx.x == 0) partials[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
+  if (threadIdx.x == 0) partials[blockIdx.x] = tot;
 }
 
 __global__ void __launch_bounds__(1024) sum_partials_kernel(const double* __restrict__ partials, int n,
@@ -431,7 +551,7 @@ static DistillLayout distill_layout(int B, int A, int h, int w, int H, int W) {
   l.off_colstart = take(sizeof(int) * (w + 1));
   l.off_moments = take(sizeof(float) * (size_t)B * H * 5 * w);
   l.n_cta_x = (A + kChanPerCta - 1) / kChanPerCta;
-  l.off_partials = take(sizeof(double) * (size_t)B * l.n_cta_x);
+  l.off_partials = take(sizeof(double) * (size_t)std::max(2 * sm_count(), 1024));
   l.total = o;
   return l;
 }
@@ -483,12 +603,17 @@ int bacs_teacher_distill(const void* old_att, const void* new_att, int dtype, in
   // an interval holds the rows whose source row is i: at most ceil(H/h) + ceil(H/(2h)) + 2
   const int rows_max = (H + h - 1) / h + (H + 2 * h - 1) / (2 * h) + 2;
   const int wp = w <= 32 ? 32 : (w <= 64 ? 64 : 128);
-  const size_t smem = sizeof(float) * ((size_t)2 * rows_max * 5 * wp + H);
+  const size_t smem = sizeof(float) * ((size_t)3 * rows_max * 5 * wp + H + h + 4);
   if (smem > 200 * 1024) {
     set_error("bacs_teacher_distill: up-sampling ratio too large for the shared-memory moment tile");
     return BACS_ERR_UNSUPPORTED;
   }
-  dim3 grid(l.n_cta_x, B);
+  const int64_t total_units = (int64_t)B * l.n_cta_x * h;
+  if (total_units > 0x3fffffff) {
+    set_error("bacs_teacher_distill: problem too large");
+    return BACS_ERR_UNSUPPORTED;
+  }
+  const int grid = (int)std::min<int64_t>(total_units, 2 * sm_count());
 #define LAUNCH_DISTILL(TT, CPL)                                                                                   \
   do {                                                                                                            \
     auto kern = distill_kernel<TT, CPL>;                                                                          \
@@ -501,7 +626,8 @@ int bacs_teacher_distill(const void* old_att, const void* new_att, int dtype, in
     }                                                                                                             \
     kern<<<grid, 32 * kDistillWarps, smem, s>>>(reinterpret_cast<const TT*>(old_att),                            \
                                                 reinterpret_cast<const TT*>(new_att), A, h, w, H, tb, moments,   \
-                                                rows_max, grad_coef, reinterpret_cast<TT*>(dnew), partials);     \
+                                                rows_max, grad_coef, reinterpret_cast<TT*>(dnew), partials,      \
+                                                l.n_cta_x, (int)total_units);                                     \
   } while (0)
   BACS_DISPATCH_DTYPE(dtype, TT, {
     if (w <= 32) LAUNCH_DISTILL(TT, 1);
@@ -510,7 +636,7 @@ int bacs_teacher_distill(const void* old_att, const void* new_att, int dtype, in
   });
 #undef LAUNCH_DISTILL
   BACS_CHECK_LAUNCH("bacs_teacher_distill");
-  sum_partials_kernel<<<1, 1024, 0, s>>>(partials, B * l.n_cta_x, loss_sum);
+  sum_partials_kernel<<<1, 1024, 0, s>>>(partials, grid, loss_sum);
   BACS_CHECK_LAUNCH("bacs_teacher_distill(reduce)");
   return BACS_OK;
 }
