@@ -75,6 +75,107 @@ __global__ void __launch_bounds__(32 * kAccWarps) proto_accumulate_kernel(const 
   }
 }
 
+// Vectorised variant (hw a multiple of 8, 16-byte aligned rows): a lane handles 8 consecutive pixels per step.
+// The 8 task bytes are read first; feature and rank vectors are only fetched for groups that hold at least one
+// foreground pixel (labels are blocky: most groups of 8 are all background / ignore), and all of a row's
+// loads are in flight together.  The per-warp table has 33-float rows so that the final column sums are
+// conflict-free.
+template <typename T>
+__global__ void __launch_bounds__(32 * kAccWarps) proto_accumulate_vec_kernel(const T* __restrict__ feat, int B, int D,
+                                                                              int hw, const int8_t* __restrict__ task,
+                                                                              const int32_t* __restrict__ rank,
+                                                                              const int32_t* __restrict__ n_bt, int Tn,
+                                                                              int mode, float* __restrict__ partial) {
+  extern __shared__ float s_acc[];  // [warp][Tn*2][33] | [warp][32] split points
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * kAccWarps + wid;
+  if (c >= D) return;
+  const int ne = Tn * 2;
+  float* acc = s_acc + (size_t)wid * ne * 33;
+  int* s_split = reinterpret_cast<int*>(s_acc + (size_t)kAccWarps * ne * 33) + wid * 32;
+  for (int i = lane; i < ne * 33; i += 32) acc[i] = 0.f;
+  int split = 0x7fffffff;
+  if (mode == 0 && lane < Tn) {
+    long long pre = 0, tot = 0;
+    for (int bb = 0; bb < B; ++bb) {
+      const int n = n_bt[bb * Tn + lane];
+      if (bb < b) pre += n;
+      tot += n;
+    }
+    const long long nb = n_bt[b * Tn + lane];
+    if (tot > 0) {
+      const long long base = (long long)D * pre + (long long)c * nb;
+      const long long r0 = base / tot;
+      const long long sp = (r0 + 1) * tot - base;
+      split = sp > 0x7fffffffLL ? 0x7fffffff : (int)sp;
+    }
+  }
+  s_split[lane] = split;
+  __syncwarp();
+  const T* row = feat + ((int64_t)b * D + c) * hw;
+  const int8_t* tk = task + (int64_t)b * hw;
+  const int32_t* rk = rank + (int64_t)b * hw;
+  const int items = hw >> 3;
+  constexpr int U = 4;
+  for (int it0 = 0; it0 < items; it0 += 32 * U) {
+    uint2 t8[U];
+    bool any[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int it = it0 + u * 32 + lane;
+      t8[u] = it < items ? *reinterpret_cast<const uint2*>(tk + it * 8) : make_uint2(0xffffffffu, 0xffffffffu);
+      any[u] = ((~t8[u].x | ~t8[u].y) & 0x80808080u) != 0u;  // some byte is >= 0
+    }
+    constexpr int NV = sizeof(T) == 4 ? 2 : 1;  // 16-byte vectors per 8 pixels
+    uint4 raw[U][NV];
+    int4 r0[U], r1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int it = it0 + u * 32 + lane;
+      r0[u] = r1[u] = make_int4(0, 0, 0, 0);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) raw[u][k] = make_uint4(0u, 0u, 0u, 0u);
+      if (any[u]) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) raw[u][k] = reinterpret_cast<const uint4*>(row + it * 8)[k];
+        if (mode == 0) {
+          r0[u] = *reinterpret_cast<const int4*>(rk + it * 8);
+          r1[u] = *reinterpret_cast<const int4*>(rk + it * 8 + 4);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (any[u]) {
+        const int rr[8] = {r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, r1[u].z, r1[u].w};
+        const T* e8 = reinterpret_cast<const T*>(&raw[u][0]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int t = (int)(int8_t)((e < 4 ? t8[u].x >> (8 * e) : t8[u].y >> (8 * (e - 4))) & 0xffu);
+          if (t >= 0) {
+            const int hi = rr[e] < s_split[t] ? 0 : 1;
+            acc[(t * 2 + hi) * 33 + lane] += DT<T>::to_f(e8[e]);
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  float* out = partial + (((int64_t)b * D + c) * Tn) * 2;
+  // column sums: lane (e, half) adds 16 of the 32 lane slots of entry e
+  for (int e0 = 0; e0 < ne; e0 += 16) {
+    const int e = e0 + (lane & 15), half = lane >> 4;
+    float sacc = 0.f;
+    if (e < ne) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) sacc += acc[e * 33 + half * 16 + k];
+    }
+    sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
+    if (half == 0 && e < ne) out[e] = sacc;
+  }
+}
+
 // One block per task g; thread r gathers the partial runs that land in output row r.
 // Image b's masked elements occupy flat positions [D*pre_b, D*(pre_b+n_b)), i.e. rows
 // lo_b .. hi_b of the D x N_g view; row r only looks at images with lo_b <= r <= hi_b + 1.
@@ -92,13 +193,13 @@ __global__ void __launch_bounds__(kFinRows* kFinLanes) proto_finalize_kernel(con
   __shared__ double s_red[kFinLanes][kFinRows];
   const int g = blockIdx.x;
   const int tid = threadIdx.x;
+  for (int bb = tid; bb < B; bb += blockDim.x) s_nb[bb] = n_bt[bb * Tn + g];  // parallel loads, serial scan below
+  __syncthreads();
   if (tid == 0) {
     long long run = 0;
     for (int bb = 0; bb < B; ++bb) {
-      const int n = n_bt[bb * Tn + g];
       s_pre[bb] = run;
-      s_nb[bb] = n;
-      run += n;
+      run += s_nb[bb];
     }
     s_tot = run;
     if (blockIdx.y == 0) counts[g] = (double)run;
@@ -223,9 +324,25 @@ int bacs_proto_accumulate(const void* features, int dtype, int B, int D, int h, 
   const int hw = h * w;
   dim3 grid((D + kAccWarps - 1) / kAccWarps, B);
   const size_t acc_smem = (size_t)kAccWarps * T * 64 * sizeof(float);
+  const size_t vec_smem = (size_t)kAccWarps * (T * 2 * 33 + 32) * sizeof(float);
+  const bool vec = hw % 8 == 0 && (reinterpret_cast<uintptr_t>(features) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(task) & 7) == 0 && (reinterpret_cast<uintptr_t>(rank) & 15) == 0;
   BACS_DISPATCH_DTYPE(dtype, TT, {
-    proto_accumulate_kernel<TT><<<grid, 32 * kAccWarps, acc_smem, s>>>(reinterpret_cast<const TT*>(features), B, D, hw,
-                                                                       task, rank, n_bt, T, mode, partial);
+    if (vec) {
+      auto kern = proto_accumulate_vec_kernel<TT>;
+      if (vec_smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vec_smem);
+        if (e != cudaSuccess) {
+          set_error("bacs_proto_accumulate: shared memory opt-in failed: %s", cudaGetErrorString(e));
+          return BACS_ERR_CUDA;
+        }
+      }
+      kern<<<grid, 32 * kAccWarps, vec_smem, s>>>(reinterpret_cast<const TT*>(features), B, D, hw, task, rank, n_bt, T,
+                                                  mode, partial);
+    } else {
+      proto_accumulate_kernel<TT><<<grid, 32 * kAccWarps, acc_smem, s>>>(reinterpret_cast<const TT*>(features), B, D,
+                                                                         hw, task, rank, n_bt, T, mode, partial);
+    }
   });
   BACS_CHECK_LAUNCH("bacs_proto_accumulate");
   proto_finalize_kernel<<<dim3(T, (D + kFinRows - 1) / kFinRows), kFinRows * kFinLanes, 0, s>>>(partial, B, D, n_bt, T,

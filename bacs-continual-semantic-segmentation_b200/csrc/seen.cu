@@ -3,92 +3,161 @@
 //              100-165 (get_seen_map_task, forward_seen_before, get_seen_probs)
 // z[b,t,q] = bias_t + sum_c w[t,c] * |sigmoid(f[b,c,q]) - sigmoid(proto[t,c])|
 // A weighted L1 distance per task head: HBM/ALU work, no GEMM form.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace bacs {
 
 constexpr int kSeenWarps = 8;
-constexpr int kSeenPix = 2;  // pixels per thread: the per-channel weights are fetched once for all of them
 
-// block = 32 lanes x 8 channel groups; a block covers 128 consecutive pixels of one image
-template <typename T, int TMAX>
-__global__ void __launch_bounds__(32 * kSeenWarps) seen_logits_kernel(const T* __restrict__ feat, int D, int hw,
+// PX consecutive pixels of one channel row as one (up to 16-byte) register vector, converted at the point of use
+template <int BYTES> struct RawVec;
+template <> struct RawVec<2> { using type = uint16_t; };
+template <> struct RawVec<4> { using type = uint32_t; };
+template <> struct RawVec<8> { using type = uint2; };
+template <> struct RawVec<16> { using type = uint4; };
+template <typename T, int PX>
+__device__ __forceinline__ void unpack_px(const typename RawVec<sizeof(T) * PX>::type& r, float* v) {
+  const T* e = reinterpret_cast<const T*>(&r);
+#pragma unroll
+  for (int i = 0; i < PX; ++i) v[i] = DT<T>::to_f(e[i]);
+}
+
+template <typename T, int PX>
+__device__ __forceinline__ void load_px(const T* p, float* v) {
+  if constexpr (PX == 1) {
+    v[0] = DT<T>::to_f(p[0]);
+  } else if constexpr (sizeof(T) == 4) {
+    if constexpr (PX == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(p);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+      const float2 t = *reinterpret_cast<const float2*>(p);
+      v[0] = t.x; v[1] = t.y;
+    }
+  } else {
+    if constexpr (PX == 4) {
+      const uint2 t = *reinterpret_cast<const uint2*>(p);
+      const T* e = reinterpret_cast<const T*>(&t);
+      v[0] = DT<T>::to_f(e[0]); v[1] = DT<T>::to_f(e[1]); v[2] = DT<T>::to_f(e[2]); v[3] = DT<T>::to_f(e[3]);
+    } else {
+      const uint32_t t = *reinterpret_cast<const uint32_t*>(p);
+      const T* e = reinterpret_cast<const T*>(&t);
+      v[0] = DT<T>::to_f(e[0]); v[1] = DT<T>::to_f(e[1]);
+    }
+  }
+}
+
+// A CTA covers 32*PX consecutive pixels of one image (lane -> PX adjacent pixels, one vector load per channel
+// row) and a slice of the channels; its 8 warps stride over the slice.  The CS CTAs of a thread-block cluster
+// split the channels and the leader adds their partial sums through distributed shared memory, so the grid
+// has enough CTAs to fill the machine while the summation order stays fixed.
+// Per channel the T (weight, sigmoid(proto)) pairs sit in one shared-memory row read with broadcast 128-bit loads.
+template <typename T, int TMAX, int PX>
+__global__ void __launch_bounds__(32 * kSeenWarps, (TMAX <= 8 ? 3 : 1)) seen_logits_kernel(const T* __restrict__ feat, int D, int hw,
                                                                        const float* __restrict__ proto,
                                                                        const float* __restrict__ weight,
                                                                        const float* __restrict__ bias, int Tn,
-                                                                       int chunk, float* __restrict__ z) {
-  extern __shared__ float smem[];
-  float* s_sp = smem;              // [chunk][Tn] sigmoid(proto)   (head index fastest: one row per channel)
-  float* s_w = smem + Tn * chunk;  // [chunk][Tn]
-  const int lane = threadIdx.x, cg = threadIdx.y;
+                                                                       int chunk, int cs, float* __restrict__ z) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int PS = 32 * PX;            // pixels per CTA
+  constexpr int stride = 2 * TMAX;       // floats per channel row: w[0..TMAX) | sigmoid(proto)[0..TMAX)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tid = threadIdx.x;
+  const int rank = (int)blockIdx.x % cs, pb = (int)blockIdx.x / cs;
   const int b = blockIdx.y;
-  const int q0 = blockIdx.x * (32 * kSeenPix) + lane;
-  const int tid = cg * 32 + lane;
-  float acc[kSeenPix][TMAX];
+  const int q0 = pb * PS + lane * PX;
+  const int per = (D + cs - 1) / cs;
+  const int c_begin = rank * per, c_end = min(D, c_begin + per);
+  float acc[PX][TMAX];
 #pragma unroll
-  for (int i = 0; i < kSeenPix; ++i)
+  for (int i = 0; i < PX; ++i)
 #pragma unroll
     for (int t = 0; t < TMAX; ++t) acc[i][t] = 0.f;
-  const T* base = feat + (int64_t)b * D * hw;
-  for (int c0 = 0; c0 < D; c0 += chunk) {
-    const int cn = min(chunk, D - c0);
+  const T* base = feat + (int64_t)b * D * hw + q0;
+  const bool live = q0 < hw;  // hw is a multiple of PX: a lane's pixels are all inside or all outside
+  for (int c0 = c_begin; c0 < c_end; c0 += chunk) {
+    const int cn = min(chunk, c_end - c0);
     __syncthreads();
     for (int i = tid; i < Tn * cn; i += 32 * kSeenWarps) {
       const int t = i / cn, c = i - t * cn;
-      s_sp[c * Tn + t] = sigmoid_fast(proto[t * D + c0 + c]);
-      s_w[c * Tn + t] = weight[t * D + c0 + c];
+      smem[c * stride + t] = weight[t * D + c0 + c];
+      smem[c * stride + TMAX + t] = sigmoid_fast(proto[t * D + c0 + c]);
     }
     __syncthreads();
-    // warp cg handles channels cg, cg + 8, ... of the chunk; two channels (8 loads) in flight per thread
-    for (int c = cg; c < cn; c += 2 * kSeenWarps) {
-      float x[2][kSeenPix];
+    // warp wid handles channels wid, wid + 8, ... of the chunk; U channel rows in flight per lane
+    constexpr int U = PX >= 4 ? 8 : 4;
+    for (int c = wid; c < cn; c += U * kSeenWarps) {
+      using Raw = typename RawVec<sizeof(T) * PX>::type;
+      Raw x[U];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int cc = c + u * kSeenWarps;
-#pragma unroll
-        for (int i = 0; i < kSeenPix; ++i) {
-          const int q = q0 + 32 * i;
-          x[u][i] = (cc < cn && q < hw) ? DT<T>::to_f(base[(int64_t)(c0 + cc) * hw + q]) : 0.f;
-        }
+        x[u] = Raw{};
+        if (cc < cn && live) x[u] = *reinterpret_cast<const Raw*>(base + (int64_t)(c0 + cc) * hw);
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int cc = c + u * kSeenWarps;
         if (cc < cn) {
-          float sx[kSeenPix];
+          float sx[PX];
+          unpack_px<T, PX>(x[u], sx);
 #pragma unroll
-          for (int i = 0; i < kSeenPix; ++i) sx[i] = sigmoid_fast(x[u][i]);
+          for (int i = 0; i < PX; ++i) sx[i] = sigmoid_fast(sx[i]);
+          const float4* row = reinterpret_cast<const float4*>(smem + cc * stride);
+          float tab[2 * TMAX];
+#pragma unroll
+          for (int k = 0; k < (2 * TMAX) / 4; ++k) {
+            const float4 v = row[k];
+            tab[4 * k] = v.x; tab[4 * k + 1] = v.y; tab[4 * k + 2] = v.z; tab[4 * k + 3] = v.w;
+          }
 #pragma unroll
           for (int t = 0; t < TMAX; ++t)
-            if (t < Tn) {
-              const float wv = s_w[cc * Tn + t], sp = s_sp[cc * Tn + t];
+            if (t < Tn) {  // uniform
 #pragma unroll
-              for (int i = 0; i < kSeenPix; ++i) acc[i][t] = fmaf(wv, fabsf(sx[i] - sp), acc[i][t]);
+              for (int i = 0; i < PX; ++i) acc[i][t] = fmaf(tab[t], fabsf(sx[i] - tab[TMAX + t]), acc[i][t]);
             }
         }
       }
     }
   }
   __syncthreads();
-  // cross-warp reduction through shared memory: red[cg][t][pixel slot]
+  // cross-warp reduction through shared memory: red[warp][t][pixel], then across the cluster
   float* red = smem;
-  constexpr int PS = 32 * kSeenPix;
 #pragma unroll
   for (int t = 0; t < TMAX; ++t)
     if (t < Tn) {
 #pragma unroll
-      for (int i = 0; i < kSeenPix; ++i) red[(cg * Tn + t) * PS + 32 * i + lane] = acc[i][t];
+      for (int i = 0; i < PX; ++i) red[(wid * Tn + t) * PS + lane * PX + i] = acc[i][t];
     }
   __syncthreads();
-  for (int t = cg; t < Tn; t += kSeenWarps) {
+  float* xfer = smem + kSeenWarps * Tn * PS;  // [cs][Tn][PS] in the leader's shared memory
+  const int n_out = Tn * PS;
+  if (cs > 1) {
+    // non-leaders push their CTA sums into the leader's xfer[rank]
+    uint32_t remote;
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(xfer + (size_t)rank * n_out);
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
+    if (rank != 0) {
+      for (int e = tid; e < n_out; e += 32 * kSeenWarps) {
+        float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kSeenPix; ++i) {
-      float s = bias[t];
-#pragma unroll
-      for (int g = 0; g < kSeenWarps; ++g) s += red[(g * Tn + t) * PS + 32 * i + lane];
-      const int q = q0 + 32 * i;
-      if (q < hw) z[((int64_t)b * Tn + t) * hw + q] = s;
+        for (int g = 0; g < kSeenWarps; ++g) s += red[g * n_out + e];
+        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote + 4u * (uint32_t)e), "f"(s) : "memory");
+      }
     }
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (rank != 0) return;
+  }
+  for (int e = tid; e < n_out; e += 32 * kSeenWarps) {
+    const int t = e / PS, px = e - t * PS;
+    float s = bias[t];
+#pragma unroll
+    for (int g = 0; g < kSeenWarps; ++g) s += red[g * n_out + e];
+    for (int r = 1; r < cs; ++r) s += xfer[(size_t)r * n_out + e];
+    const int q = pb * PS + px;
+    if (q < hw) z[((int64_t)b * Tn + t) * hw + q] = s;
   }
 }
 
@@ -174,6 +243,83 @@ __global__ void __launch_bounds__(512) seen_head_backward_kernel(const T* __rest
   if (threadIdx.x == 0) dweight[c] = acc * scale;
 }
 
+// Vectorised variant (hw a multiple of 8, 16-byte aligned rows): a thread handles 8 consecutive pixels per step
+// (one 16-byte feature load, two 16-byte gz loads, one 16-byte gradient store), three steps in flight.
+template <typename T>
+__global__ void __launch_bounds__(256, 3) seen_head_backward_vec_kernel(const T* __restrict__ feat, int B, int D, int hw,
+                                                                     const float* __restrict__ proto_t,
+                                                                     const float* __restrict__ weight_t,
+                                                                     const float* __restrict__ gz,
+                                                                     const float* __restrict__ scale_dev,
+                                                                     float* __restrict__ dweight,
+                                                                     float* __restrict__ dbias, T* __restrict__ dfeat) {
+  __shared__ float scratch[32];
+  const int c = blockIdx.x;
+  const float scale = scale_dev ? *scale_dev : 1.f;
+  if (c == D) {  // extra block: bias gradient
+    float s = 0.f;
+    const float4* g4 = reinterpret_cast<const float4*>(gz);
+    for (int i = threadIdx.x; i < (B * hw) / 4; i += blockDim.x) {
+      const float4 v = g4[i];
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) dbias[0] = s * scale;
+    return;
+  }
+  const float sp = sigmoid_fast(proto_t[c]);
+  const float coef = scale * weight_t[c];
+  const int ipr = hw >> 3;           // 8-pixel items per row
+  const int items = B * ipr;
+  float acc = 0.f;
+  constexpr int U = 3;
+  constexpr int EB = 8 * sizeof(T);  // bytes per item
+  using Raw = typename RawVec<(EB > 16 ? 16 : EB)>::type;
+  for (int i0 = threadIdx.x; i0 < items; i0 += U * blockDim.x) {
+    Raw x[U][EB / 16 > 0 ? EB / 16 : 1];
+    float4 ga[U], gb[U];
+    int64_t off[U];
+    bool on[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * blockDim.x;
+      on[u] = i < items;
+      const int b = on[u] ? i / ipr : 0;
+      const int q = on[u] ? (i - b * ipr) * 8 : 0;
+      off[u] = ((int64_t)b * D + c) * hw + q;
+      const Raw* src = reinterpret_cast<const Raw*>(feat + off[u]);
+#pragma unroll
+      for (int k = 0; k < (EB / 16 > 0 ? EB / 16 : 1); ++k) x[u][k] = on[u] ? src[k] : Raw{};
+      const float4* gp = reinterpret_cast<const float4*>(gz + (int64_t)b * hw + q);
+      ga[u] = on[u] ? gp[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+      gb[u] = on[u] ? gp[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!on[u]) continue;
+      const T* e8 = reinterpret_cast<const T*>(&x[u][0]);
+      const float g8[8] = {ga[u].x, ga[u].y, ga[u].z, ga[u].w, gb[u].x, gb[u].y, gb[u].z, gb[u].w};
+      T o8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float sx = sigmoid_fast(DT<T>::to_f(e8[e]));
+        const float d = sx - sp;
+        acc = fmaf(g8[e], fabsf(d), acc);
+        const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+        o8[e] = DT<T>::from_f(g8[e] * coef * sg * sx * (1.f - sx));
+      }
+      if (dfeat) {
+        Raw* dst = reinterpret_cast<Raw*>(dfeat + off[u]);
+        const Raw* o = reinterpret_cast<const Raw*>(o8);
+#pragma unroll
+        for (int k = 0; k < (EB / 16 > 0 ? EB / 16 : 1); ++k) dst[k] = o[k];
+      }
+    }
+  }
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) dweight[c] = acc * scale;
+}
+
 // scale = weight * ready * [#bg > 0] / #kept ; focal = scale * sum(focal terms)
 __global__ void focal_scale_kernel(const double* __restrict__ acc, const int32_t* __restrict__ ready, float weight,
                                    float* __restrict__ scale_out, double* __restrict__ out2) {
@@ -199,18 +345,39 @@ int bacs_seen_logits(const void* features, int dtype, int B, int D, int h, int w
   BACS_REQUIRE(B > 0 && B < 65536 && D > 0 && h > 0 && w > 0, "bacs_seen_logits: bad shape");
   BACS_REQUIRE(T > 0 && T <= 32, "bacs_seen_logits: T=%d not in [1,32]", T);
   const int hw = h * w;
-  // chunk of channels whose sigmoid(proto) / weight rows fit in <= 48 KB of shared memory
-  int chunk = (48 * 1024 / 4 / 2) / T;
-  chunk = chunk / kSeenWarps * kSeenWarps;
-  if (chunk > D) chunk = (D + kSeenWarps - 1) / kSeenWarps * kSeenWarps;
-  size_t smem = (size_t)2 * T * chunk * sizeof(float);
-  const size_t red = (size_t)kSeenWarps * T * 32 * kSeenPix * sizeof(float);
-  if (smem < red) smem = red;
-  dim3 grid((hw + 32 * kSeenPix - 1) / (32 * kSeenPix), B), block(32, kSeenWarps);
+  const int tmax = T <= 4 ? 4 : (T <= 8 ? 8 : (T <= 16 ? 16 : 32));
+  int px = tmax <= 8 ? 4 : (tmax == 16 ? 2 : 1);
+  const size_t es = dtype_size(dtype);
+  if (hw % px != 0 || (reinterpret_cast<uintptr_t>(features) % (px * es)) != 0) px = 1;
+  const int ps = 32 * px;
+  const int n_pb = (hw + ps - 1) / ps;
+  // cluster size: split the channels while the whole grid still fits the machine in one wave (3 CTAs per SM)
+  int cs = 1;
+  while (cs < 8 && (int64_t)n_pb * B * cs * 2 <= (int64_t)3 * sm_count() && D / (2 * cs) >= 2 * kSeenWarps) cs *= 2;
+  const int stride = 2 * tmax;
+  const int per = (D + cs - 1) / cs;
+  int chunk = (32 * 1024 / 4) / stride;  // table of <= 32 KB
+  chunk = std::max(kSeenWarps, chunk / kSeenWarps * kSeenWarps);
+  if (chunk > per) chunk = (per + kSeenWarps - 1) / kSeenWarps * kSeenWarps;
+  const size_t table = (size_t)chunk * stride * sizeof(float);
+  const size_t red = (size_t)(kSeenWarps + cs) * T * ps * sizeof(float);
+  const size_t smem = std::max(table, red);
   cudaStream_t s = (cudaStream_t)stream;
-#define LAUNCH_Z(TT, TM)                                                                                          \
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_pb * cs), (unsigned)B);
+  cfg.blockDim = dim3(32 * kSeenWarps);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define LAUNCH_Z(TT, TM, PXV)                                                                                     \
   do {                                                                                                            \
-    auto kern = seen_logits_kernel<TT, TM>;                                                                       \
+    auto kern = seen_logits_kernel<TT, TM, PXV>;                                                                  \
     if (smem > 48 * 1024) {                                                                                       \
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
       if (e != cudaSuccess) {                                                                                     \
@@ -218,14 +385,25 @@ int bacs_seen_logits(const void* features, int dtype, int B, int D, int h, int w
         return BACS_ERR_CUDA;                                                                                     \
       }                                                                                                           \
     }                                                                                                             \
-    kern<<<grid, block, smem, s>>>(reinterpret_cast<const TT*>(features), D, hw, proto, weight, bias, T, chunk, z); \
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const TT*>(features), D, hw, proto, weight,  \
+                                        bias, T, chunk, cs, z);                                                   \
+    if (le != cudaSuccess) {                                                                                      \
+      set_error("bacs_seen_logits: launch failed: %s", cudaGetErrorString(le));                                  \
+      return BACS_ERR_CUDA;                                                                                       \
+    }                                                                                                             \
+  } while (0)
+#define LAUNCH_Z_PX(TT, TM, PXV)     \
+  do {                               \
+    if (px == 1) LAUNCH_Z(TT, TM, 1); \
+    else LAUNCH_Z(TT, TM, PXV);      \
   } while (0)
   BACS_DISPATCH_DTYPE(dtype, TT, {
-    if (T <= 4) LAUNCH_Z(TT, 4);
-    else if (T <= 8) LAUNCH_Z(TT, 8);
-    else if (T <= 16) LAUNCH_Z(TT, 16);
-    else LAUNCH_Z(TT, 32);
+    if (tmax == 4) LAUNCH_Z_PX(TT, 4, 4);
+    else if (tmax == 8) LAUNCH_Z_PX(TT, 8, 4);
+    else if (tmax == 16) LAUNCH_Z_PX(TT, 16, 2);
+    else LAUNCH_Z(TT, 32, 1);
   });
+#undef LAUNCH_Z_PX
 #undef LAUNCH_Z
   BACS_CHECK_LAUNCH("bacs_seen_logits");
   return BACS_OK;
@@ -253,10 +431,18 @@ int bacs_seen_head_backward(const void* features, int dtype, int B, int D, int h
   BACS_REQUIRE(B > 0 && D > 0 && h > 0 && w > 0, "bacs_seen_head_backward: bad shape");
   const int hw = h * w;
   cudaStream_t s = (cudaStream_t)stream;
+  const bool vec = hw % 8 == 0 && (reinterpret_cast<uintptr_t>(features) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(gz) & 15) == 0 &&
+                   (!dfeatures || (reinterpret_cast<uintptr_t>(dfeatures) & 15) == 0);
   BACS_DISPATCH_DTYPE(dtype, TT, {
-    seen_head_backward_kernel<TT><<<D + 1, 512, 0, s>>>(reinterpret_cast<const TT*>(features), B, D, hw, proto_t,
-                                                        weight_t, gz, scale_dev, dweight, dbias,
-                                                        reinterpret_cast<TT*>(dfeatures));
+    if (vec)
+      seen_head_backward_vec_kernel<TT><<<D + 1, 256, 0, s>>>(reinterpret_cast<const TT*>(features), B, D, hw, proto_t,
+                                                              weight_t, gz, scale_dev, dweight, dbias,
+                                                              reinterpret_cast<TT*>(dfeatures));
+    else
+      seen_head_backward_kernel<TT><<<D + 1, 512, 0, s>>>(reinterpret_cast<const TT*>(features), B, D, hw, proto_t,
+                                                          weight_t, gz, scale_dev, dweight, dbias,
+                                                          reinterpret_cast<TT*>(dfeatures));
   });
   BACS_CHECK_LAUNCH("bacs_seen_head_backward");
   return BACS_OK;
