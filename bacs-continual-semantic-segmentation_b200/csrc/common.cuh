@@ -134,6 +134,14 @@ __device__ __forceinline__ F2 sub2(F2 a, F2 b) {
 
 // fast sigmoid (ex2.approx + rcp.approx, ~2 ulp): used on the bulk feature data
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// the same two approximations issued directly (no range fix-ups: ex2.approx.ftz saturates to 0 / +inf, and
+// rcp.approx.ftz(+inf) = 0): FMUL, MUFU.EX2, FADD, MUFU.RCP
+__device__ __forceinline__ float sigmoid_mufu(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 // accurate sigmoid (used where a threshold decision depends on it)
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 

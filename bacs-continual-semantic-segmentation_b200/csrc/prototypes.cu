@@ -87,9 +87,23 @@ __global__ void __launch_bounds__(32 * kAccWarps) proto_accumulate_vec_kernel(co
                                                                               const int32_t* __restrict__ n_bt, int Tn,
                                                                               int mode, float* __restrict__ partial) {
   extern __shared__ float s_acc[];  // [warp][Tn*2][33] | [warp][32] split points
+  __shared__ long long s_pre[32], s_tot[32];  // per task: masked pixels in the images before b / in all images
+  __shared__ int s_nb[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int c = blockIdx.x * kAccWarps + wid;
+  if (wid == 0 && lane < Tn && mode == 0) {  // the same for all channels of the block: computed once
+    long long pre = 0, tot = 0;
+    for (int bb = 0; bb < B; ++bb) {
+      const int n = n_bt[bb * Tn + lane];
+      if (bb < b) pre += n;
+      tot += n;
+    }
+    s_pre[lane] = pre;
+    s_tot[lane] = tot;
+    s_nb[lane] = n_bt[b * Tn + lane];
+  }
+  __syncthreads();
   if (c >= D) return;
   const int ne = Tn * 2;
   float* acc = s_acc + (size_t)wid * ne * 33;
@@ -97,16 +111,12 @@ __global__ void __launch_bounds__(32 * kAccWarps) proto_accumulate_vec_kernel(co
   for (int i = lane; i < ne * 33; i += 32) acc[i] = 0.f;
   int split = 0x7fffffff;
   if (mode == 0 && lane < Tn) {
-    long long pre = 0, tot = 0;
-    for (int bb = 0; bb < B; ++bb) {
-      const int n = n_bt[bb * Tn + lane];
-      if (bb < b) pre += n;
-      tot += n;
-    }
-    const long long nb = n_bt[b * Tn + lane];
+    const long long tot = s_tot[lane], nb = s_nb[lane];
     if (tot > 0) {
-      const long long base = (long long)D * pre + (long long)c * nb;
-      const long long r0 = base / tot;
+      const long long base = (long long)D * s_pre[lane] + (long long)c * nb;
+      long long r0;
+      if ((long long)D * tot < 0x7fffffffLL) r0 = (long long)((unsigned)base / (unsigned)tot);  // 32-bit division
+      else r0 = base / tot;
       const long long sp = (r0 + 1) * tot - base;
       split = sp > 0x7fffffffLL ? 0x7fffffff : (int)sp;
     }

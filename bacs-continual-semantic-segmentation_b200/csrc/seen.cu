@@ -55,7 +55,7 @@ __device__ __forceinline__ void load_px(const T* p, float* v) {
 // has enough CTAs to fill the machine while the summation order stays fixed.
 // Per channel the T (weight, sigmoid(proto)) pairs sit in one shared-memory row read with broadcast 128-bit loads.
 template <typename T, int TMAX, int PX>
-__global__ void __launch_bounds__(32 * kSeenWarps, (TMAX <= 8 ? 3 : 1)) seen_logits_kernel(const T* __restrict__ feat, int D, int hw,
+__global__ void __launch_bounds__(32 * kSeenWarps, (TMAX * PX <= 32 ? 3 : 1)) seen_logits_kernel(const T* __restrict__ feat, int D, int hw,
                                                                        const float* __restrict__ proto,
                                                                        const float* __restrict__ weight,
                                                                        const float* __restrict__ bias, int Tn,
@@ -80,10 +80,10 @@ __global__ void __launch_bounds__(32 * kSeenWarps, (TMAX <= 8 ? 3 : 1)) seen_log
   for (int c0 = c_begin; c0 < c_end; c0 += chunk) {
     const int cn = min(chunk, c_end - c0);
     __syncthreads();
-    for (int i = tid; i < Tn * cn; i += 32 * kSeenWarps) {
+    for (int i = tid; i < TMAX * cn; i += 32 * kSeenWarps) {
       const int t = i / cn, c = i - t * cn;
-      smem[c * stride + t] = weight[t * D + c0 + c];
-      smem[c * stride + TMAX + t] = sigmoid_fast(proto[t * D + c0 + c]);
+      smem[c * stride + t] = t < Tn ? weight[t * D + c0 + c] : 0.f;
+      smem[c * stride + TMAX + t] = t < Tn ? sigmoid_fast(proto[t * D + c0 + c]) : 0.f;
     }
     __syncthreads();
     // warp wid handles channels wid, wid + 8, ... of the chunk; U channel rows in flight per lane
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(32 * kSeenWarps, (TMAX <= 8 ? 3 : 1)) seen_log
           float sx[PX];
           unpack_px<T, PX>(x[u], sx);
 #pragma unroll
-          for (int i = 0; i < PX; ++i) sx[i] = sigmoid_fast(sx[i]);
+          for (int i = 0; i < PX; ++i) sx[i] = sigmoid_mufu(sx[i]);
           const float4* row = reinterpret_cast<const float4*>(smem + cc * stride);
           float tab[2 * TMAX];
 #pragma unroll
@@ -112,12 +112,21 @@ __global__ void __launch_bounds__(32 * kSeenWarps, (TMAX <= 8 ? 3 : 1)) seen_log
             const float4 v = row[k];
             tab[4 * k] = v.x; tab[4 * k + 1] = v.y; tab[4 * k + 2] = v.z; tab[4 * k + 3] = v.w;
           }
+          // heads t >= Tn have weight 0 in the table: no predicate in the inner loop
 #pragma unroll
-          for (int t = 0; t < TMAX; ++t)
-            if (t < Tn) {  // uniform
+          for (int t = 0; t < TMAX; ++t) {
+            if constexpr (PX % 2 == 0) {
+#pragma unroll
+              for (int i = 0; i < PX; i += 2) {
+                const F2 d = sub2(f2(sx[i], sx[i + 1]), f2b(tab[TMAX + t]));  // one FADD2 for two pixels
+                acc[i][t] = fmaf(tab[t], fabsf(f2lo(d)), acc[i][t]);
+                acc[i + 1][t] = fmaf(tab[t], fabsf(f2hi(d)), acc[i + 1][t]);
+              }
+            } else {
 #pragma unroll
               for (int i = 0; i < PX; ++i) acc[i][t] = fmaf(tab[t], fabsf(sx[i] - tab[TMAX + t]), acc[i][t]);
             }
+          }
         }
       }
     }
@@ -246,7 +255,7 @@ __global__ void __launch_bounds__(512) seen_head_backward_kernel(const T* __rest
 // Vectorised variant (hw a multiple of 8, 16-byte aligned rows): a thread handles 8 consecutive pixels per step
 // (one 16-byte feature load, two 16-byte gz loads, one 16-byte gradient store), three steps in flight.
 template <typename T>
-__global__ void __launch_bounds__(256, 3) seen_head_backward_vec_kernel(const T* __restrict__ feat, int B, int D, int hw,
+__global__ void __launch_bounds__(256, 4) seen_head_backward_vec_kernel(const T* __restrict__ feat, int B, int D, int hw,
                                                                      const float* __restrict__ proto_t,
                                                                      const float* __restrict__ weight_t,
                                                                      const float* __restrict__ gz,
@@ -272,7 +281,7 @@ __global__ void __launch_bounds__(256, 3) seen_head_backward_vec_kernel(const T*
   const int ipr = hw >> 3;           // 8-pixel items per row
   const int items = B * ipr;
   float acc = 0.f;
-  constexpr int U = 3;
+  constexpr int U = 2;
   constexpr int EB = 8 * sizeof(T);  // bytes per item
   using Raw = typename RawVec<(EB > 16 ? 16 : EB)>::type;
   for (int i0 = threadIdx.x; i0 < items; i0 += U * blockDim.x) {
@@ -302,7 +311,7 @@ __global__ void __launch_bounds__(256, 3) seen_head_backward_vec_kernel(const T*
       T o8[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float sx = sigmoid_fast(DT<T>::to_f(e8[e]));
+        const float sx = sigmoid_mufu(DT<T>::to_f(e8[e]));
         const float d = sx - sp;
         acc = fmaf(g8[e], fabsf(d), acc);
         const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
@@ -345,8 +354,8 @@ int bacs_seen_logits(const void* features, int dtype, int B, int D, int h, int w
   BACS_REQUIRE(B > 0 && B < 65536 && D > 0 && h > 0 && w > 0, "bacs_seen_logits: bad shape");
   BACS_REQUIRE(T > 0 && T <= 32, "bacs_seen_logits: T=%d not in [1,32]", T);
   const int hw = h * w;
-  const int tmax = T <= 4 ? 4 : (T <= 8 ? 8 : (T <= 16 ? 16 : 32));
-  int px = tmax <= 8 ? 4 : (tmax == 16 ? 2 : 1);
+  const int tmax = T <= 2 ? 2 : (T <= 4 ? 4 : (T <= 6 ? 6 : (T <= 8 ? 8 : (T <= 12 ? 12 : (T <= 16 ? 16 : 32)))));
+  int px = tmax <= 8 ? 4 : (tmax <= 16 ? 2 : 1);
   const size_t es = dtype_size(dtype);
   if (hw % px != 0 || (reinterpret_cast<uintptr_t>(features) % (px * es)) != 0) px = 1;
   const int ps = 32 * px;
@@ -398,8 +407,11 @@ int bacs_seen_logits(const void* features, int dtype, int B, int D, int h, int w
     else LAUNCH_Z(TT, TM, PXV);      \
   } while (0)
   BACS_DISPATCH_DTYPE(dtype, TT, {
-    if (tmax == 4) LAUNCH_Z_PX(TT, 4, 4);
+    if (tmax == 2) LAUNCH_Z_PX(TT, 2, 4);
+    else if (tmax == 4) LAUNCH_Z_PX(TT, 4, 4);
+    else if (tmax == 6) LAUNCH_Z_PX(TT, 6, 4);
     else if (tmax == 8) LAUNCH_Z_PX(TT, 8, 4);
+    else if (tmax == 12) LAUNCH_Z_PX(TT, 12, 2);
     else if (tmax == 16) LAUNCH_Z_PX(TT, 16, 2);
     else LAUNCH_Z(TT, 32, 1);
   });
