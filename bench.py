@@ -139,6 +139,12 @@ def run_reference(args):
     if rank != 0:
         return
     from bacs_b200 import synth
+    # torchrun exports OMP_NUM_THREADS=1: the reference arm uses every host core this process may run on
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    torch.set_num_threads(max(1, ncores))
     cfg = synth.CONFIGS[args.config]
     steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
     value, dt, sample = oracle_step_time(cfg, args.cpu_sample_batch, steps, warmup, args.dtype)
@@ -226,7 +232,7 @@ def main():
 
     # ---- the same step captured once in a CUDA graph (the step never synchronises with the host)
     ms_graph = None
-    if not args.no_graph and world == 1:
+    if not args.no_graph:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -259,7 +265,7 @@ def main():
     alg_bytes = pixels * (2 * cfg.K * es + 8 + 8 + 1) + z.numel() * 4
     peak, peak_src = peaks()
     achieved = alg_bytes / (ms_pix * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "pixel_loss_kernel (weighted CE + focal + argmax + distill mask + dlogits)",
+    roofline = {"bound": "hbm", "kernel": "pixel_wce_kernel (weighted CE + focal + argmax + distill mask + dlogits)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_pix,
                 "share_of_step": ms_pix / ms_step}
@@ -322,6 +328,10 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+        except AttributeError:
+            pass
         v, dt, sample = oracle_step_time(cfg, args.cpu_sample_batch, 3, 1, args.dtype)
         cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
                "ms_per_step": dt * 1e3}
@@ -341,7 +351,16 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # A captured graph that holds NCCL kernels must be gone before the communicator is torn down; the
+        # teardown itself is skipped (it can block on a communicator that was used under capture) and the
+        # ranks leave together after a final barrier.
+        graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
