@@ -265,8 +265,13 @@ def main():
     alg_bytes = pixels * (2 * cfg.K * es + 8 + 8 + 1) + z.numel() * 4
     peak, peak_src = peaks()
     achieved = alg_bytes / (ms_pix * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_pixel_wce_traffic.json")
+    if os.path.exists(tpath) and args.config == "voc15-1_b24" and args.dtype == "bf16":
+        with open(tpath) as f:
+            traffic = json.load(f).get("traffic_bytes_per_launch")   # dram read + write of one launch (ncu --set full)
     roofline = {"bound": "hbm", "kernel": "pixel_wce_kernel (weighted CE + focal + argmax + distill mask + dlogits)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_pix,
                 "share_of_step": ms_pix / ms_step}
 
