@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T*
   float o_prev[NC][CPL], n_prev[NC][CPL];
   T o_nxt[NC][CPL], n_nxt[NC][CPL];
   float carry[NC][CPL];  // gradient already collected for the upper row by the interval above
-  float loss_acc = 0.f;
+  float loss_acc = 0.f;   // row norms known to every lane (scalar tail rows): counted once per warp
+  float loss_quad = 0.f;  // row norms held by the 4 lanes of a quad (transposed reduction)
   auto load_row = [&](const T* base, int b, int ch, int row, T* v) {
 #pragma unroll
     for (int m = 0; m < CPL; ++m) {
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T*
     const int row1 = min(i + 1, h - 1);
     const int buf = k % 3;
     const float* s_mom = s_dyn + buf * mom_stride;
-    const float loss_before = loss_acc;
+    const float loss_before = loss_acc, quad_before = loss_quad;
     // Unit k+1 goes into the buffer unit k-2 used: its readers had a whole unit to finish, so the staging
     // thread practically never waits and no CTA-wide barrier is needed.
     if (bulk_ok) {
@@ -358,28 +359,46 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T*
           }
         }
       }
+      // Transposed butterfly over the 8 row sums of this call (2 row pairs x 2 channels x 2 halves): every level
+      // halves the number of sums a lane still carries, so 7 + 2 shuffles replace 5 x 8, and ONE rsqrt per lane
+      // serves all eight rows.  Afterwards lane l holds the total of row sum (l >> 2) & 7.
+      static_assert(NC == 2, "the transposed reduction is written for two channels per warp");
+      const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0, up4 = (lane & 4) != 0;
+      F2 k0, k1;
+      {
+        const F2 send0 = up16 ? S[0][0] : S[1][0], send1 = up16 ? S[0][1] : S[1][1];
+        const F2 keep0 = up16 ? S[1][0] : S[0][0], keep1 = up16 ? S[1][1] : S[0][1];
+        F2 r0, r1;
+        r0.v = __shfl_xor_sync(kFull, send0.v, 16);
+        r1.v = __shfl_xor_sync(kFull, send1.v, 16);
+        k0 = add2(keep0, r0);
+        k1 = add2(keep1, r1);
+      }
+      F2 kk;
+      {
+        const F2 send = up8 ? k0 : k1, keep = up8 ? k1 : k0;
+        F2 r;
+        r.v = __shfl_xor_sync(kFull, send.v, 8);
+        kk = add2(keep, r);
+      }
+      float tot;
+      {
+        const float lo = f2lo(kk), hi = f2hi(kk);
+        const float send = up4 ? lo : hi, keep = up4 ? hi : lo;
+        tot = keep + __shfl_xor_sync(kFull, send, 4);
+      }
+      tot += __shfl_xor_sync(kFull, tot, 2);
+      tot += __shfl_xor_sync(kFull, tot, 1);
+      // zero (or rounding-negative) row: norm 0 and sub-gradient 0, as torch's norm backward
+      const float rs_mine = tot > 0.f ? rsqrt_fast(tot) : 0.f;
+      loss_quad = fmaf(tot, rs_mine, loss_quad);  // every row sum is held by 4 lanes: scaled by 1/4 at the end
+      if (want_grad) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int q = 0; q < RP; ++q)
+        for (int q = 0; q < RP; ++q) {
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
-            F2 other;
-            other.v = __shfl_xor_sync(kFull, S[q][c].v, o);
-            S[q][c] = add2(S[q][c], other);
-          }
-      }
-#pragma unroll
-      for (int q = 0; q < RP; ++q) {
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          // zero (or rounding-negative) row: norm 0 and sub-gradient 0, as torch's norm backward
-          const float sa = f2lo(S[q][c]), sb = f2hi(S[q][c]);
-          const float rsa = sa > 0.f ? rsqrt_fast(sa) : 0.f;
-          const float rsb = sb > 0.f ? rsqrt_fast(sb) : 0.f;
-          loss_acc = fmaf(sa, rsa, loss_acc);
-          loss_acc = fmaf(sb, rsb, loss_acc);
-          if (want_grad) {
+            const float rsa = __shfl_sync(kFull, rs_mine, q * 16 + c * 8);
+            const float rsb = __shfl_sync(kFull, rs_mine, q * 16 + c * 8 + 4);
             const F2 rs = f2(rsa, rsb);
             const F2 rst = mul2(rs, ty2[q]);
 #pragma unroll
@@ -514,10 +533,13 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T*
         }
       }
     }
-    if (halo) loss_acc = loss_before;
+    if (halo) {
+      loss_acc = loss_before;
+      loss_quad = quad_before;
+    }
   }
   // every lane holds the same loss_acc (the shuffle reduction broadcasts); count it once per warp
-  const double mine = (lane == 0) ? (double)loss_acc : 0.0;
+  const double mine = ((lane == 0) ? (double)loss_acc : 0.0) + 0.25 * (double)loss_quad;
   const double tot = block_sum(mine, red_scratch);
   if (threadIdx.x == 0) partials[blockIdx.x] = tot;
 }
