@@ -40,7 +40,9 @@ def _oracle_step(cfg, inp, first_task, proto_mode="exact"):
 
 
 @pytest.mark.parametrize("name,first_task,dtype", [("tiny", False, torch.float32), ("tiny", True, torch.float32),
-                                                   ("small", False, torch.float32), ("small", False, torch.bfloat16)])
+                                                   ("small", False, torch.float32), ("small", False, torch.bfloat16),
+                                                   ("row512", False, torch.float32), ("row512", False, torch.bfloat16),
+                                                   ("row512", True, torch.float32)])
 def test_full_step_matches_oracle(name, first_task, dtype):
     from bacs_b200 import synth
     cfg = synth.CONFIGS[name]
