@@ -47,11 +47,12 @@ _SIGNATURES = {
     "bacs_seen_upsample": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "bacs_seen_head_backward": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "bacs_focal_scale": (i32, [vp, vp, f32, vp, vp, vp]),
+    "bacs_focal_scale_loss": (i32, [vp, vp, f32, f32, i32, vp, vp, vp]),
     "bacs_pixel_workspace_bytes": (sz, [C.POINTER(PixelArgs)]),
     "bacs_pixel_kernel_variant": (i32, [C.POINTER(PixelArgs)]),
     "bacs_pixel_loss": (i32, [C.POINTER(PixelArgs), vp, sz, vp]),
     "bacs_distill_workspace_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
-    "bacs_teacher_distill": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, f32, vp, vp, vp, sz, vp]),
+    "bacs_teacher_distill": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, f32, vp, vp, vp, vp, sz, vp]),
     "bacs_der_workspace_bytes": (sz, [i32, i32, i32]),
     "bacs_der_mse": (i32, [vp, i32, vp, i32, i32, vp, i32, i32, i32, i32, f32, vp, vp, vp, sz, vp]),
     "bacs_unbiased_kd_workspace_bytes": (sz, [i64]),
@@ -60,6 +61,7 @@ _SIGNATURES = {
     "bacs_confmat_accumulate": (i32, [vp, i32, vp, i64, i32, vp, vp, vp]),
     "bacs_confmat_metrics": (i32, [vp, i32, vp, vp]),
     "bacs_scale_inplace": (i32, [vp, i32, i64, vp, vp]),
+    "bacs_scale_inplace_multi": (i32, [i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(i64), vp, vp]),
     "bacs_pack_state": (i32, [vp, vp, i32, i32, vp, i32, vp, vp]),
     "bacs_unpack_state": (i32, [vp, i32, i32, vp, vp, vp, i32, vp]),
     "bacs_combine_scalars": (i32, [i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(vp), C.POINTER(i32),

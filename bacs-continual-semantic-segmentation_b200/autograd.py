@@ -50,20 +50,22 @@ class PixelLossFunction(torch.autograd.Function):
         acc = out["acc"]
         B, _, H, W = logits.shape
         scale = cfg.get("loss_scale", 1.0)
-        if mode == _cabi.PIX_WEIGHTED_CE:
-            terms = [(acc, _cabi.ACC_LOSS, scale / float(B * H * W))]           # mean over ALL pixels (Q6)
-        else:
-            terms = [(acc, _cabi.ACC_LOSS, scale, acc, _cabi.ACC_WSUM)]
+        over_wsum = mode != _cabi.PIX_WEIGHTED_CE
+        main_coef = scale if over_wsum else scale / float(B * H * W)            # WEIGHTED_CE: mean over ALL pixels (Q6)
         dweight = dbias = dfeat = None
         if has_focal:
-            fscale, out2 = ops.focal_scale(acc, cfg.get("ready"), cfg.get("focal_weight", 1.0))
-            terms.append((out2, 1, 1.0))
+            # focal normaliser and the loss scalar (main term + focal term) in one single-thread launch
+            fscale, loss = ops.focal_scale_loss(acc, cfg.get("ready"), cfg.get("focal_weight", 1.0), main_coef, over_wsum)
             if head_weight is not None and (ctx.needs_input_grad[2] or ctx.needs_input_grad[1]):
                 want_df = bool(cfg.get("features_grad", False)) and ctx.needs_input_grad[1]
                 proto_t = cfg["proto"][focal_head]
                 dweight, dbias, dfeat = ops.seen_head_backward(
                     features, proto_t, head_weight.detach().reshape(-1).float().contiguous(), out["gz"], fscale, want_df)
-        loss = ops.combine_scalars(terms, logits.device).reshape(())
+            loss = loss.reshape(())
+        elif over_wsum:
+            loss = ops.combine_scalars([(acc, _cabi.ACC_LOSS, main_coef, acc, _cabi.ACC_WSUM)], logits.device).reshape(())
+        else:
+            loss = ops.combine_scalars([(acc, _cabi.ACC_LOSS, main_coef)], logits.device).reshape(())
         ctx.grads = (out["dlogits"], dfeat, dweight, dbias)
         ctx.shapes = (None if head_weight is None else head_weight.shape, None if head_bias is None else head_bias.shape,
                       None if head_weight is None else head_weight.dtype)
@@ -81,11 +83,10 @@ class PixelLossFunction(torch.autograd.Function):
         if g is None:
             return None, None, None, None, None, None
         wshape, bshape, wdtype = ctx.shapes
-        dlogits = _scaled(dlogits, g)
-        dfeat = _scaled(dfeat, g)
+        ops.scale_inplace_multi([dlogits, dfeat, dweight, dbias], g)   # one launch for all four gradients
         if dweight is not None:
-            dweight = _scaled(dweight, g).reshape(wshape).to(wdtype)
-            dbias = _scaled(dbias, g).reshape(bshape).to(wdtype)
+            dweight = dweight.reshape(wshape).to(wdtype)
+            dbias = dbias.reshape(bshape).to(wdtype)
         return dlogits, dfeat, dweight, dbias, None, None
 
 
@@ -97,10 +98,10 @@ class TeacherDistillFunction(torch.autograd.Function):
         B, A, h, w = new_att.shape
         H, W = out_hw
         coef = float(lkd) / float(B * A * H)
-        total, dnew = ops.teacher_distill(old_att.detach(), new_att.detach(), mask_u8, (H, W), coef,
-                                          ctx.needs_input_grad[0])
+        _, dnew, loss = ops.teacher_distill(old_att.detach(), new_att.detach(), mask_u8, (H, W), coef,
+                                            ctx.needs_input_grad[0], want_scaled=True)
         ctx.dnew = dnew
-        return ops.combine_scalars([(total, 0, coef)], new_att.device).reshape(())
+        return loss.reshape(())
 
     @staticmethod
     def backward(ctx, g):

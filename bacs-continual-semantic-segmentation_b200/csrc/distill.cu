@@ -545,12 +545,16 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T*
 }
 
 __global__ void __launch_bounds__(1024) sum_partials_kernel(const double* __restrict__ partials, int n,
-                                                            double* __restrict__ out) {
+                                                            double* __restrict__ out, float coef,
+                                                            float* __restrict__ out_scaled) {
   __shared__ double scratch[32];
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += partials[i];
   s = block_sum(s, scratch);
-  if (threadIdx.x == 0) out[0] = s;
+  if (threadIdx.x == 0) {
+    out[0] = s;
+    if (out_scaled) out_scaled[0] = (float)((double)coef * s);
+  }
 }
 
 struct DistillLayout {
@@ -590,7 +594,7 @@ size_t bacs_distill_workspace_bytes(int B, int A, int h, int w, int H, int W) {
 }
 
 int bacs_teacher_distill(const void* old_att, const void* new_att, int dtype, int B, int A, int h, int w,
-                         const uint8_t* mask, int H, int W, float grad_coef, double* loss_sum, void* dnew,
+                         const uint8_t* mask, int H, int W, float grad_coef, double* loss_sum, float* loss_scaled, void* dnew,
                          void* workspace, size_t workspace_bytes, bacs_stream_t stream) {
   BACS_REQUIRE(old_att && new_att && loss_sum && workspace, "bacs_teacher_distill: null pointer");
   BACS_REQUIRE(B > 0 && B < 65536 && A > 0 && h > 0 && w > 0, "bacs_teacher_distill: bad shape");
@@ -658,7 +662,7 @@ int bacs_teacher_distill(const void* old_att, const void* new_att, int dtype, in
   });
 #undef LAUNCH_DISTILL
   BACS_CHECK_LAUNCH("bacs_teacher_distill");
-  sum_partials_kernel<<<1, 1024, 0, s>>>(partials, grid, loss_sum);
+  sum_partials_kernel<<<1, 1024, 0, s>>>(partials, grid, loss_sum, grad_coef, loss_scaled);
   BACS_CHECK_LAUNCH("bacs_teacher_distill(reduce)");
   return BACS_OK;
 }

@@ -250,6 +250,31 @@ __global__ void __launch_bounds__(256) scale_inplace_kernel(T* __restrict__ x, i
     x[i] = DT<T>::from_f(DT<T>::to_f(x[i]) * s);
 }
 
+// Up to 8 tensors in ONE launch (the backward of the fused per-pixel Function rescales logits-, feature-, weight-
+// and bias-gradients by the same upstream scalar): block ranges are assigned per tensor.
+struct ScaleMulti {
+  void* p[8];
+  int64_t n[8];
+  int dt[8];
+  int blk0[9];
+  int cnt;
+};
+template <typename T>
+__device__ __forceinline__ void scale_range(T* x, int64_t n, float s, int lb, int nb) {
+  for (int64_t i = (int64_t)lb * blockDim.x + threadIdx.x; i < n; i += (int64_t)nb * blockDim.x)
+    x[i] = DT<T>::from_f(DT<T>::to_f(x[i]) * s);
+}
+__global__ void __launch_bounds__(256) scale_multi_kernel(const ScaleMulti a, const float* __restrict__ g) {
+  const float s = *g;
+  if (s == 1.f) return;
+  int i = 0;
+  while (i + 1 < a.cnt && (int)blockIdx.x >= a.blk0[i + 1]) ++i;
+  const int lb = (int)blockIdx.x - a.blk0[i], nb = a.blk0[i + 1] - a.blk0[i];
+  if (a.dt[i] == BACS_F32) scale_range(reinterpret_cast<float*>(a.p[i]), a.n[i], s, lb, nb);
+  else if (a.dt[i] == BACS_BF16) scale_range(reinterpret_cast<__nv_bfloat16*>(a.p[i]), a.n[i], s, lb, nb);
+  else scale_range(reinterpret_cast<__half*>(a.p[i]), a.n[i], s, lb, nb);
+}
+
 __global__ void pack_state_kernel(const double* __restrict__ sums, const double* __restrict__ counts, int TD, int T,
                                   const int64_t* __restrict__ confmat, int KK, double* __restrict__ packed) {
   const int n = TD + T + KK;
@@ -427,6 +452,30 @@ int bacs_scale_inplace(void* x, int dtype, int64_t n, const float* g_dev, bacs_s
   BACS_DISPATCH_DTYPE(dtype, TT,
                       { scale_inplace_kernel<TT><<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<TT*>(x), n, g_dev); });
   BACS_CHECK_LAUNCH("bacs_scale_inplace");
+  return BACS_OK;
+}
+
+int bacs_scale_inplace_multi(int n, void* const* x, const int* dtype, const int64_t* numel, const float* g_dev,
+                             bacs_stream_t stream) {
+  BACS_REQUIRE(n >= 0 && n <= 8 && (n == 0 || (x && dtype && numel)) && g_dev, "bacs_scale_inplace_multi: bad arguments");
+  ScaleMulti a;
+  a.cnt = 0;
+  a.blk0[0] = 0;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  for (int i = 0; i < n; ++i) {
+    if (!x[i] || numel[i] <= 0) continue;
+    BACS_REQUIRE(dtype[i] >= 0 && dtype[i] <= BACS_F16, "bacs_scale_inplace_multi: unknown dtype %d", dtype[i]);
+    int64_t blocks = (numel[i] + 256 * 8 - 1) / (256 * 8);
+    if (blocks > cap) blocks = cap;
+    a.p[a.cnt] = x[i];
+    a.n[a.cnt] = numel[i];
+    a.dt[a.cnt] = dtype[i];
+    a.blk0[a.cnt + 1] = a.blk0[a.cnt] + (int)blocks;
+    ++a.cnt;
+  }
+  if (a.cnt == 0) return BACS_OK;
+  scale_multi_kernel<<<a.blk0[a.cnt], 256, 0, (cudaStream_t)stream>>>(a, g_dev);
+  BACS_CHECK_LAUNCH("bacs_scale_inplace_multi");
   return BACS_OK;
 }
 

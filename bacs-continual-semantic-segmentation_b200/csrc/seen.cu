@@ -342,6 +342,20 @@ __global__ void focal_scale_kernel(const double* __restrict__ acc, const int32_t
   }
 }
 
+__global__ void focal_scale_loss_kernel(const double* __restrict__ acc, const int32_t* __restrict__ ready, float weight,
+                                        float main_coef, int main_over_wsum, float* __restrict__ scale_out,
+                                        float* __restrict__ loss_out) {
+  const double kept = acc[BACS_ACC_KEPT];
+  const bool on = (ready == nullptr || *ready != 0) && acc[BACS_ACC_BG] > 0.0 && kept > 0.0;
+  const double s = on ? (double)weight / kept : 0.0;
+  if (scale_out) *scale_out = (float)s;
+  if (loss_out) {
+    double main = (double)main_coef * acc[BACS_ACC_LOSS];
+    if (main_over_wsum) main /= acc[BACS_ACC_WSUM];
+    *loss_out = (float)(main + s * acc[BACS_ACC_FOCAL]);
+  }
+}
+
 }  // namespace bacs
 
 using namespace bacs;
@@ -465,6 +479,15 @@ int bacs_focal_scale(const double* acc, const int32_t* ready, float weight, floa
   BACS_REQUIRE(acc, "bacs_focal_scale: null pointer");
   focal_scale_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(acc, ready, weight, scale_out, out2);
   BACS_CHECK_LAUNCH("bacs_focal_scale");
+  return BACS_OK;
+}
+
+int bacs_focal_scale_loss(const double* acc, const int32_t* ready, float weight, float main_coef, int main_over_wsum,
+                          float* scale_out, float* loss_out, bacs_stream_t stream) {
+  BACS_REQUIRE(acc, "bacs_focal_scale_loss: null pointer");
+  focal_scale_loss_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(acc, ready, weight, main_coef, main_over_wsum, scale_out,
+                                                             loss_out);
+  BACS_CHECK_LAUNCH("bacs_focal_scale_loss");
   return BACS_OK;
 }
 

@@ -181,6 +181,18 @@ def focal_scale(acc: torch.Tensor, ready: Optional[torch.Tensor], weight: float)
     return scale, out2
 
 
+def focal_scale_loss(acc: torch.Tensor, ready: Optional[torch.Tensor], weight: float, main_coef: float,
+                     main_over_wsum: bool):
+    """-> (focal scale fp32 [1], loss fp32 [1] = main_coef * acc[LOSS] (/ acc[WSUM]) + scale * acc[FOCAL])"""
+    dev = acc.device
+    scale = torch.empty(1, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    check(_lib().bacs_focal_scale_loss(acc.data_ptr(), _ptr(ready), float(weight), float(main_coef),
+                                       int(bool(main_over_wsum)), scale.data_ptr(), loss.data_ptr(), _stream()),
+          "bacs_focal_scale_loss")
+    return scale, loss
+
+
 # --------------------------------------------------------------------------------------
 # fused per-pixel kernel
 # --------------------------------------------------------------------------------------
@@ -249,7 +261,8 @@ def pixel_loss(logits: torch.Tensor, labels: torch.Tensor, mode: int, *, want_gr
 # teacher distillation / DER
 # --------------------------------------------------------------------------------------
 def teacher_distill(old_att: torch.Tensor, new_att: torch.Tensor, mask: Optional[torch.Tensor], out_hw,
-                    grad_coef: float, want_grad: bool):
+                    grad_coef: float, want_grad: bool, want_scaled: bool = False):
+    """-> (sum of row norms fp64 [1], grad_coef * d(sum)/d(new) or None[, grad_coef * sum as fp32 [1]])"""
     old_att = _cuda(old_att, "teacher_distill")
     new_att = _cuda(new_att, "teacher_distill")
     if old_att.dtype != new_att.dtype:
@@ -262,12 +275,15 @@ def teacher_distill(old_att: torch.Tensor, new_att: torch.Tensor, mask: Optional
         mask = _cuda(mask, "teacher_distill", torch.uint8)
     dev = new_att.device
     loss_sum = torch.empty(1, dtype=torch.float64, device=dev)
+    loss_scaled = torch.empty(1, dtype=torch.float32, device=dev) if want_scaled else None
     dnew = torch.empty_like(new_att) if want_grad else None
     lib = _lib()
     ws = _ws(lib.bacs_distill_workspace_bytes(B, A, h, w, H, W), dev)
     check(lib.bacs_teacher_distill(old_att.data_ptr(), new_att.data_ptr(), _dt(new_att), B, A, h, w, _ptr(mask), H, W,
-                                   float(grad_coef), loss_sum.data_ptr(), _ptr(dnew), ws.data_ptr(), ws.numel(),
-                                   _stream()), "bacs_teacher_distill")
+                                   float(grad_coef), loss_sum.data_ptr(), _ptr(loss_scaled), _ptr(dnew), ws.data_ptr(),
+                                   ws.numel(), _stream()), "bacs_teacher_distill")
+    if want_scaled:
+        return loss_sum, dnew, loss_scaled
     return loss_sum, dnew
 
 
@@ -377,6 +393,25 @@ def scale_inplace(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
         g = g.float()
     check(_lib().bacs_scale_inplace(x.data_ptr(), _dt(x), x.numel(), g.data_ptr(), _stream()), "bacs_scale_inplace")
     return x
+
+
+def scale_inplace_multi(xs: Sequence[Optional[torch.Tensor]], g: torch.Tensor) -> None:
+    """x *= g for every tensor of ``xs`` (None entries skipped) in one launch; g is a device scalar."""
+    live = [x for x in xs if x is not None and x.numel() > 0]
+    if not live:
+        return
+    for x in live:
+        _cuda(x, "scale_inplace_multi")
+        if not x.is_contiguous():
+            raise ValueError("scale_inplace_multi works in place: tensors must be contiguous")
+    g = _cuda(g.reshape(1).float(), "scale_inplace_multi")
+    n = len(live)
+    if n > 8:
+        raise ValueError("scale_inplace_multi: at most 8 tensors")
+    ptrs = (C.c_void_p * n)(*[x.data_ptr() for x in live])
+    dts = (C.c_int * n)(*[_dt(x) for x in live])
+    nums = (C.c_int64 * n)(*[x.numel() for x in live])
+    check(_lib().bacs_scale_inplace_multi(n, ptrs, dts, nums, g.data_ptr(), _stream()), "bacs_scale_inplace_multi")
 
 
 def combine_scalars(terms: Sequence[tuple], device) -> torch.Tensor:

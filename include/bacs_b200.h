@@ -141,6 +141,11 @@ int bacs_seen_head_backward(const void* features, int dtype, int B, int D, int h
  *   scale * acc[BACS_ACC_FOCAL]} (for bacs_combine_scalars).  Either may be NULL. */
 int bacs_focal_scale(const double* acc, const int32_t* ready, float weight, float* scale_out,
                      double* out2, bacs_stream_t stream);
+/* The same plus the loss scalar of the fused per-pixel Function in one launch:
+ *   loss_out float[1] = main_coef * acc[BACS_ACC_LOSS] / (main_over_wsum ? acc[BACS_ACC_WSUM] : 1)
+ *                       + scale * acc[BACS_ACC_FOCAL]. */
+int bacs_focal_scale_loss(const double* acc, const int32_t* ready, float weight, float main_coef,
+                          int main_over_wsum, float* scale_out, float* loss_out, bacs_stream_t stream);
 
 /* ---------------------------------------------------------------------------------
  * The fused per-pixel kernel: softmax statistics read ONCE per pixel, then
@@ -218,13 +223,14 @@ int bacs_pixel_loss(const bacs_pixel_args* args_host, void* workspace, size_t wo
  *   U = bilinear up-sample to HxW, align_corners=False; gradient to `new` only.
  * mask u8[B,H,W] (from bacs_pixel_loss) or NULL = all ones.
  * loss_sum fp64[1] OVERWRITTEN with sum over rows of the row norms (caller scales by
- * lkd / (B*A*H)); dnew (dtype, [B,A,h,w]) OVERWRITTEN with grad_coef * d(sum)/dnew, or NULL.
+ * lkd / (B*A*H)); loss_scaled fp32[1] OVERWRITTEN with grad_coef * that sum (the loss term itself when
+ * grad_coef = lkd / (B*A*H)), or NULL; dnew (dtype, [B,A,h,w]) OVERWRITTEN with grad_coef * d(sum)/dnew, or NULL.
  * --------------------------------------------------------------------------------- */
 size_t bacs_distill_workspace_bytes(int B, int A, int h, int w, int H, int W);
 int bacs_teacher_distill(const void* old_att, const void* new_att, int dtype, int B, int A,
                          int h, int w, const uint8_t* mask, int H, int W, float grad_coef,
-                         double* loss_sum, void* dnew, void* workspace, size_t workspace_bytes,
-                         bacs_stream_t stream);
+                         double* loss_sum, float* loss_scaled, void* dnew, void* workspace,
+                         size_t workspace_bytes, bacs_stream_t stream);
 
 /* ---------------------------------------------------------------------------------
  * Dark-experience-replay logit MSE with transplant (loss/bacs_loss.py:387-431)
@@ -277,6 +283,9 @@ int bacs_confmat_metrics(const int64_t* confmat, int K, float* out, bacs_stream_
 /* In-place x *= *g for a gradient tensor when the upstream gradient is not 1; the kernel
  * exits immediately (uniformly) when *g == 1. */
 int bacs_scale_inplace(void* x, int dtype, int64_t n, const float* g_dev, bacs_stream_t stream);
+/* The same for up to 8 tensors in one launch (x[i] may be NULL: skipped). */
+int bacs_scale_inplace_multi(int n, void* const* x, const int* dtype, const int64_t* numel,
+                             const float* g_dev, bacs_stream_t stream);
 
 /* out[0] = sum_i coef[i] * src[i][idx[i]] / (den[i] ? den[i][didx[i]] : 1), n <= 8 terms:
  * assembles the step's loss scalar on the device from the fp64 accumulators.  src/den

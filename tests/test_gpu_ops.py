@@ -301,6 +301,10 @@ def test_pixel_focal_term(ops, synth):
         scale, out2 = ops.focal_scale(out["acc"], None, 0.75)
         close(out2[1], 0.75 * want, what="focal scaled")
         close(scale, 0.75 / kept, what="focal scale")
+        # the one-launch variant that also assembles the loss scalar: main term + focal term
+        scale2, loss = ops.focal_scale_loss(out["acc"], None, 0.75, 0.5, False)
+        close(scale2, 0.75 / kept, what="focal scale (fused)")
+        close(loss, 0.5 * float(out["acc"][_cabi.ACC_LOSS]) + 0.75 * float(want), what="fused loss scalar")
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -495,6 +499,13 @@ def test_pack_unpack_and_scale(ops):
     assert torch.equal(x, y)
     ops.scale_inplace(y, torch.tensor([0.5]).cuda())
     assert torch.equal(y, x * 0.5)
+    # several tensors of mixed types in one launch; None entries are skipped
+    t1, t2, t3 = torch.randn(5000).cuda(), torch.randn(3, 7).cuda().bfloat16(), torch.randn(1).cuda().half()
+    w1, w2, w3 = t1.clone(), t2.clone(), t3.clone()
+    ops.scale_inplace_multi([t1, None, t2, t3], torch.tensor(1.0).cuda())
+    assert torch.equal(t1, w1) and torch.equal(t2, w2) and torch.equal(t3, w3)
+    ops.scale_inplace_multi([t1, None, t2, t3], torch.tensor(0.25).cuda())
+    assert torch.equal(t1, w1 * 0.25) and torch.equal(t2, w2 * 0.25) and torch.equal(t3, w3 * 0.25)
     a = torch.tensor([2.0, 8.0], dtype=torch.float64).cuda()
     r = ops.combine_scalars([(a, 0, 3.0), (a, 1, 1.0, a, 0)], a.device)
     assert math.isclose(float(r), 2 * 3 + 8 / 2)
