@@ -28,6 +28,8 @@ class PixelArgs(C.Structure):
         ("ignore_index", i32), ("seen_scale", i32),
         ("gamma", f32), ("threshold", f32), ("focal_gamma", f32), ("focal_alpha", f32),
         ("lkd_threshold", f32), ("grad_scale", f32),
+        ("ready", vp), ("focal_scale_out", vp), ("loss_out", vp),
+        ("focal_weight", f32), ("loss_coef", f32), ("loss_over_wsum", i32),
     ]
 
 

@@ -38,6 +38,14 @@ class PixelLossFunction(torch.autograd.Function):
         focal_head = cfg.get("focal_head", -1)
         want_grad = bool(cfg.get("want_grad", True)) and ctx.needs_input_grad[0]
         has_focal = z is not None and focal_head >= 0
+        B, _, H, W = logits.shape
+        scale = cfg.get("loss_scale", 1.0)
+        over_wsum = mode != _cabi.PIX_WEIGHTED_CE
+        main_coef = scale if over_wsum else scale / float(B * H * W)            # WEIGHTED_CE: mean over ALL pixels (Q6)
+        # the reduction launch of the kernel also produces the focal normaliser and the loss scalar
+        epilogue = {"ready": cfg.get("ready") if has_focal else None,
+                    "focal_weight": cfg.get("focal_weight", 1.0) if has_focal else 0.0,
+                    "loss_coef": main_coef, "over_wsum": over_wsum}
         out = ops.pixel_loss(
             logits, labels, mode, want_grad=want_grad, want_preds=True, z=z,
             want_distill_mask=bool(cfg.get("want_distill_mask", False)), focal_head=focal_head if has_focal else -1,
@@ -46,26 +54,16 @@ class PixelLossFunction(torch.autograd.Function):
             focal_gamma=cfg.get("focal_gamma", 2.0), focal_alpha=cfg.get("focal_alpha"),
             lkd_threshold=cfg.get("lkd_threshold", 0.5), ignore_index=cfg.get("ignore_index", 255),
             grad_scale=cfg.get("loss_scale", 1.0), seen_scale=cfg.get("seen_scale", 16),
-            seen_max=cfg.get("seen_max"))
+            seen_max=cfg.get("seen_max"), epilogue=epilogue)
         acc = out["acc"]
-        B, _, H, W = logits.shape
-        scale = cfg.get("loss_scale", 1.0)
-        over_wsum = mode != _cabi.PIX_WEIGHTED_CE
-        main_coef = scale if over_wsum else scale / float(B * H * W)            # WEIGHTED_CE: mean over ALL pixels (Q6)
+        loss = out["loss"].reshape(())
         dweight = dbias = dfeat = None
-        if has_focal:
-            # focal normaliser and the loss scalar (main term + focal term) in one single-thread launch
-            fscale, loss = ops.focal_scale_loss(acc, cfg.get("ready"), cfg.get("focal_weight", 1.0), main_coef, over_wsum)
-            if head_weight is not None and (ctx.needs_input_grad[2] or ctx.needs_input_grad[1]):
-                want_df = bool(cfg.get("features_grad", False)) and ctx.needs_input_grad[1]
-                proto_t = cfg["proto"][focal_head]
-                dweight, dbias, dfeat = ops.seen_head_backward(
-                    features, proto_t, head_weight.detach().reshape(-1).float().contiguous(), out["gz"], fscale, want_df)
-            loss = loss.reshape(())
-        elif over_wsum:
-            loss = ops.combine_scalars([(acc, _cabi.ACC_LOSS, main_coef, acc, _cabi.ACC_WSUM)], logits.device).reshape(())
-        else:
-            loss = ops.combine_scalars([(acc, _cabi.ACC_LOSS, main_coef)], logits.device).reshape(())
+        if has_focal and head_weight is not None and (ctx.needs_input_grad[2] or ctx.needs_input_grad[1]):
+            want_df = bool(cfg.get("features_grad", False)) and ctx.needs_input_grad[1]
+            proto_t = cfg["proto"][focal_head]
+            dweight, dbias, dfeat = ops.seen_head_backward(
+                features, proto_t, head_weight.detach().reshape(-1).float().contiguous(), out["gz"],
+                out["focal_scale"], want_df)
         ctx.grads = (out["dlogits"], dfeat, dweight, dbias)
         ctx.shapes = (None if head_weight is None else head_weight.shape, None if head_bias is None else head_bias.shape,
                       None if head_weight is None else head_weight.dtype)

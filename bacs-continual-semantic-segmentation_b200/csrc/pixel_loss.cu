@@ -544,10 +544,19 @@ __global__ void __launch_bounds__(kConsumers + 32, (KREG > 0 ? 2 : 1)) pixel_los
 }
 
 // Deterministic reduction of the partials: block 0 -> acc; in SCORE mode block 1+b -> score[b].
+struct PixelEpilogue {
+  const int32_t* ready;
+  float* focal_scale_out;
+  float* loss_out;
+  float focal_weight, loss_coef;
+  int loss_over_wsum;
+};
 __global__ void __launch_bounds__(256) pixel_reduce_kernel(const double* __restrict__ partials, int n_part,
                                                            int tiles_per_image, double* __restrict__ acc,
-                                                           double* __restrict__ score, double inv_hw) {
+                                                           double* __restrict__ score, double inv_hw,
+                                                           const PixelEpilogue ep) {
   __shared__ double scratch[8][BACS_NACC];
+  __shared__ double total[BACS_NACC];
   const bool whole = blockIdx.x == 0;
   const int t0 = whole ? 0 : (blockIdx.x - 1) * tiles_per_image;
   const int t1 = whole ? n_part : t0 + tiles_per_image;
@@ -563,8 +572,25 @@ __global__ void __launch_bounds__(256) pixel_reduce_kernel(const double* __restr
   if (threadIdx.x < BACS_NACC) {
     double r = 0.0;
     for (int wv = 0; wv < 8; ++wv) r += scratch[wv][threadIdx.x];
-    if (whole) acc[threadIdx.x] = r;
-    else if (threadIdx.x == BACS_ACC_LOSS) score[blockIdx.x - 1] = -r * inv_hw;
+    if (whole) {
+      acc[threadIdx.x] = r;
+      total[threadIdx.x] = r;
+    } else if (threadIdx.x == BACS_ACC_LOSS) {
+      score[blockIdx.x - 1] = -r * inv_hw;
+    }
+  }
+  if (!whole || (ep.focal_scale_out == nullptr && ep.loss_out == nullptr)) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {  // the step's scalar epilogue (focal normaliser, loss value)
+    const double kept = total[BACS_ACC_KEPT];
+    const bool on = (ep.ready == nullptr || *ep.ready != 0) && total[BACS_ACC_BG] > 0.0 && kept > 0.0;
+    const double fs = on ? (double)ep.focal_weight / kept : 0.0;
+    if (ep.focal_scale_out) *ep.focal_scale_out = (float)fs;
+    if (ep.loss_out) {
+      double main = (double)ep.loss_coef * total[BACS_ACC_LOSS];
+      if (ep.loss_over_wsum) main /= total[BACS_ACC_WSUM];
+      *ep.loss_out = (float)(main + fs * total[BACS_ACC_FOCAL]);
+    }
   }
 }
 
@@ -816,8 +842,15 @@ int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_
 #undef LAUNCH_PIX
   BACS_CHECK_LAUNCH("bacs_pixel_loss");
   const int nblk = 1 + (a->mode == BACS_PIX_SCORE ? a->B : 0);
+  PixelEpilogue ep;
+  ep.ready = a->ready;
+  ep.focal_scale_out = a->focal_scale_out;
+  ep.loss_out = a->loss_out;
+  ep.focal_weight = a->focal_weight;
+  ep.loss_coef = a->loss_coef;
+  ep.loss_over_wsum = a->loss_over_wsum;
   pixel_reduce_kernel<<<nblk, 256, 0, s>>>(p.partials, (int)n_part, p.tiles_per_image, a->acc, a->score,
-                                           1.0 / (double)HW);
+                                           1.0 / (double)HW, ep);
   BACS_CHECK_LAUNCH("bacs_pixel_loss(reduce)");
   return BACS_OK;
 }

@@ -202,7 +202,9 @@ def pixel_loss(logits: torch.Tensor, labels: torch.Tensor, mode: int, *, want_gr
                ukd: bool = True, gamma: float = 2.0, threshold: float = 0.5, focal_gamma: float = 2.0,
                focal_alpha: Optional[float] = None, lkd_threshold: float = 0.5, ignore_index: int = 255,
                grad_scale: float = 1.0, seen_scale: int = 16, want_score: bool = False,
-               seen_max: Optional[torch.Tensor] = None) -> dict:
+               seen_max: Optional[torch.Tensor] = None, epilogue: Optional[dict] = None) -> dict:
+    """``epilogue`` = {"ready": int32 [1] tensor or None, "focal_weight": float, "loss_coef": float,
+    "over_wsum": bool}: the reduction launch also writes out["focal_scale"] and out["loss"] (fp32 [1])."""
     logits = _cuda(logits, "pixel_loss")
     labels = _cuda(labels, "pixel_loss", torch.int64)
     B, K, H, W = logits.shape
@@ -246,6 +248,17 @@ def pixel_loss(logits: torch.Tensor, labels: torch.Tensor, mode: int, *, want_gr
     a.gamma, a.threshold, a.focal_gamma = float(gamma), float(threshold), float(focal_gamma)
     a.focal_alpha = -1.0 if focal_alpha is None else float(focal_alpha)
     a.lkd_threshold, a.grad_scale = float(lkd_threshold), float(grad_scale)
+    out["focal_scale"] = out["loss"] = None
+    a.ready = a.focal_scale_out = a.loss_out = None
+    a.focal_weight = a.loss_coef = 0.0
+    a.loss_over_wsum = 0
+    if epilogue is not None:
+        out["focal_scale"] = torch.empty(1, dtype=torch.float32, device=dev)
+        out["loss"] = torch.empty(1, dtype=torch.float32, device=dev)
+        a.ready = _ptr(epilogue.get("ready"))
+        a.focal_scale_out, a.loss_out = out["focal_scale"].data_ptr(), out["loss"].data_ptr()
+        a.focal_weight, a.loss_coef = float(epilogue.get("focal_weight", 0.0)), float(epilogue["loss_coef"])
+        a.loss_over_wsum = int(bool(epilogue.get("over_wsum", False)))
     lib = _lib()
     nbytes = lib.bacs_pixel_workspace_bytes(C.byref(a))
     if nbytes == 0:

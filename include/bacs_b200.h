@@ -207,6 +207,16 @@ typedef struct bacs_pixel_args {
   float focal_alpha;      /* < 0 = no alpha weighting */
   float lkd_threshold;
   float grad_scale;       /* static multiplier folded into dlogits (e.g. beta) */
+  /* Optional epilogue evaluated by the reduction launch (saves two single-thread launches per step):
+   *   focal_scale_out[0] = focal_weight * [ready] * [#background > 0] / #kept      (as bacs_focal_scale)
+   *   loss_out[0] = loss_coef * acc[LOSS] / (loss_over_wsum ? acc[WSUM] : 1) + focal_scale * acc[FOCAL]
+   * Both pointers NULL = off. */
+  const int32_t* ready;   /* device flag of bacs_proto_update, or NULL = ready */
+  float* focal_scale_out; /* float[1] or NULL */
+  float* loss_out;        /* float[1] or NULL */
+  float focal_weight;
+  float loss_coef;
+  int32_t loss_over_wsum;
 } bacs_pixel_args;
 
 size_t bacs_pixel_workspace_bytes(const bacs_pixel_args* args_host);
