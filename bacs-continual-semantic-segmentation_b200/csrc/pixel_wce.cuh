@@ -279,43 +279,40 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
     int am0, am1;
     Raw<T>::finish(mt, mx0, mx1, am0, am1);
 
-    // ---- one exp per logit; sums in groups of four so that S_old costs one add per full group ------
+    // ---- one exp per logit; sums in groups of four so that S_old costs one add per full group.  The two pixels
+    //      of a thread travel as one packed fp32 pair (FFMA2 / FADD2): half the issue slots of the scalar form ------
     const float nm0 = -mx0 * kLog2e, nm1 = -mx1 * kLog2e;
-    float e0[KREG], e1[KREG];
-    float sa0 = 0.f, sa1 = 0.f, so0 = 0.f, so1 = 0.f;
+    const F2 nm2 = f2(nm0, nm1), l2e2 = f2b(kLog2e);
+    F2 e2[KREG];
+    F2 sa2 = f2b(0.f), so2 = f2b(0.f);
     float x00, x01;
     Raw<T>::unpack(raw[0], x00, x01);
 #pragma unroll
     for (int g = 0; g < (KREG + 3) / 4; ++g) {
-      float g0 = 0.f, g1 = 0.f;
+      F2 g2 = f2b(0.f);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int c = 4 * g + i;
         if (c < KREG) {
           float v0, v1;
           Raw<T>::unpack(raw[c], v0, v1);
-          e0[c] = ex2_fast(fmaf(v0, kLog2e, nm0));
-          e1[c] = ex2_fast(fmaf(v1, kLog2e, nm1));
-          g0 = i == 0 ? e0[c] : g0 + e0[c];
-          g1 = i == 0 ? e1[c] : g1 + e1[c];
+          const F2 arg = fma2(f2(v0, v1), l2e2, nm2);
+          e2[c] = f2(ex2_fast(f2lo(arg)), ex2_fast(f2hi(arg)));
+          g2 = i == 0 ? e2[c] : add2(g2, e2[c]);
         }
       }
-      sa0 += g0;
-      sa1 += g1;
+      sa2 = add2(sa2, g2);
       if (4 * g + 4 <= old_cl) {  // uniform: the whole group is old
-        so0 += g0;
-        so1 += g1;
+        so2 = add2(so2, g2);
       } else if (4 * g < old_cl) {  // uniform: the boundary group
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int c = 4 * g + i;
-          if (c < KREG && c < old_cl) {
-            so0 += e0[c];
-            so1 += e1[c];
-          }
+          if (c < KREG && c < old_cl) so2 = add2(so2, e2[c]);
         }
       }
     }
+    const float sa0 = f2lo(sa2), sa1 = f2hi(sa2), so0 = f2lo(so2), so1 = f2hi(so2);
 
     // ---- per-pixel terms: loss, gradient coefficients, distill mask, focal term (select-only) ------
     //   gradient of pixel = e_c * cg[group(c)] - [c==0] d0 - [c==y] dy,  groups: c == 0 | 1 <= c < old_cl | c >= old_cl
@@ -324,7 +321,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const float mx = j == 0 ? mx0 : mx1, Sa = j == 0 ? sa0 : sa1, So = fmaxf(j == 0 ? so0 : so1, 1e-37f);
-      const float ec0 = j == 0 ? e0[0] : e1[0], x0 = j == 0 ? x00 : x01;
+      const float ec0 = j == 0 ? f2lo(e2[0]) : f2hi(e2[0]), x0 = j == 0 ? x00 : x01;
       const bool valid = y[j] >= 0, isbg = y[j] == 0, isnew = y[j] >= old_cl;
       const float Sfg = fmaxf(Sa - ec0, 1e-37f);
       const float lS = lg2_fast(Sa), iS = rcp_fast(Sa);
@@ -381,28 +378,38 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
 
     // ---- gradient rows, in place ----------------------------------------------------------------------------
     if (want_grad) {
-      Raw<T>::st(col, fmaf(e0[0], cg0[0], -d0[0]), fmaf(e1[0], cg0[1], -d0[1]));
+      const F2 cgo = f2(cg1[0], cg1[1]), cgn = f2(cg2[0], cg2[1]);  // old / new class coefficient of both pixels
+      {
+        const F2 g0 = fma2(e2[0], f2(cg0[0], cg0[1]), f2(-d0[0], -d0[1]));
+        Raw<T>::st(col, f2lo(g0), f2hi(g0));
+      }
 #pragma unroll
       for (int g = 0; g < (KREG + 3) / 4; ++g) {
         if (4 * g + 4 <= old_cl) {  // uniform: old classes only
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int c = 4 * g + i;
-            if (c >= 1 && c < KREG) Raw<T>::st(col + (size_t)c * kBox, e0[c] * cg1[0], e1[c] * cg1[1]);
+            if (c >= 1 && c < KREG) {
+              const F2 gg = mul2(e2[c], cgo);
+              Raw<T>::st(col + (size_t)c * kBox, f2lo(gg), f2hi(gg));
+            }
           }
         } else if (4 * g >= old_cl) {  // uniform: new classes only
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int c = 4 * g + i;
-            if (c >= 1 && c < KREG) Raw<T>::st(col + (size_t)c * kBox, e0[c] * cg2[0], e1[c] * cg2[1]);
+            if (c >= 1 && c < KREG) {
+              const F2 gg = mul2(e2[c], cgn);
+              Raw<T>::st(col + (size_t)c * kBox, f2lo(gg), f2hi(gg));
+            }
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int c = 4 * g + i;
             if (c >= 1 && c < KREG) {
-              const bool oldc = c < old_cl;
-              Raw<T>::st(col + (size_t)c * kBox, e0[c] * (oldc ? cg1[0] : cg2[0]), e1[c] * (oldc ? cg1[1] : cg2[1]));
+              const F2 gg = mul2(e2[c], c < old_cl ? cgo : cgn);
+              Raw<T>::st(col + (size_t)c * kBox, f2lo(gg), f2hi(gg));
             }
           }
         }
