@@ -665,23 +665,30 @@ static bool make_plan(const bacs_pixel_args& a, PixelPlan* plan) {
       }
     // 4 stages of {kreg logit rows, 512 int64 labels, seen-head rows} + one [T][8] float2 strip per warp
     const size_t zrows = a.z ? (((size_t)a.T * 2 * a.w * 4 + 127) & ~(size_t)127) : 0;
-    const size_t smem = (size_t)4 * ((size_t)kreg * 512 * es + 4096 + zrows) + (a.z ? (size_t)8 * a.T * 8 * 8 : 0) + 64;
+    const size_t stage = (size_t)kreg * 512 * es + 4096 + zrows;
+    const size_t tail = (a.z ? (size_t)8 * a.T * 8 * 8 : 0) + 64;
+    // row tiles: a tile lies inside one image row and 64 pixels touch <= 6 low-res columns
+    const bool rowtile = a.z != nullptr && a.W % 512 == 0 && a.seen_scale >= 16 && a.w % 4 == 0 &&
+                         (reinterpret_cast<uintptr_t>(a.z) & 15) == 0;
+    // 228 KB of shared memory per SM, 1 KB reserved per resident CTA, < 0.5 KB static
+    auto two_fit = [](size_t smem) { return 2 * (smem + 1024 + 512) <= (size_t)228 * 1024; };
+    // the training-step kernel also runs with a 3-stage ring when that is what lets two CTAs share an SM
+    const bool wce = rowtile && a.mode == BACS_PIX_WEIGHTED_CE && !a.seen_max && encode_tiled_fn() != nullptr &&
+                     a.w <= 256 && a.T <= 256 && a.K <= 256;
+    int stages = 4;
+    if (wce && !two_fit(4 * stage + tail) && two_fit(3 * stage + tail)) stages = 3;
+    const size_t smem = (size_t)stages * stage + tail;
     if (smem + 1024 <= cap) {
-      // 228 KB of shared memory per SM, 1 KB reserved per resident CTA, < 0.5 KB static
-      const int per_sm = (2 * (smem + 1024 + 512) <= (size_t)228 * 1024) ? 2 : 1;
+      const int per_sm = two_fit(smem) ? 2 : 1;
       const int64_t tiles = HW / 512 * a.B;
       plan->fast = 1;
       plan->ppt = 2;
       plan->P = 512;
       plan->kreg = kreg;
-      plan->stages = 4;
+      plan->stages = stages;
       plan->smem = smem;
       plan->grid = (int)std::min<int64_t>(tiles, (int64_t)sms * per_sm);
-      // row tiles: a tile lies inside one image row and 64 pixels touch <= 6 low-res columns
-      plan->rowtile = (a.z != nullptr && a.W % 512 == 0 && a.seen_scale >= 16 && a.w % 4 == 0 &&
-                       (reinterpret_cast<uintptr_t>(a.z) & 15) == 0)
-                          ? 1
-                          : 0;
+      plan->rowtile = rowtile ? 1 : 0;
       return true;
     }
   }
@@ -816,6 +823,10 @@ int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_
     else LAUNCH_PIX(TT, PPT, 0, false);             \
   } while (0)
   const bool wce = p.use_tmap && wce_eligible(*a, plan);
+  if (plan.fast && plan.stages != 4 && !wce) {
+    set_error("bacs_pixel_loss: tensor-map creation failed for the 3-stage training kernel");
+    return BACS_ERR_CUDA;
+  }
   if (wce) {  // the training step's kernel
     int rc;
     switch (a->dtype) {

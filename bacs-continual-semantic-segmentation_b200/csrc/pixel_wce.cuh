@@ -67,14 +67,15 @@ template <> struct NegInf<__half> {
 // Shared memory (dynamic): 4 stages of { [2][KREG][256] logits, 512 int64 labels, [T][2][w] seen-head rows }
 // followed by one warp-private [T][8] strip of float2 per warp.
 // STD: the reference's hyper-parameters (gamma = focal gamma = 2, no alpha weighting, ukd) folded at compile time.
-template <typename T, int KREG, bool STD>
+template <typename T, int KREG, bool STD, int S>
 __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid_constant__ PixelParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar_full[4];
   __shared__ uint64_t bar_done[4];
   __shared__ float red_scratch[8][BACS_NACC];
 
-  constexpr int P = kFastP, S = 4;
+  constexpr int P = kFastP;
+  static_assert(S == 3 || S == 4, "ring depth");
   constexpr int KMIN = wce_kmin(KREG);
   constexpr size_t tile_bytes_smem = (size_t)KREG * P * sizeof(T);
   const bacs_pixel_args& a = p.a;
@@ -118,11 +119,13 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
     b = g / tpi;
     t = g - b * tpi;
   };
+  auto slot_of = [](int k) { return k % S; };
+  auto phase_of = [](int k) { return (uint32_t)((k / S) & 1); };
   const uint32_t tx_bytes = (uint32_t)K * (uint32_t)(P * sizeof(T)) + kLabelBytes + zrow_bytes;
   auto issue_load = [&](int k) {
     int b, t;
     tile_coords(k, b, t);
-    const int s = k & (S - 1);
+    const int s = slot_of(k);
     mbar_expect_tx(&bar_full[s], tx_bytes);
     T* dst = stage_tile(s);
     const Lerp ly = lerp_align_corners(row_of_tile(t), a.h, p.sy);
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
   auto issue_store = [&](int k) {
     int b, t;
     tile_coords(k, b, t);
-    const T* src = stage_tile(k & (S - 1));
+    const T* src = stage_tile(slot_of(k));
     tma_store_3d(&p.tmap_out, t * P, 0, b, src);
     tma_store_3d(&p.tmap_out, t * P + kBox, 0, b, src + (size_t)KREG * kBox);
     bulk_commit();
@@ -194,14 +197,14 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
       tt -= tpi;
       ++tb;
     }
-    const int s = k & (S - 1);
+    const int s = slot_of(k);
     T* tile = stage_tile(s);
     const int Yrow = row_of_tile(t_in);
     const Lerp ly_row = lerp_align_corners(Yrow, a.h, p.sy);
     if (!tpr1) set_x((t_in - Yrow * tiles_per_row) * P + wid * 64);
 
     // ---- wait for the tile (logit rows + labels + seen-head rows) -------------------------------
-    mbar_wait_sleepy(&bar_full[s], (uint32_t)((k >> 2) & 1));
+    mbar_wait_sleepy(&bar_full[s], phase_of(k));
     const longlong2 lab = *reinterpret_cast<const longlong2*>(stage_labels(s) + px0);
 
     // ---- seen heads of this warp's 64 pixels: y-interpolated strip, stored per low-res column c as
@@ -426,20 +429,31 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
     }
     mbar_arrive(&bar_done[s]);
 
-    // ---- tile owners: write tile k-1 back; refill the stage of tile k-2 with tile k+2 ------------------
+    // ---- tile owners: write tile k-1 back; refill a drained stage with tile k+2 ---------------------------
+    // 4 stages: tile k+2 goes into the stage of tile k-2, whose owner stored it one iteration ago.
+    // 3 stages (when two CTAs per SM only fit that way): tile k+2 goes into the stage of tile k-1, so its owner
+    // stores, waits for the store to have read the stage, and reloads in the same visit.
     if (k >= 1 && wid == ((k - 1) & 7)) {
       if (elect_one()) {
-        mbar_wait(&bar_done[(k - 1) & (S - 1)], (uint32_t)(((k - 1) >> 2) & 1));  // gradients of tile k-1 written
+        mbar_wait(&bar_done[slot_of(k - 1)], phase_of(k - 1));  // gradients of tile k-1 written
         if (want_grad) issue_store(k - 1);
+        if (S == 3) {
+          if (want_grad) bulk_wait_read0();
+          if (k + 2 < my_tiles) issue_load(k + 2);
+        }
       }
       __syncwarp();
     }
-    if (wid == ((k + 6) & 7)) {
+    if (S == 4 && wid == ((k + 6) & 7)) {
       if (elect_one()) {
         // this lane waited for bar_done of tile k-2 one iteration ago; its store has had a tile to drain
         if (want_grad) bulk_wait_read0();
         if (k + 2 < my_tiles) issue_load(k + 2);
       }
+      __syncwarp();
+    }
+    if (S == 3 && k == 0 && wid == 7) {  // the third stage is still fresh: nothing to drain
+      if (elect_one() && 2 < my_tiles) issue_load(2);
       __syncwarp();
     }
 
@@ -486,7 +500,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
     const int kl = my_tiles - 1;
     if (elect_one()) {
       if (wid == (kl & 7)) {
-        mbar_wait(&bar_done[kl & (S - 1)], (uint32_t)((kl >> 2) & 1));
+        mbar_wait(&bar_done[slot_of(kl)], phase_of(kl));
         if (want_grad) issue_store(kl);
       }
       bulk_wait_all();
@@ -521,7 +535,8 @@ template <typename T, int KREG>
 static int launch_wce_one(const PixelParams& p, const PixelPlan& plan, cudaStream_t s) {
   const bacs_pixel_args& a = p.a;
   const bool std_hp = a.gamma == 2.f && a.ukd && (!a.gz || (a.focal_gamma == 2.f && a.focal_alpha < 0.f));
-  auto kern = std_hp ? pixel_wce_kernel<T, KREG, true> : pixel_wce_kernel<T, KREG, false>;
+  auto kern = plan.stages == 3 ? (std_hp ? pixel_wce_kernel<T, KREG, true, 3> : pixel_wce_kernel<T, KREG, false, 3>)
+                               : (std_hp ? pixel_wce_kernel<T, KREG, true, 4> : pixel_wce_kernel<T, KREG, false, 4>);
   if (plan.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) {

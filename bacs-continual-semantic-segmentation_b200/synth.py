@@ -65,6 +65,11 @@ CONFIGS = {
     "row512_k17": StepConfig("row512_k17", B=2, K=17, old_cl=16, T=2, H=32, W=512, D=32, A=16),
     "row512_k11": StepConfig("row512_k11", B=1, K=11, old_cl=6, T=11, H=32, W=512, D=32, A=16, initial_classes=6,
                              increment=5),
+    # 3-stage ring of the training-step kernel: many seen heads / 24 register rows
+    "row512_t11": StepConfig("row512_t11", B=1, K=21, old_cl=20, T=11, H=32, W=512, D=32, A=16, initial_classes=11,
+                             increment=1),
+    "row512_k24": StepConfig("row512_k24", B=1, K=24, old_cl=20, T=3, H=32, W=512, D=32, A=16, initial_classes=20,
+                             increment=2),
     "row512_k7": StepConfig("row512_k7", B=1, K=7, old_cl=5, T=3, H=32, W=512, D=32, A=16, initial_classes=3,
                             increment=2),
 }
