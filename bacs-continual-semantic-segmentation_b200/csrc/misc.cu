@@ -51,26 +51,51 @@ __global__ void __launch_bounds__(256) der_cut_kernel(const int64_t* __restrict_
   __shared__ int present[1024];
   __shared__ int rank_of[1024];
   __shared__ int uniq[1024];
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) present[i] = 0;
+  __shared__ int warp_tot[8];
+  __shared__ int s_first[1024];  // class count (clamped) of the first min(Br, 1024) samples
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  auto clampv = [](int64_t n) { return n < 0 ? 0 : (n > 1023 ? 1023 : (int)n); };
+  for (int i = tid; i < 1024; i += blockDim.x) present[i] = 0;
   __syncthreads();
-  for (int j = threadIdx.x; j < Br; j += blockDim.x) {
-    const int64_t n = n_classes[j];
-    present[n < 0 ? 0 : (n > 1023 ? 1023 : (int)n)] = 1;
+  for (int j = tid; j < Br; j += blockDim.x) {
+    const int v = clampv(n_classes[j]);
+    present[v] = 1;
+    if (j < 1024) s_first[j] = v;
     cut[j] = K;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  // rank of every present value = exclusive prefix count: thread t owns values 4t .. 4t+3 (block scan)
+  int p[4], mine = 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    p[e] = present[4 * tid + e];
+    mine += p[e];
+  }
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  int base = incl - mine;
+  for (int wv = 0; wv < wid; ++wv) base += warp_tot[wv];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    if (p[e]) {
+      rank_of[4 * tid + e] = base;
+      uniq[base] = 4 * tid + e;
+      ++base;
+    }
+  __syncthreads();
+  if (tid == 0) {
     int r = 0;
-    for (int v = 0; v < 1024; ++v)
-      if (present[v]) {
-        rank_of[v] = r;
-        uniq[r] = v;
-        ++r;
-      }
-    // sequential like the reference's Python loop (later writes win, all are mins of the same slot)
+    for (int wv = 0; wv < 8; ++wv) r += warp_tot[wv];
+    // sequential like the reference's Python loop (later writes win, all are mins of the same slot);
+    // i < r <= 1024 distinct values and i < Br, so s_first covers every sample the loop reads
     for (int i = 0; i < r && i < Br; ++i) {
-      const int64_t nj = n_classes[i];
-      const int j = rank_of[nj < 0 ? 0 : (nj > 1023 ? 1023 : (int)nj)];  // inv[i]
+      const int j = rank_of[s_first[i]];  // inv[i]
       if (uniq[i] < K && j < Br) cut[j] = min(cut[j], uniq[i]);
     }
   }

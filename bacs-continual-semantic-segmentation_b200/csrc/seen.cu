@@ -55,7 +55,7 @@ __device__ __forceinline__ void load_px(const T* p, float* v) {
 // has enough CTAs to fill the machine while the summation order stays fixed.
 // Per channel the T (weight, sigmoid(proto)) pairs sit in one shared-memory row read with broadcast 128-bit loads.
 template <typename T, int TMAX, int PX>
-__global__ void __launch_bounds__(32 * kSeenWarps, (TMAX * PX <= 32 ? 3 : 1)) seen_logits_kernel(const T* __restrict__ feat, int D, int hw,
+__global__ void __launch_bounds__(32 * kSeenWarps, (TMAX * PX <= 32 ? 3 : (TMAX * PX <= 48 ? 2 : 1))) seen_logits_kernel(const T* __restrict__ feat, int D, int hw,
                                                                        const float* __restrict__ proto,
                                                                        const float* __restrict__ weight,
                                                                        const float* __restrict__ bias, int Tn,
@@ -369,14 +369,15 @@ int bacs_seen_logits(const void* features, int dtype, int B, int D, int h, int w
   BACS_REQUIRE(T > 0 && T <= 32, "bacs_seen_logits: T=%d not in [1,32]", T);
   const int hw = h * w;
   const int tmax = T <= 2 ? 2 : (T <= 4 ? 4 : (T <= 6 ? 6 : (T <= 8 ? 8 : (T <= 12 ? 12 : (T <= 16 ? 16 : 32)))));
-  int px = tmax <= 8 ? 4 : (tmax <= 16 ? 2 : 1);
+  int px = tmax <= 8 ? 4 : (tmax <= 16 ? 2 : 1);   // measured: 4 pixels x 12 heads (112 registers) is slower than 2 x 12
   const size_t es = dtype_size(dtype);
   if (hw % px != 0 || (reinterpret_cast<uintptr_t>(features) % (px * es)) != 0) px = 1;
   const int ps = 32 * px;
   const int n_pb = (hw + ps - 1) / ps;
-  // cluster size: split the channels while the whole grid still fits the machine in one wave (3 CTAs per SM)
+  // cluster size: split the channels while the whole grid still fits the machine in one wave
+  const int per_sm = tmax * px <= 32 ? 3 : (tmax * px <= 48 ? 2 : 1);  // resident CTAs (register budget, see the kernel)
   int cs = 1;
-  while (cs < 8 && (int64_t)n_pb * B * cs * 2 <= (int64_t)3 * sm_count() && D / (2 * cs) >= 2 * kSeenWarps) cs *= 2;
+  while (cs < 8 && (int64_t)n_pb * B * cs * 2 <= (int64_t)per_sm * sm_count() && D / (2 * cs) >= 2 * kSeenWarps) cs *= 2;
   const int stride = 2 * tmax;
   const int per = (D + cs - 1) / cs;
   int chunk = (32 * 1024 / 4) / stride;  // table of <= 32 KB
