@@ -99,8 +99,8 @@ __global__ void __launch_bounds__(256) distill_moments_kernel(const uint8_t* __r
 #define BACS_DISTILL_RB 4
 #endif
 constexpr int kDistillWarps = 8;
-constexpr int kChanPerWarp = 2;
-constexpr int kChanPerCta = kDistillWarps * kChanPerWarp;
+// channels per warp: 2 when a lane owns one low-res column (w <= 32), 1 for wider maps (register budget)
+__host__ __device__ constexpr int distill_nc(int cpl) { return cpl == 1 ? 2 : 1; }
 
 // Value of a quantity that is linear in the row weight ty:  v(ty) = p + q * ty.
 struct Lin {
@@ -156,7 +156,7 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
 //   dL/da_n = -rs (u0 2a_n + u1 2d_n), dL/dd_n = -rs (u1 2a_n + u2 2d_n), 2a_n = sigma - alpha, 2d_n = eps - delta,
 //   accumulated against {1, ty} so that the corner gradients are assembled once per interval.
 template <typename T, int CPL>
-__global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T* __restrict__ old_att,
+__global__ void __launch_bounds__(32 * kDistillWarps, (CPL <= 2 ? 2 : 1)) distill_kernel(const T* __restrict__ old_att,
                                                                       const T* __restrict__ new_att, int A, int h,
                                                                       int w, int H, DistillTables tb,
                                                                       const float* __restrict__ moments, int rows_max,
@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T*
   __shared__ uint64_t mom_bar[3];   // moments of an interval have landed (TMA expect-tx)
   __shared__ uint64_t free_bar[3];  // all warps are done with the buffer
   constexpr int WP = 32 * CPL;
-  constexpr int NC = kChanPerWarp;
+  constexpr int NC = distill_nc(CPL);
+  constexpr int kChanPerWarp = NC, kChanPerCta = kDistillWarps * NC;
   constexpr unsigned kFull = 0xffffffffu;
   const size_t mom_stride = (size_t)rows_max * 5 * WP;
   float* s_ty = s_dyn + 3 * mom_stride;
@@ -362,43 +363,73 @@ __global__ void __launch_bounds__(32 * kDistillWarps, 2) distill_kernel(const T*
       // Transposed butterfly over the 8 row sums of this call (2 row pairs x 2 channels x 2 halves): every level
       // halves the number of sums a lane still carries, so 7 + 2 shuffles replace 5 x 8, and ONE rsqrt per lane
       // serves all eight rows.  Afterwards lane l holds the total of row sum (l >> 2) & 7.
-      static_assert(NC == 2, "the transposed reduction is written for two channels per warp");
-      const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0, up4 = (lane & 4) != 0;
-      F2 k0, k1;
-      {
-        const F2 send0 = up16 ? S[0][0] : S[1][0], send1 = up16 ? S[0][1] : S[1][1];
-        const F2 keep0 = up16 ? S[1][0] : S[0][0], keep1 = up16 ? S[1][1] : S[0][1];
-        F2 r0, r1;
-        r0.v = __shfl_xor_sync(kFull, send0.v, 16);
-        r1.v = __shfl_xor_sync(kFull, send1.v, 16);
-        k0 = add2(keep0, r0);
-        k1 = add2(keep1, r1);
+      float rs_mine = 0.f;
+      float rs_all[RP][NC][2];
+      if constexpr (NC == 2) {
+        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0, up4 = (lane & 4) != 0;
+        F2 k0, k1;
+        {
+          const F2 send0 = up16 ? S[0][0] : S[1][0], send1 = up16 ? S[0][1] : S[1][1];
+          const F2 keep0 = up16 ? S[1][0] : S[0][0], keep1 = up16 ? S[1][1] : S[0][1];
+          F2 r0, r1;
+          r0.v = __shfl_xor_sync(kFull, send0.v, 16);
+          r1.v = __shfl_xor_sync(kFull, send1.v, 16);
+          k0 = add2(keep0, r0);
+          k1 = add2(keep1, r1);
+        }
+        F2 kk;
+        {
+          const F2 send = up8 ? k0 : k1, keep = up8 ? k1 : k0;
+          F2 r;
+          r.v = __shfl_xor_sync(kFull, send.v, 8);
+          kk = add2(keep, r);
+        }
+        float tot;
+        {
+          const float lo = f2lo(kk), hi = f2hi(kk);
+          const float send = up4 ? lo : hi, keep = up4 ? hi : lo;
+          tot = keep + __shfl_xor_sync(kFull, send, 4);
+        }
+        tot += __shfl_xor_sync(kFull, tot, 2);
+        tot += __shfl_xor_sync(kFull, tot, 1);
+        // zero (or rounding-negative) row: norm 0 and sub-gradient 0, as torch's norm backward
+        rs_mine = tot > 0.f ? rsqrt_fast(tot) : 0.f;
+        loss_quad = fmaf(tot, rs_mine, loss_quad);  // every row sum is held by 4 lanes: scaled by 1/4 at the end
+      } else {  // one channel per warp: plain butterfly, every lane ends up with every row sum
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int q = 0; q < RP; ++q)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              F2 other;
+              other.v = __shfl_xor_sync(kFull, S[q][c].v, o);
+              S[q][c] = add2(S[q][c], other);
+            }
+#pragma unroll
+        for (int q = 0; q < RP; ++q)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const float sa = f2lo(S[q][c]), sb = f2hi(S[q][c]);
+            rs_all[q][c][0] = sa > 0.f ? rsqrt_fast(sa) : 0.f;
+            rs_all[q][c][1] = sb > 0.f ? rsqrt_fast(sb) : 0.f;
+            loss_acc = fmaf(sa, rs_all[q][c][0], loss_acc);
+            loss_acc = fmaf(sb, rs_all[q][c][1], loss_acc);
+          }
       }
-      F2 kk;
-      {
-        const F2 send = up8 ? k0 : k1, keep = up8 ? k1 : k0;
-        F2 r;
-        r.v = __shfl_xor_sync(kFull, send.v, 8);
-        kk = add2(keep, r);
-      }
-      float tot;
-      {
-        const float lo = f2lo(kk), hi = f2hi(kk);
-        const float send = up4 ? lo : hi, keep = up4 ? hi : lo;
-        tot = keep + __shfl_xor_sync(kFull, send, 4);
-      }
-      tot += __shfl_xor_sync(kFull, tot, 2);
-      tot += __shfl_xor_sync(kFull, tot, 1);
-      // zero (or rounding-negative) row: norm 0 and sub-gradient 0, as torch's norm backward
-      const float rs_mine = tot > 0.f ? rsqrt_fast(tot) : 0.f;
-      loss_quad = fmaf(tot, rs_mine, loss_quad);  // every row sum is held by 4 lanes: scaled by 1/4 at the end
       if (want_grad) {
 #pragma unroll
         for (int q = 0; q < RP; ++q) {
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
-            const float rsa = __shfl_sync(kFull, rs_mine, q * 16 + c * 8);
-            const float rsb = __shfl_sync(kFull, rs_mine, q * 16 + c * 8 + 4);
+            float rsa, rsb;
+            if constexpr (NC == 2) {
+              rsa = __shfl_sync(kFull, rs_mine, q * 16 + c * 8);
+              rsb = __shfl_sync(kFull, rs_mine, q * 16 + c * 8 + 4);
+            } else {
+              rsa = rs_all[q][c][0];
+              rsb = rs_all[q][c][1];
+            }
             const F2 rs = f2(rsa, rsb);
             const F2 rst = mul2(rs, ty2[q]);
 #pragma unroll
@@ -576,7 +607,8 @@ static DistillLayout distill_layout(int B, int A, int h, int w, int H, int W) {
   l.off_rowstart = take(sizeof(int) * (h + 1));
   l.off_colstart = take(sizeof(int) * (w + 1));
   l.off_moments = take(sizeof(float) * (size_t)B * H * 5 * w);
-  l.n_cta_x = (A + kChanPerCta - 1) / kChanPerCta;
+  const int chan_per_cta = kDistillWarps * distill_nc(w <= 32 ? 1 : (w <= 64 ? 2 : 4));
+  l.n_cta_x = (A + chan_per_cta - 1) / chan_per_cta;
   l.off_partials = take(sizeof(double) * (size_t)std::max(2 * sm_count(), 1024));
   l.total = o;
   return l;

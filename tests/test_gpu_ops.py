@@ -382,7 +382,9 @@ def test_pixel_all_ignored_and_invalid(ops):
 # teacher distill / DER
 # --------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name,dtype,with_mask", [("tiny", torch.float32, True), ("tiny", torch.float32, False),
-                                                  ("small", torch.float32, True), ("small", torch.bfloat16, True)])
+                                                  ("small", torch.float32, True), ("small", torch.bfloat16, True),
+                                                  ("row512", torch.float32, True), ("row1024", torch.float32, True),
+                                                  ("row1024", torch.bfloat16, False), ("wide1536", torch.float32, True)])
 def test_teacher_distill(ops, synth, name, dtype, with_mask):
     cfg = synth.CONFIGS[name]
     inp = synth.make_step_inputs(cfg, seed=6, dtype=dtype)
