@@ -26,7 +26,7 @@ namespace bacs {
 
 // Shared-memory layout (dynamic): [stages][K*P] tiles | zr[T][w] | gacc[w+1]
 template <typename T, int PPT, int KREG, bool ROWTILE>
-__global__ void __launch_bounds__(kConsumers + 32, (KREG > 0 ? 2 : 1)) pixel_loss_kernel(const PixelParams p) {
+__global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 : 1)) pixel_loss_kernel(const PixelParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar_full[kMaxStages];  // producer -> consumers: tile landed
   __shared__ uint64_t bar_done[kMaxStages];  // consumers -> producer: gradients written; store / refill the stage
@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(kConsumers + 32, (KREG > 0 ? 2 : 1)) pixel_los
           mx[j] = -INFINITY;
           s_all[j] = s_old[j] = 0.f;
         }
+        #pragma unroll 8
         for (int c = 0; c < K; ++c) {
           Vec<T, PPT>::ld(col + (size_t)c * P, v);
 #pragma unroll
@@ -355,6 +356,7 @@ __global__ void __launch_bounds__(kConsumers + 32, (KREG > 0 ? 2 : 1)) pixel_los
         }
 #pragma unroll
         for (int j = 0; j < PPT; ++j) nm[j] = -mx[j] * kLog2e;
+        #pragma unroll 8
         for (int c = 0; c < old_cl; ++c) {
           Vec<T, PPT>::ld(col + (size_t)c * P, v);
 #pragma unroll
@@ -362,6 +364,7 @@ __global__ void __launch_bounds__(kConsumers + 32, (KREG > 0 ? 2 : 1)) pixel_los
         }
 #pragma unroll
         for (int j = 0; j < PPT; ++j) s_all[j] = s_old[j];
+        #pragma unroll 8
         for (int c = old_cl; c < K; ++c) {
           Vec<T, PPT>::ld(col + (size_t)c * P, v);
 #pragma unroll
@@ -378,12 +381,14 @@ __global__ void __launch_bounds__(kConsumers + 32, (KREG > 0 ? 2 : 1)) pixel_los
 #pragma unroll
           for (int j = 0; j < PPT; ++j) g[j] = e0[j] * pc[j].cg0 - pc[j].d0;
           Vec<T, PPT>::st(col, g);
+          #pragma unroll 8
           for (int c = 1; c < old_cl; ++c) {
             Vec<T, PPT>::ld(col + (size_t)c * P, v);
 #pragma unroll
             for (int j = 0; j < PPT; ++j) g[j] = ex2_fast(fmaf(v[j], kLog2e, nm[j])) * pc[j].cg1;
             Vec<T, PPT>::st(col + (size_t)c * P, g);
           }
+          #pragma unroll 8
           for (int c = max(old_cl, 1); c < K; ++c) {
             Vec<T, PPT>::ld(col + (size_t)c * P, v);
 #pragma unroll
@@ -709,11 +714,25 @@ static bool make_plan(const bacs_pixel_args& a, PixelPlan* plan) {
         }
       if (!stages) continue;
       const int64_t tiles = (HW + P - 1) / P * a.B;
+      size_t smem = (size_t)stages * tile + extra;
+      int per_sm = 1;
+      if (ppt == 1) {
+        // large K: one pixel per thread.  Two CTAs per SM double the warps that hide latency; when two stages each
+        // do not fit, one stage each still overlaps -- one CTA computes while the other one loads / stores.
+        auto two_fit = [](size_t sm) { return 2 * (sm + 1024 + 512) <= (size_t)228 * 1024; };
+        for (int st = std::min(stages, 2); st >= 1; --st)
+          if (two_fit((size_t)st * tile + extra)) {
+            stages = st;
+            smem = (size_t)st * tile + extra;
+            per_sm = 2;
+            break;
+          }
+      }
       plan->ppt = ppt;
       plan->P = P;
       plan->stages = stages;
-      plan->smem = (size_t)stages * tile + extra;
-      plan->grid = (int)std::min<int64_t>(tiles, (int64_t)sms);
+      plan->smem = smem;
+      plan->grid = (int)std::min<int64_t>(tiles, (int64_t)sms * per_sm);
       plan->rowtile = (a.z != nullptr && P <= a.W && a.W % P == 0) ? 1 : 0;
       return true;
     }
