@@ -292,7 +292,7 @@ __device__ __forceinline__ void pixel_terms(const bacs_pixel_args& a, float inv_
 
 
 struct PixelPlan {
-  int ppt, P, kreg, stages, grid, rowtile, fast;
+  int ppt, P, kreg, stages, grid, rowtile, fast, coop;
   size_t smem;
 };
 

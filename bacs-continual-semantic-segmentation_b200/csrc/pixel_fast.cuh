@@ -33,6 +33,7 @@ template <> struct Raw<float> {
   __device__ static __forceinline__ void fill(float* p, float v) { *p = v; }
   __device__ static __forceinline__ void unpack(reg_t r, float& a, float& b) { a = r.x; b = r.y; }
   __device__ static __forceinline__ Max init(reg_t r) { return Max{r.x, r.y, 0, 0}; }
+  __device__ static __forceinline__ void set_first(Max& m, int c) { m.a0 = m.a1 = c; }
   __device__ static __forceinline__ void update(Max& m, reg_t r, int c) {
     if (r.x > m.m0) { m.m0 = r.x; m.a0 = c; }
     if (r.y > m.m1) { m.m1 = r.y; m.a1 = c; }
@@ -57,6 +58,7 @@ template <> struct Raw<__nv_bfloat16> {
     b = __uint_as_float(u & 0xffff0000u);
   }
   __device__ static __forceinline__ Max init(reg_t r) { return Max{*reinterpret_cast<__nv_bfloat162*>(&r), 0u}; }
+  __device__ static __forceinline__ void set_first(Max& m, int c) { m.a = (uint32_t)c | ((uint32_t)c << 16); }
   __device__ static __forceinline__ void update(Max& m, reg_t r, int c) {
     const __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&r);
     const uint32_t mask = __hgt2_mask(v, m.m);
@@ -86,6 +88,7 @@ template <> struct Raw<__half> {
     a = f.x; b = f.y;
   }
   __device__ static __forceinline__ Max init(reg_t r) { return Max{*reinterpret_cast<__half2*>(&r), 0u}; }
+  __device__ static __forceinline__ void set_first(Max& m, int c) { m.a = (uint32_t)c | ((uint32_t)c << 16); }
   __device__ static __forceinline__ void update(Max& m, reg_t r, int c) {
     const __half2 v = *reinterpret_cast<__half2*>(&r);
     const uint32_t mask = __hgt2_mask(v, m.m);

@@ -20,12 +20,16 @@
 // plus 8 + 8 (+1) bytes per pixel, and the consumers never wait for a store.
 #include <algorithm>
 
-#include "pixel_common.cuh"
+#include "pixel_fast.cuh"  // Raw<T>: packed pixel pairs
 
 namespace bacs {
 
-// Shared-memory layout (dynamic): [stages][K*P] tiles | zr[T][w] | gacc[w+1]
-template <typename T, int PPT, int KREG, bool ROWTILE>
+// Shared-memory layout (dynamic): [stages][K*PITCH] tiles | zr[T][w] | gacc[w+1]
+// COOP (large K, one pixel per thread for everything per-pixel): the two threads of an even/odd lane pair walk the
+// channel loops together on their two adjacent pixels as PACKED pairs, each taking every other channel, and
+// exchange max / arg-max / sums / coefficients by shuffle.  Rows are 64 bytes longer than P elements so that the
+// two halves of a warp (rows c and c+1) hit disjoint banks.
+template <typename T, int PPT, int KREG, bool ROWTILE, bool COOP = false>
 __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 : 1)) pixel_loss_kernel(const PixelParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar_full[kMaxStages];  // producer -> consumers: tile landed
@@ -35,9 +39,10 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
 
   const bacs_pixel_args& a = p.a;
   const int P = p.P, K = a.K, S = p.stages;
+  const int PITCH = COOP ? P + 64 / (int)sizeof(T) : P;  // elements between channel rows of a tile
   const int tid = threadIdx.x;
   const int64_t HW = (int64_t)a.H * a.W;
-  const size_t tile_elems = (size_t)K * P;
+  const size_t tile_elems = (size_t)K * PITCH;
   T* tiles = reinterpret_cast<T*>(smem_raw);
   float* zr = reinterpret_cast<float*>(smem_raw + ((S * tile_elems * sizeof(T) + 15) / 16) * 16);
   float* gacc = zr + (ROWTILE ? a.T * a.w : 0);
@@ -86,10 +91,10 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
         if (lane == 0) mbar_expect_tx(&bar_full[s], (uint32_t)(K * npx * (int)sizeof(T)));
         __syncwarp();
         for (int c = lane; c < K; c += 32)
-          bulk_g2s(dst + (size_t)c * P, src + (int64_t)c * HW, (uint32_t)(npx * sizeof(T)), &bar_full[s]);
+          bulk_g2s(dst + (size_t)c * PITCH, src + (int64_t)c * HW, (uint32_t)(npx * sizeof(T)), &bar_full[s]);
       } else {  // ragged / unaligned rows: plain copies by the producer warp
         for (int c = 0; c < K; ++c)
-          for (int i = lane; i < npx; i += 32) dst[(size_t)c * P + i] = src[(int64_t)c * HW + i];
+          for (int i = lane; i < npx; i += 32) dst[(size_t)c * PITCH + i] = src[(int64_t)c * HW + i];
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_full[s]);
       }
@@ -108,12 +113,12 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
         const bool bulk = p.use_bulk && ((npx * (int)sizeof(T)) & 15) == 0;
         if (bulk) {
           for (int c = lane; c < K; c += 32)
-            bulk_s2g(dst + (int64_t)c * HW, src + (size_t)c * P, (uint32_t)(npx * sizeof(T)));
+            bulk_s2g(dst + (int64_t)c * HW, src + (size_t)c * PITCH, (uint32_t)(npx * sizeof(T)));
           bulk_commit();
           if (k + S < my_tiles) bulk_wait_read0();  // the stage is about to be refilled
         } else {
           for (int c = 0; c < K; ++c)
-            for (int i = lane; i < npx; i += 32) dst[(int64_t)c * HW + i] = src[(size_t)c * P + i];
+            for (int i = lane; i < npx; i += 32) dst[(int64_t)c * HW + i] = src[(size_t)c * PITCH + i];
         }
         __syncwarp();
       }
@@ -264,6 +269,7 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
     // ---- wait for the tile, softmax statistics, gradients ------------------------------
     mbar_wait(&bar_full[s], (uint32_t)((k / S) & 1));
     const bool live = px0 < npx;
+    const unsigned live_mask = __ballot_sync(0xffffffffu, live);  // (cooperative path: pairs are live together)
     PixCoef pc[PPT];
     float gfoc[PPT];
     uint8_t dmask[PPT];
@@ -279,7 +285,7 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
       float xy[PPT], x0[PPT];
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
-        xy[j] = (y[j] >= 0) ? DT<T>::to_f(col[(size_t)y[j] * P + j]) : 0.f;
+        xy[j] = (y[j] >= 0) ? DT<T>::to_f(col[(size_t)y[j] * PITCH + j]) : 0.f;
         x0[j] = DT<T>::to_f(col[j]);
       }
       if (KREG > 0) {
@@ -333,8 +339,89 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
                 if (c == 0) g[j] -= pc[j].d0;
                 if (c == y[j]) g[j] -= pc[j].dy;
               }
-              Vec<T, PPT>::st(col + (size_t)c * P, g);
+              Vec<T, PPT>::st(col + (size_t)c * PITCH, g);
             }
+        }
+      } else if constexpr (COOP) {
+        // ---------------- cooperative packed path (large K) ----------------
+        static_assert(!COOP || PPT == 1, "one pixel per thread");
+        const unsigned full = live_mask;
+        const int half = tid & 1;                    // this thread takes channels half, half + 2, ...
+        T* colp = tile + (px0 & ~1);                 // the pair's first pixel
+        // pass 1: packed max / arg-max over my channels, then merged with the partner's (ties -> lowest channel)
+        typename Raw<T>::Max mt = Raw<T>::init(Raw<T>::ld(colp + (size_t)half * PITCH));
+        Raw<T>::set_first(mt, half);
+#pragma unroll 4
+        for (int c = half + 2; c < K; c += 2) Raw<T>::update(mt, Raw<T>::ld(colp + (size_t)c * PITCH), c);
+        float m0, m1;
+        int a0, a1;
+        Raw<T>::finish(mt, m0, m1, a0, a1);
+        {
+          const float pm0 = __shfl_xor_sync(full, m0, 1), pm1 = __shfl_xor_sync(full, m1, 1);
+          const int pa0 = __shfl_xor_sync(full, a0, 1), pa1 = __shfl_xor_sync(full, a1, 1);
+          if (pm0 > m0 || (pm0 == m0 && pa0 < a0)) { m0 = pm0; a0 = pa0; }
+          if (pm1 > m1 || (pm1 == m1 && pa1 < a1)) { m1 = pm1; a1 = pa1; }
+        }
+        // pass 2: exponent sums of both pixels as packed pairs; old and new classes in separate loops
+        const F2 nm2 = f2(-m0 * kLog2e, -m1 * kLog2e), l2e2 = f2b(kLog2e);
+        auto exp_pair = [&](int c) {
+          float v0, v1;
+          Raw<T>::unpack(Raw<T>::ld(colp + (size_t)c * PITCH), v0, v1);
+          const F2 arg = fma2(f2(v0, v1), l2e2, nm2);
+          return f2(ex2_fast(f2lo(arg)), ex2_fast(f2hi(arg)));
+        };
+        F2 so2 = f2b(0.f), sn2 = f2b(0.f);
+#pragma unroll 4
+        for (int c = half; c < old_cl; c += 2) so2 = add2(so2, exp_pair(c));
+#pragma unroll 4
+        for (int c = old_cl + ((old_cl ^ half) & 1); c < K; c += 2) sn2 = add2(sn2, exp_pair(c));
+        {
+          F2 po, pn;
+          po.v = __shfl_xor_sync(full, so2.v, 1);
+          pn.v = __shfl_xor_sync(full, sn2.v, 1);
+          so2 = add2(so2, po);
+          sn2 = add2(sn2, pn);
+        }
+        const F2 sa2 = add2(so2, sn2);
+        const F2 e02 = exp_pair(0);
+        // per-pixel terms: thread `half` owns pixel `half` of the pair; coefficients are swapped by shuffle
+        const float mx_me = half ? m1 : m0;
+        amax[0] = half ? a1 : a0;
+        pixel_terms(a, p.inv_n, s_norm, old_cl, y[0], is_ign[0], mx_me, half ? f2hi(sa2) : f2lo(sa2),
+                    half ? f2hi(so2) : f2lo(so2), half ? f2hi(e02) : f2lo(e02), x0[0], xy[0], seen[0], have_seen, zfoc[0],
+                    acc, pc[0], gfoc[0], dmask[0]);
+        if (a.dlogits) {
+          PixCoef po;
+          po.cg0 = __shfl_xor_sync(full, pc[0].cg0, 1);
+          po.cg1 = __shfl_xor_sync(full, pc[0].cg1, 1);
+          po.cg2 = __shfl_xor_sync(full, pc[0].cg2, 1);
+          po.d0 = __shfl_xor_sync(full, pc[0].d0, 1);
+          const PixCoef& pa = half ? po : pc[0];   // pixel 0 of the pair
+          const PixCoef& pb = half ? pc[0] : po;   // pixel 1 of the pair
+          const F2 cgo = f2(pa.cg1, pb.cg1), cgn = f2(pa.cg2, pb.cg2);
+          // pass 3: gradient rows of my channels, both pixels at once
+          if (half == 0) {
+            const F2 g = fma2(e02, f2(pa.cg0, pb.cg0), f2(-pa.d0, -pb.d0));
+            Raw<T>::st(colp, f2lo(g), f2hi(g));
+          }
+#pragma unroll 4
+          for (int c = half == 0 ? 2 : 1; c < old_cl; c += 2) {
+            const F2 g = mul2(exp_pair(c), cgo);
+            Raw<T>::st(colp + (size_t)c * PITCH, f2lo(g), f2hi(g));
+          }
+#pragma unroll 4
+          for (int c = max(old_cl, 1) + ((max(old_cl, 1) ^ half) & 1); c < K; c += 2) {
+            const F2 g = mul2(exp_pair(c), cgn);
+            Raw<T>::st(colp + (size_t)c * PITCH, f2lo(g), f2hi(g));
+          }
+          __syncwarp(full);  // the partner's packed row stores are done before single elements are patched
+          // the label's own channel, recomputed in fp32 so -dy is applied before rounding
+          if (y[0] >= 0 && pc[0].dy != 0.f) {
+            const int kk = y[0];
+            const float cgk = kk == 0 ? pc[0].cg0 : (kk < old_cl ? pc[0].cg1 : pc[0].cg2);
+            const float ey = ex2_fast(fmaf(xy[0], kLog2e, -mx_me * kLog2e));
+            col[(size_t)kk * PITCH] = DT<T>::from_f(ey * cgk - pc[0].dy - (kk == 0 ? pc[0].d0 : 0.f));
+          }
         }
       } else {
         // ---------------- generic path: three passes over the shared-memory tile ----------------
@@ -346,7 +433,7 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
         }
         #pragma unroll 8
         for (int c = 0; c < K; ++c) {
-          Vec<T, PPT>::ld(col + (size_t)c * P, v);
+          Vec<T, PPT>::ld(col + (size_t)c * PITCH, v);
 #pragma unroll
           for (int j = 0; j < PPT; ++j)
             if (v[j] > mx[j]) {
@@ -358,7 +445,7 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
         for (int j = 0; j < PPT; ++j) nm[j] = -mx[j] * kLog2e;
         #pragma unroll 8
         for (int c = 0; c < old_cl; ++c) {
-          Vec<T, PPT>::ld(col + (size_t)c * P, v);
+          Vec<T, PPT>::ld(col + (size_t)c * PITCH, v);
 #pragma unroll
           for (int j = 0; j < PPT; ++j) s_old[j] += ex2_fast(fmaf(v[j], kLog2e, nm[j]));
         }
@@ -366,7 +453,7 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
         for (int j = 0; j < PPT; ++j) s_all[j] = s_old[j];
         #pragma unroll 8
         for (int c = old_cl; c < K; ++c) {
-          Vec<T, PPT>::ld(col + (size_t)c * P, v);
+          Vec<T, PPT>::ld(col + (size_t)c * PITCH, v);
 #pragma unroll
           for (int j = 0; j < PPT; ++j) s_all[j] += ex2_fast(fmaf(v[j], kLog2e, nm[j]));
         }
@@ -383,17 +470,17 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
           Vec<T, PPT>::st(col, g);
           #pragma unroll 8
           for (int c = 1; c < old_cl; ++c) {
-            Vec<T, PPT>::ld(col + (size_t)c * P, v);
+            Vec<T, PPT>::ld(col + (size_t)c * PITCH, v);
 #pragma unroll
             for (int j = 0; j < PPT; ++j) g[j] = ex2_fast(fmaf(v[j], kLog2e, nm[j])) * pc[j].cg1;
-            Vec<T, PPT>::st(col + (size_t)c * P, g);
+            Vec<T, PPT>::st(col + (size_t)c * PITCH, g);
           }
           #pragma unroll 8
           for (int c = max(old_cl, 1); c < K; ++c) {
-            Vec<T, PPT>::ld(col + (size_t)c * P, v);
+            Vec<T, PPT>::ld(col + (size_t)c * PITCH, v);
 #pragma unroll
             for (int j = 0; j < PPT; ++j) g[j] = ex2_fast(fmaf(v[j], kLog2e, nm[j])) * pc[j].cg2;
-            Vec<T, PPT>::st(col + (size_t)c * P, g);
+            Vec<T, PPT>::st(col + (size_t)c * PITCH, g);
           }
           // the label's own channel, recomputed in fp32 so -dy is applied before rounding
 #pragma unroll
@@ -402,7 +489,7 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
               const int kk = y[j];
               const float cgk = kk == 0 ? pc[j].cg0 : (kk < old_cl ? pc[j].cg1 : pc[j].cg2);
               const float ey = ex2_fast(fmaf(xy[j], kLog2e, nm[j]));
-              col[(size_t)kk * P + j] = DT<T>::from_f(ey * cgk - pc[j].dy - (kk == 0 ? pc[j].d0 : 0.f));
+              col[(size_t)kk * PITCH + j] = DT<T>::from_f(ey * cgk - pc[j].dy - (kk == 0 ? pc[j].d0 : 0.f));
             }
           }
         }
@@ -687,6 +774,7 @@ static bool make_plan(const bacs_pixel_args& a, PixelPlan* plan) {
       const int per_sm = two_fit(smem) ? 2 : 1;
       const int64_t tiles = HW / 512 * a.B;
       plan->fast = 1;
+      plan->coop = 0;
       plan->ppt = 2;
       plan->P = 512;
       plan->kreg = kreg;
@@ -705,7 +793,9 @@ static bool make_plan(const bacs_pixel_args& a, PixelPlan* plan) {
     for (int ppt = 2; ppt >= 1; --ppt) {
       if (ppt == 2 && (HW & 1)) continue;  // pixel pairs need even image sizes
       const int P = ppt * kConsumers;
-      const size_t tile = (size_t)a.K * P * es;
+      // one pixel per thread and even images: lane pairs walk the channels together on padded rows (see the kernel)
+      const bool coop = ppt == 1 && (HW & 1) == 0 && a.K >= 2;
+      const size_t tile = (size_t)a.K * ((size_t)P * es + (coop ? 64 : 0));
       int stages = 0;
       for (int st = 3; st >= min_stages; --st)
         if ((size_t)st * tile + extra + 1024 <= cap) {
@@ -729,6 +819,7 @@ static bool make_plan(const bacs_pixel_args& a, PixelPlan* plan) {
           }
       }
       plan->ppt = ppt;
+      plan->coop = coop ? 1 : 0;
       plan->P = P;
       plan->stages = stages;
       plan->smem = smem;
@@ -823,9 +914,9 @@ int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_
                    ? 1
                    : 0;
   cudaStream_t s = (cudaStream_t)stream;
-#define LAUNCH_PIX(TT, PPT, KREG, ROWT)                                                                        \
+#define LAUNCH_PIX(TT, PPT, KREG, ROWT, COOPV)                                                                 \
   do {                                                                                                         \
-    auto kern = pixel_loss_kernel<TT, PPT, KREG, ROWT>;                                                        \
+    auto kern = pixel_loss_kernel<TT, PPT, KREG, ROWT, COOPV>;                                                        \
     if (plan.smem > 48 * 1024) {                                                                               \
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem); \
       if (e != cudaSuccess) {                                                                                  \
@@ -836,10 +927,10 @@ int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_
     }                                                                                                          \
     kern<<<plan.grid, kConsumers + 32, plan.smem, s>>>(p);                                                     \
   } while (0)
-#define LAUNCH_PIX_K(TT, PPT)                       \
-  do {                                              \
-    if (plan.rowtile) LAUNCH_PIX(TT, PPT, 0, true); \
-    else LAUNCH_PIX(TT, PPT, 0, false);             \
+#define LAUNCH_PIX_K(TT, PPT, COOPV)                       \
+  do {                                                     \
+    if (plan.rowtile) LAUNCH_PIX(TT, PPT, 0, true, COOPV); \
+    else LAUNCH_PIX(TT, PPT, 0, false, COOPV);             \
   } while (0)
   const bool wce = p.use_tmap && wce_eligible(*a, plan);
   if (plan.fast && plan.stages != 4 && !wce) {
@@ -864,8 +955,9 @@ int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_
     if (rc != BACS_OK) return rc;
   } else {
     BACS_DISPATCH_DTYPE(a->dtype, TT, {
-      if (plan.ppt == 2) LAUNCH_PIX_K(TT, 2);
-      else LAUNCH_PIX_K(TT, 1);
+      if (plan.ppt == 2) LAUNCH_PIX_K(TT, 2, false);
+      else if (plan.coop) LAUNCH_PIX_K(TT, 1, true);
+      else LAUNCH_PIX_K(TT, 1, false);
     });
   }
 #undef LAUNCH_PIX_K

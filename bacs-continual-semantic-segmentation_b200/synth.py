@@ -71,6 +71,9 @@ CONFIGS = {
     "row512_k24": StepConfig("row512_k24", B=1, K=24, old_cl=20, T=3, H=32, W=512, D=32, A=16, initial_classes=20,
                              increment=2),
     "wide1536": StepConfig("wide1536", B=1, K=5, old_cl=3, T=2, H=32, W=1536, D=16, A=12, initial_classes=3, increment=2),
+    # more classes than fit in registers: the shared-memory kernel with cooperating lane pairs (ADE20K-like)
+    "row512_k40": StepConfig("row512_k40", B=2, K=40, old_cl=31, T=2, H=32, W=512, D=32, A=16, initial_classes=31,
+                             increment=9),
     "row512_k7": StepConfig("row512_k7", B=1, K=7, old_cl=5, T=3, H=32, W=512, D=32, A=16, initial_classes=3,
                             increment=2),
 }
