@@ -349,10 +349,14 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
         const int half = tid & 1;                    // this thread takes channels half, half + 2, ...
         T* colp = tile + (px0 & ~1);                 // the pair's first pixel
         // pass 1: packed max / arg-max over my channels, then merged with the partner's (ties -> lowest channel)
-        typename Raw<T>::Max mt = Raw<T>::init(Raw<T>::ld(colp + (size_t)half * PITCH));
+        // (channel rows are walked with running pointers: two rows per step)
+        const size_t step = 2 * (size_t)PITCH;
+        const T* rp = colp + (size_t)half * PITCH;
+        typename Raw<T>::Max mt = Raw<T>::init(Raw<T>::ld(rp));
         Raw<T>::set_first(mt, half);
+        rp += step;
 #pragma unroll 4
-        for (int c = half + 2; c < K; c += 2) Raw<T>::update(mt, Raw<T>::ld(colp + (size_t)c * PITCH), c);
+        for (int c = half + 2; c < K; c += 2, rp += step) Raw<T>::update(mt, Raw<T>::ld(rp), c);
         float m0, m1;
         int a0, a1;
         Raw<T>::finish(mt, m0, m1, a0, a1);
@@ -364,17 +368,20 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
         }
         // pass 2: exponent sums of both pixels as packed pairs; old and new classes in separate loops
         const F2 nm2 = f2(-m0 * kLog2e, -m1 * kLog2e), l2e2 = f2b(kLog2e);
-        auto exp_pair = [&](int c) {
+        auto exp_at = [&](const T* q) {
           float v0, v1;
-          Raw<T>::unpack(Raw<T>::ld(colp + (size_t)c * PITCH), v0, v1);
+          Raw<T>::unpack(Raw<T>::ld(q), v0, v1);
           const F2 arg = fma2(f2(v0, v1), l2e2, nm2);
           return f2(ex2_fast(f2lo(arg)), ex2_fast(f2hi(arg)));
         };
+        const int new0 = old_cl + ((old_cl ^ half) & 1);  // my first new-class channel
         F2 so2 = f2b(0.f), sn2 = f2b(0.f);
+        rp = colp + (size_t)half * PITCH;
 #pragma unroll 4
-        for (int c = half; c < old_cl; c += 2) so2 = add2(so2, exp_pair(c));
+        for (int c = half; c < old_cl; c += 2, rp += step) so2 = add2(so2, exp_at(rp));
+        rp = colp + (size_t)new0 * PITCH;
 #pragma unroll 4
-        for (int c = old_cl + ((old_cl ^ half) & 1); c < K; c += 2) sn2 = add2(sn2, exp_pair(c));
+        for (int c = new0; c < K; c += 2, rp += step) sn2 = add2(sn2, exp_at(rp));
         {
           F2 po, pn;
           po.v = __shfl_xor_sync(full, so2.v, 1);
@@ -383,7 +390,7 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
           sn2 = add2(sn2, pn);
         }
         const F2 sa2 = add2(so2, sn2);
-        const F2 e02 = exp_pair(0);
+        const F2 e02 = exp_at(colp);
         // per-pixel terms: thread `half` owns pixel `half` of the pair; coefficients are swapped by shuffle
         const float mx_me = half ? m1 : m0;
         amax[0] = half ? a1 : a0;
@@ -404,15 +411,21 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
             const F2 g = fma2(e02, f2(pa.cg0, pb.cg0), f2(-pa.d0, -pb.d0));
             Raw<T>::st(colp, f2lo(g), f2hi(g));
           }
+          {
+            const int c0 = half == 0 ? 2 : 1;
+            T* wp = colp + (size_t)c0 * PITCH;
 #pragma unroll 4
-          for (int c = half == 0 ? 2 : 1; c < old_cl; c += 2) {
-            const F2 g = mul2(exp_pair(c), cgo);
-            Raw<T>::st(colp + (size_t)c * PITCH, f2lo(g), f2hi(g));
-          }
+            for (int c = c0; c < old_cl; c += 2, wp += step) {
+              const F2 g = mul2(exp_at(wp), cgo);
+              Raw<T>::st(wp, f2lo(g), f2hi(g));
+            }
+            const int n1 = max(old_cl, 1) + ((max(old_cl, 1) ^ half) & 1);
+            wp = colp + (size_t)n1 * PITCH;
 #pragma unroll 4
-          for (int c = max(old_cl, 1) + ((max(old_cl, 1) ^ half) & 1); c < K; c += 2) {
-            const F2 g = mul2(exp_pair(c), cgn);
-            Raw<T>::st(colp + (size_t)c * PITCH, f2lo(g), f2hi(g));
+            for (int c = n1; c < K; c += 2, wp += step) {
+              const F2 g = mul2(exp_at(wp), cgn);
+              Raw<T>::st(wp, f2lo(g), f2hi(g));
+            }
           }
           __syncwarp(full);  // the partner's packed row stores are done before single elements are patched
           // the label's own channel, recomputed in fp32 so -dy is applied before rounding
