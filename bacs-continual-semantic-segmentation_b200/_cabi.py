@@ -64,6 +64,8 @@ _SIGNATURES = {
     "bacs_confmat_metrics": (i32, [vp, i32, vp, vp]),
     "bacs_scale_inplace": (i32, [vp, i32, i64, vp, vp]),
     "bacs_scale_inplace_multi": (i32, [i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(i64), vp, vp]),
+    "bacs_peer_allreduce": (i32, [vp, i32, i32, i32, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), vp, vp, vp, vp, i32,
+                                  i32, i32, vp, vp]),
     "bacs_pack_state": (i32, [vp, vp, i32, i32, vp, i32, vp, vp]),
     "bacs_unpack_state": (i32, [vp, i32, i32, vp, vp, vp, i32, vp]),
     "bacs_combine_scalars": (i32, [i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(vp), C.POINTER(i32),

@@ -122,12 +122,20 @@ class Prototypes(BaseLoss):
         if self.sync_across_ranks and torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size()
         mode = 0 if (self.exact and world == 1) else 1
-        sums, counts = ops.proto_accumulate(features, task, rank, n_bt, T, mode)
-        if world > 1:
-            from ..distributed import allreduce_packed
-            allreduce_packed(sums, counts)
         if not self._prototypes_tensors.is_contiguous():
             self._prototypes_tensors = self._prototypes_tensors.contiguous()
+        if world > 1:
+            from ..distributed import allreduce_packed, peer_reducer
+            packed = torch.empty(T * D + T, dtype=torch.float64, device=features.device)
+            sums, counts = ops.proto_accumulate(features, task, rank, n_bt, T, mode, out=packed)
+            reducer = peer_reducer(packed.numel(), features.device)
+            if reducer is not None and self._count_features.is_contiguous():
+                # one launch: sum over the ranks through NVLink peer memory + running-mean update
+                self.ready_flag = reducer.allreduce(packed, self._prototypes_tensors, self._count_features, T, D)
+                return
+            allreduce_packed(sums, counts)
+        else:
+            sums, counts = ops.proto_accumulate(features, task, rank, n_bt, T, mode)
         self.ready_flag = ops.proto_update(self._prototypes_tensors, self._count_features, sums, counts)
 
     def update_prototypes(self, model, img, target):

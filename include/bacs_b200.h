@@ -304,6 +304,21 @@ int bacs_combine_scalars(int n, const double* const* src_host, const int* idx_ho
                          const double* const* den_host, const int* didx_host,
                          const float* coef_host, float* out, bacs_stream_t stream);
 
+/* One-shot all-reduce (sum) of the packed fp64 state over NVLink PEER MEMORY, optionally fused with the
+ * prototype running-mean update of bacs_proto_update (pass proto = NULL for the plain all-reduce):
+ * no counterpart in the reference (each DDP rank keeps its own prototypes, loss/prototypes.py:157-163).
+ *   peer_buf_host[r]  : device address, valid on THIS GPU, of rank r's symmetric region of 2*n_max doubles
+ *   peer_flag_host[r] : device address of rank r's flag row of >= 16 zero-initialised uint32
+ *   step_dev          : device uint32 step counter of this rank (0 at start; the kernel increments it, so
+ *                       the call can be replayed from a CUDA graph)
+ *   error_dev         : set to 1 when a peer did not show up within ~2 s (the kernel never hangs), or NULL
+ * Every rank must make the same sequence of calls.  packed is summed in rank order: all ranks obtain
+ * bit-identical results. */
+int bacs_peer_allreduce(double* packed, int n, int n_max, int rank, int world,
+                        const uint64_t* peer_buf_host, const uint64_t* peer_flag_host, uint32_t* step_dev,
+                        int32_t* error_dev, float* proto, void* count, int count_is_int64, int T, int D,
+                        int32_t* ready, bacs_stream_t stream);
+
 /* Pack / unpack the per-step cross-rank state into ONE fp64 buffer for a single
  * all-reduce: [T*D prototype sums | T counts | K*K confusion matrix (optional)]. */
 int bacs_pack_state(const double* sums, const double* counts, int T, int D,

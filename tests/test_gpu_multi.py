@@ -1,0 +1,20 @@
+"""Multi-GPU checks that need real peers (skipped on a single-GPU box): the NVLink peer-memory all-reduce
+fused with the prototype update (csrc/peer.cu) against NCCL, bit-exact, eager and under CUDA-graph replay."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_peer_allreduce_matches_nccl():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tests", "multigpu", "peer_allreduce_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("peer all-reduce ok") == 2, out.stdout[-2000:]
