@@ -19,6 +19,7 @@
 // stores issued by the producer warp, so HBM sees one read and one write of [B,K,H,W]
 // plus 8 + 8 (+1) bytes per pixel, and the consumers never wait for a store.
 #include <algorithm>
+#include <cstdlib>
 
 #include "pixel_fast.cuh"  // Raw<T>: packed pixel pairs
 
@@ -819,7 +820,7 @@ static bool make_plan(const bacs_pixel_args& a, PixelPlan* plan) {
       const int64_t tiles = (HW + P - 1) / P * a.B;
       size_t smem = (size_t)stages * tile + extra;
       int per_sm = 1;
-      if (ppt == 1) {
+      if (ppt == 1) {  // (measured at K = 151: 2 CTAs x 1 stage 1.57 ms, 1 CTA x 2 stages 1.75 ms)
         // large K: one pixel per thread.  Two CTAs per SM double the warps that hide latency; when two stages each
         // do not fit, one stage each still overlaps -- one CTA computes while the other one loads / stores.
         auto two_fit = [](size_t sm) { return 2 * (sm + 1024 + 512) <= (size_t)228 * 1024; };

@@ -85,7 +85,7 @@ class PeerReducer:
                   count: Optional[torch.Tensor] = None, T: int = 0, D: int = 0) -> Optional[torch.Tensor]:
         """In-place sum of ``packed`` (fp64, contiguous) over the ranks; with ``proto`` / ``count`` the running-mean
         prototype update runs in the same launch and the int32 ready flag is returned."""
-        from . import _cabi
+        from . import _cabi, ops
         if packed.dtype != torch.float64 or not packed.is_contiguous() or packed.numel() > self.n_max:
             raise ValueError("PeerReducer.allreduce: packed must be contiguous fp64 with <= %d elements" % self.n_max)
         ready = None
@@ -97,7 +97,7 @@ class PeerReducer:
         lib = _cabi.load()
         _cabi.check(lib.bacs_peer_allreduce(packed.data_ptr(), packed.numel(), self.n_max, self.rank, self.world,
                                             self.peer_buf, self.peer_flag, self.step.data_ptr(), self.error.data_ptr(),
-                                            *args_proto, torch.cuda.current_stream().cuda_stream),
+                                            *args_proto, ops._stream()),
                     "bacs_peer_allreduce")
         return ready
 

@@ -166,7 +166,8 @@ class BaseLoss:
         where ``seen_map`` is a :class:`SeenMap` (call ``.materialize()`` for the tensor)."""
         old_atts, attentions, seen_map = None, None, None
         is_experience_replay = task_num != -1
-        self.weighted_ce.old_cl = self.old_classes
+        if self.weighted_ce.old_cl != self.old_classes:      # (nn.Module.__setattr__ is slow: only on change)
+            self.weighted_ce.old_cl = self.old_classes
         seen_net = getattr(model, "seen_fg_network", None)
         train_seen_detector = (seen_net is not None and (self.same_task or not is_experience_replay) and train)
         return_penultimate = train_seen_detector or use_weighted_ce or self._prototypes is not None

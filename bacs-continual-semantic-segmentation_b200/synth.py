@@ -180,6 +180,8 @@ class SeenHeads(torch.nn.Module):
         self.stop_gradients = False
 
     def set_stop_gradients(self, stop):
+        if stop == self.stop_gradients:
+            return
         self.stop_gradients = stop
         for h in self.seen_not_seen_clf:
             h.stop_gradients = stop
