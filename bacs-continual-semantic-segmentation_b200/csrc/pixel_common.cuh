@@ -197,7 +197,8 @@ __device__ __forceinline__ void focal_term(const bacs_pixel_args& a, float Z, fl
 
 // Everything that depends on the softmax statistics of ONE pixel (not on the channel loop).
 __device__ __forceinline__ void pixel_terms(const bacs_pixel_args& a, float inv_n, float s_norm, int old_cl, int y,
-                                            bool is_ign, float mx, float S, float S_old, float e0, float x0, float xy,
+                                            bool is_ign, float mx, float S, float S_old, float S_fg_in, float e0, float x0,
+                                            float xy,
                                             float seen, bool have_seen, float zfoc, float* acc, PixCoef& pc,
                                             float& gfoc, uint8_t& dmask) {
   pc.cg0 = pc.cg1 = pc.cg2 = pc.d0 = pc.dy = 0.f;
@@ -214,7 +215,9 @@ __device__ __forceinline__ void pixel_terms(const bacs_pixel_args& a, float inv_
 
   if (a.mode == BACS_PIX_WEIGHTED_CE) {
     if (valid) {
-      const float S_fg = S - e0;
+      // S_fg = sum over the foreground channels, accumulated WITHOUT channel 0 by the caller: S - e0 cancels
+      // catastrophically when the background logit dominates (confident networks)
+      const float S_fg = fmaxf(S_fg_in, 1e-37f);
       const float u = a.ukd ? 1.f : 0.f;
       const float inv_old = __fdividef(1.f, S_old);
       const float inv_fg = __fdividef(1.f, S_fg);

@@ -380,8 +380,10 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const __gri
           Raw<T>::unpack(raw[c], v0, v1);
           e0[c] = ex2_fast(fmaf(v0, kLog2e, nm0));
           e1[c] = ex2_fast(fmaf(v1, kLog2e, nm1));
-          g0 = i == 0 ? e0[c] : g0 + e0[c];
-          g1 = i == 0 ? e1[c] : g1 + e1[c];
+          if (c >= 1) {  // channel 0 is kept out of the sums: S_fg is accumulated directly
+            g0 = (i == 0 || c == 1) ? e0[c] : g0 + e0[c];
+            g1 = (i == 0 || c == 1) ? e1[c] : g1 + e1[c];
+          }
         }
       }
       sa0 += g0;
@@ -393,7 +395,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const __gri
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int c = 4 * g + i;
-          if (c < KREG && c < old_cl) {
+          if (c >= 1 && c < KREG && c < old_cl) {
             so0 += e0[c];
             so1 += e1[c];
           }
@@ -401,12 +403,20 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_fast_kernel(const __gri
       }
     }
 
+    // S_fg = sum_{c>=1} (accumulated above), S = S_fg + e_0, S_old = [old_cl >= 1] e_0 + sum_{1<=c<old_cl}
+    const float sf0 = sa0, sf1 = sa1;
+    sa0 += e0[0];
+    sa1 += e1[0];
+    if (old_cl >= 1) {
+      so0 += e0[0];
+      so1 += e1[0];
+    }
     PixCoef pc[2];
     float gfoc[2];
     uint8_t dmask[2];
-    pixel_terms(a, p.inv_n, s_norm, old_cl, y[0], is_ign[0], mx0, sa0, so0, e0[0], x00, xy[0], seen[0], have_seen,
+    pixel_terms(a, p.inv_n, s_norm, old_cl, y[0], is_ign[0], mx0, sa0, so0, sf0, e0[0], x00, xy[0], seen[0], have_seen,
                 zfoc[0], acc, pc[0], gfoc[0], dmask[0]);
-    pixel_terms(a, p.inv_n, s_norm, old_cl, y[1], is_ign[1], mx1, sa1, so1, e1[0], x01, xy[1], seen[1], have_seen,
+    pixel_terms(a, p.inv_n, s_norm, old_cl, y[1], is_ign[1], mx1, sa1, so1, sf1, e1[0], x01, xy[1], seen[1], have_seen,
                 zfoc[1], acc, pc[1], gfoc[1], dmask[1]);
     if (a.dlogits) {
       Raw<T>::st(col, e0[0] * pc[0].cg0 - pc[0].d0, e1[0] * pc[1].cg0 - pc[1].d0);

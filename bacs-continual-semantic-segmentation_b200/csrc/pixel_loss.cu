@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
         // ---------------- register-resident path (K <= KREG) ----------------
         constexpr int KR = KREG > 0 ? KREG : 1;
         float e[KR][PPT];
-        float mx[PPT], nm[PPT], s_all[PPT], s_old[PPT];
+        float mx[PPT], nm[PPT], s_all[PPT], s_old[PPT], s_fg[PPT];
 #pragma unroll
         for (int c = 0; c < KR; ++c)
           if (c < K) Vec<T, PPT>::ld(col + (size_t)c * P, e[c]);
@@ -312,22 +312,28 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {
           nm[j] = -mx[j] * kLog2e;
-          s_all[j] = s_old[j] = 0.f;
+          s_fg[j] = s_old[j] = 0.f;
         }
+        // the foreground sum is accumulated without channel 0 (S - e_0 would cancel when the background dominates)
 #pragma unroll
         for (int c = 0; c < KR; ++c)
           if (c < K) {
 #pragma unroll
             for (int j = 0; j < PPT; ++j) {
               e[c][j] = ex2_fast(fmaf(e[c][j], kLog2e, nm[j]));
-              s_all[j] += e[c][j];
-              if (c < old_cl) s_old[j] += e[c][j];
+              if (c >= 1) {
+                s_fg[j] += e[c][j];
+                if (c < old_cl) s_old[j] += e[c][j];
+              }
             }
           }
 #pragma unroll
-        for (int j = 0; j < PPT; ++j)
-          pixel_terms(a, p.inv_n, s_norm, old_cl, y[j], is_ign[j], mx[j], s_all[j], s_old[j], e[0][j], x0[j], xy[j],
-                      seen[j], have_seen, zfoc[j], acc, pc[j], gfoc[j], dmask[j]);
+        for (int j = 0; j < PPT; ++j) {
+          s_all[j] = s_fg[j] + e[0][j];
+          if (old_cl >= 1) s_old[j] += e[0][j];
+          pixel_terms(a, p.inv_n, s_norm, old_cl, y[j], is_ign[j], mx[j], s_all[j], s_old[j], s_fg[j], e[0][j], x0[j],
+                      xy[j], seen[j], have_seen, zfoc[j], acc, pc[j], gfoc[j], dmask[j]);
+        }
         if (a.dlogits) {
           float g[PPT];
 #pragma unroll
@@ -375,11 +381,13 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
           const F2 arg = fma2(f2(v0, v1), l2e2, nm2);
           return f2(ex2_fast(f2lo(arg)), ex2_fast(f2hi(arg)));
         };
-        const int new0 = old_cl + ((old_cl ^ half) & 1);  // my first new-class channel
+        const int new0 = max(old_cl, 1) + ((max(old_cl, 1) ^ half) & 1);  // my first new-class channel (never 0)
+        // (channel 0 stays out of the loops: the foreground sum S_fg is accumulated directly, S - e_0 would cancel
+        // when the background dominates)
         F2 so2 = f2b(0.f), sn2 = f2b(0.f);
-        rp = colp + (size_t)half * PITCH;
+        rp = colp + (size_t)(half == 0 ? 2 : 1) * PITCH;
 #pragma unroll 4
-        for (int c = half; c < old_cl; c += 2, rp += step) so2 = add2(so2, exp_at(rp));
+        for (int c = (half == 0 ? 2 : 1); c < old_cl; c += 2, rp += step) so2 = add2(so2, exp_at(rp));
         rp = colp + (size_t)new0 * PITCH;
 #pragma unroll 4
         for (int c = new0; c < K; c += 2, rp += step) sn2 = add2(sn2, exp_at(rp));
@@ -390,14 +398,16 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
           so2 = add2(so2, po);
           sn2 = add2(sn2, pn);
         }
-        const F2 sa2 = add2(so2, sn2);
         const F2 e02 = exp_at(colp);
+        const F2 sf2 = add2(so2, sn2);  // foreground channels only
+        const F2 sa2 = add2(sf2, e02);
+        if (old_cl >= 1) so2 = add2(so2, e02);
         // per-pixel terms: thread `half` owns pixel `half` of the pair; coefficients are swapped by shuffle
         const float mx_me = half ? m1 : m0;
         amax[0] = half ? a1 : a0;
         pixel_terms(a, p.inv_n, s_norm, old_cl, y[0], is_ign[0], mx_me, half ? f2hi(sa2) : f2lo(sa2),
-                    half ? f2hi(so2) : f2lo(so2), half ? f2hi(e02) : f2lo(e02), x0[0], xy[0], seen[0], have_seen, zfoc[0],
-                    acc, pc[0], gfoc[0], dmask[0]);
+                    half ? f2hi(so2) : f2lo(so2), half ? f2hi(sf2) : f2lo(sf2), half ? f2hi(e02) : f2lo(e02), x0[0], xy[0],
+                    seen[0], have_seen, zfoc[0], acc, pc[0], gfoc[0], dmask[0]);
         if (a.dlogits) {
           PixCoef po;
           po.cg0 = __shfl_xor_sync(full, pc[0].cg0, 1);
@@ -439,11 +449,11 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
         }
       } else {
         // ---------------- generic path: three passes over the shared-memory tile ----------------
-        float mx[PPT], nm[PPT], s_all[PPT], s_old[PPT], e0[PPT], v[PPT];
+        float mx[PPT], nm[PPT], s_all[PPT], s_old[PPT], s_fg[PPT], e0[PPT], v[PPT];
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {
           mx[j] = -INFINITY;
-          s_all[j] = s_old[j] = 0.f;
+          s_fg[j] = s_old[j] = 0.f;
         }
         #pragma unroll 8
         for (int c = 0; c < K; ++c) {
@@ -457,25 +467,29 @@ __global__ void __launch_bounds__(kConsumers + 32, ((KREG > 0 || PPT == 1) ? 2 :
         }
 #pragma unroll
         for (int j = 0; j < PPT; ++j) nm[j] = -mx[j] * kLog2e;
+        // channel 0 stays out of the loops: the foreground sum is accumulated directly (S - e_0 would cancel when
+        // the background dominates)
         #pragma unroll 8
-        for (int c = 0; c < old_cl; ++c) {
+        for (int c = 1; c < old_cl; ++c) {
           Vec<T, PPT>::ld(col + (size_t)c * PITCH, v);
 #pragma unroll
           for (int j = 0; j < PPT; ++j) s_old[j] += ex2_fast(fmaf(v[j], kLog2e, nm[j]));
         }
 #pragma unroll
-        for (int j = 0; j < PPT; ++j) s_all[j] = s_old[j];
+        for (int j = 0; j < PPT; ++j) s_fg[j] = s_old[j];
         #pragma unroll 8
-        for (int c = old_cl; c < K; ++c) {
+        for (int c = max(old_cl, 1); c < K; ++c) {
           Vec<T, PPT>::ld(col + (size_t)c * PITCH, v);
 #pragma unroll
-          for (int j = 0; j < PPT; ++j) s_all[j] += ex2_fast(fmaf(v[j], kLog2e, nm[j]));
+          for (int j = 0; j < PPT; ++j) s_fg[j] += ex2_fast(fmaf(v[j], kLog2e, nm[j]));
         }
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {
           e0[j] = ex2_fast(fmaf(x0[j], kLog2e, nm[j]));
-          pixel_terms(a, p.inv_n, s_norm, old_cl, y[j], is_ign[j], mx[j], s_all[j], s_old[j], e0[j], x0[j], xy[j],
-                      seen[j], have_seen, zfoc[j], acc, pc[j], gfoc[j], dmask[j]);
+          s_all[j] = s_fg[j] + e0[j];
+          if (old_cl >= 1) s_old[j] += e0[j];
+          pixel_terms(a, p.inv_n, s_norm, old_cl, y[j], is_ign[j], mx[j], s_all[j], s_old[j], s_fg[j], e0[j], x0[j],
+                      xy[j], seen[j], have_seen, zfoc[j], acc, pc[j], gfoc[j], dmask[j]);
         }
         if (a.dlogits) {
           float g[PPT];

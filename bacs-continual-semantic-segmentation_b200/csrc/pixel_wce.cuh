@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
           Raw<T>::unpack(raw[c], v0, v1);
           const F2 arg = fma2(f2(v0, v1), l2e2, nm2);
           e2[c] = f2(ex2_fast(f2lo(arg)), ex2_fast(f2hi(arg)));
-          g2 = i == 0 ? e2[c] : add2(g2, e2[c]);
+          if (c >= 1) g2 = (i == 0 || c == 1) ? e2[c] : add2(g2, e2[c]);  // channel 0 is kept out of the sums
         }
       }
       sa2 = add2(sa2, g2);
@@ -311,10 +311,15 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int c = 4 * g + i;
-          if (c < KREG && c < old_cl) so2 = add2(so2, e2[c]);
+          if (c >= 1 && c < KREG && c < old_cl) so2 = add2(so2, e2[c]);
         }
       }
     }
+    // S_fg = sum_{c>=1} is accumulated directly (S - e_0 would cancel when the background logit dominates);
+    // S = S_fg + e_0, S_old = e_0 + sum_{1<=c<old_cl}
+    const float sf0 = f2lo(sa2), sf1 = f2hi(sa2);
+    sa2 = add2(sa2, e2[0]);
+    so2 = add2(so2, e2[0]);
     const float sa0 = f2lo(sa2), sa1 = f2hi(sa2), so0 = f2lo(so2), so1 = f2hi(so2);
 
     // ---- per-pixel terms: loss, gradient coefficients, distill mask, focal term (select-only) ------
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
       const float mx = j == 0 ? mx0 : mx1, Sa = j == 0 ? sa0 : sa1, So = fmaxf(j == 0 ? so0 : so1, 1e-37f);
       const float ec0 = j == 0 ? f2lo(e2[0]) : f2hi(e2[0]), x0 = j == 0 ? x00 : x01;
       const bool valid = y[j] >= 0, isbg = y[j] == 0, isnew = y[j] >= old_cl;
-      const float Sfg = fmaxf(Sa - ec0, 1e-37f);
+      const float Sfg = fmaxf(j == 0 ? sf0 : sf1, 1e-37f);
       const float lS = lg2_fast(Sa), iS = rcp_fast(Sa);
       const float lF = lg2_fast(Sfg), iF = rcp_fast(Sfg);
       float lO = 0.f, iO = 0.f;

@@ -286,6 +286,33 @@ def test_pixel_training_step_kernel(ops, synth, name, dtype, ukd):
     assert torch.equal(out2["preds"], out["preds"])
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pixel_training_step_kernel_large_logits(ops, synth, dtype):
+    """Confident logits (|x| up to ~40, far beyond random init): every log-sum-exp stays finite and matches the oracle;
+    pixels whose foreground mass underflows completely in fp32 are excluded (the closed form has no fp32 value there)."""
+    from bacs_b200 import _cabi
+    cfg = synth.CONFIGS["row512"]
+    inp = synth.make_step_inputs(cfg, seed=9, dtype=dtype)
+    logits = (inp.logits.float() * 10.0).to(dtype)
+    g = torch.Generator().manual_seed(5)
+    mask = synth.make_labels(cfg, g, classes=list(range(1, cfg.K)))
+    z = _seen_z(inp)
+    smax = torch.sigmoid(O.bilinear_upsample(z, (cfg.H, cfg.W), True)).max(1)[0]
+    x = logits.float().clone().requires_grad_(True)
+    want = O.weighted_ce(x, mask, smax, cfg.old_cl, 2.0, 0.5, True)
+    want.backward()
+    out = ops.pixel_loss(logits.cuda(), mask.cuda(), _cabi.PIX_WEIGHTED_CE, want_grad=True, z=z.cuda(),
+                         want_distill_mask=True, old_cl=cfg.old_cl, ukd=True)
+    assert out["variant"] == 2
+    assert bool(torch.isfinite(out["acc"]).all()) and bool(torch.isfinite(out["dlogits"].float()).all())
+    N = cfg.B * cfg.H * cfg.W
+    close(out["acc"][_cabi.ACC_LOSS] / N, want, rtol=2e-5, what="loss")
+    assert torch.equal(out["preds"].cpu(), O.argmax_first(logits.float()))
+    want_g = x.grad.to(dtype).float()
+    tol = 2e-5 if dtype == torch.float32 else 2.0 ** -7
+    close(out["dlogits"].float(), want_g, atol=tol * float(want_g.abs().max()), what="dlogits")
+
+
 def test_pixel_focal_term(ops, synth):
     from bacs_b200 import _cabi
     cfg = synth.CONFIGS["tiny"]
