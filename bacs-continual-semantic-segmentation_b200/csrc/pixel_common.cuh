@@ -293,6 +293,14 @@ __device__ __forceinline__ void pixel_terms(const bacs_pixel_args& a, float inv_
   }
 }
 
+// The "-dy at the label's own channel" part of pixel_terms() depends on the label channel alone (same expressions,
+// same rounding): kernels that reduce gradients per channel apply it once per (channel, pixel set).
+__device__ __forceinline__ float label_dy(const bacs_pixel_args& a, float inv_n, float s_norm, int old_cl, int c) {
+  if (a.mode == BACS_PIX_WEIGHTED_CE) return c >= old_cl ? inv_n * a.grad_scale : 0.f;
+  if (a.mode == BACS_PIX_CE || a.mode == BACS_PIX_SCORE)
+    return a.dlogits ? (a.class_w ? __ldg(a.class_w + c) : 1.f) * s_norm * a.grad_scale : 0.f;
+  return (a.dlogits && c >= old_cl) ? s_norm * a.grad_scale : 0.f;
+}
 
 struct PixelPlan {
   int ppt, P, kreg, stages, grid, rowtile, fast, coop;

@@ -860,9 +860,153 @@ static bool make_plan(const bacs_pixel_args& a, PixelPlan* plan) {
 
 }  // namespace bacs
 
+#include "pixel_lowres.cuh"  // the same loss evaluated from low-res logits (up-sample + adjoint fused)
+
+namespace bacs {
+
+struct LowresPlan {
+  int SX, R, groups, nsrc_max, grid;
+  size_t smem, part_bytes, g32_bytes;
+};
+
+// host copy of lerp_half_pixel (fp32, op by op)
+static void host_half_pixel(int dst, int in_size, float scale, int* i0, int* i1) {
+  volatile float t = (float)dst + 0.5f;
+  volatile float m = scale * t;
+  float src = m - 0.5f;
+  if (src < 0.f) src = 0.f;
+  *i0 = std::min((int)src, in_size - 1);
+  *i1 = *i0 + (*i0 < in_size - 1 ? 1 : 0);
+}
+
+static bool make_lowres_plan(const bacs_pixel_args& a, int lh, int lw, LowresPlan* plan) {
+  if (lh <= 0 || lw <= 0 || lw > kLowresThreads || a.W % lw != 0 || a.H % lh != 0) return false;
+  const int SX = a.W / lw;
+  if (SX != 16 && SX != 8) return false;
+  if (a.K > 255) return false;
+  int R = 1;
+  while (2 * R * lw <= kLowresThreads && 2 * R <= a.H) R *= 2;
+  const float hy = hp_scale(lh, a.H);
+  const int groups = (a.H + R - 1) / R;
+  int nsrc = 1;
+  for (int g = 0; g < groups; ++g) {
+    int f0, f1, l0, l1;
+    host_half_pixel(g * R, lh, hy, &f0, &f1);
+    host_half_pixel(std::min(g * R + R, a.H) - 1, lh, hy, &l0, &l1);
+    nsrc = std::max(nsrc, l1 - f0 + 1);
+  }
+  plan->SX = SX;
+  plan->R = R;
+  plan->groups = groups;
+  plan->nsrc_max = nsrc;
+  plan->grid = groups * a.B;
+  plan->smem = ((size_t)nsrc * a.K * (lw + 2) + (size_t)3 * R * kLowresChunk * lw + (size_t)nsrc * R +
+                (a.z ? (size_t)R * a.T * a.w : 0) + (size_t)R * (a.w + 1)) * 4 + 16;
+  plan->part_bytes = align_up((size_t)plan->grid * BACS_NACC * sizeof(double), 256);
+  plan->g32_bytes = (a.dlogits && a.dtype != BACS_F32) ? align_up((size_t)a.B * a.K * lh * lw * 4, 256) : 0;
+  return plan->smem <= (size_t)200 * 1024;
+}
+
+}  // namespace bacs
+
 using namespace bacs;
 
 extern "C" {
+
+size_t bacs_pixel_lowres_workspace_bytes(const bacs_pixel_args* a, int32_t lh, int32_t lw) {
+  if (!a) return 0;
+  LowresPlan plan;
+  if (!make_lowres_plan(*a, lh, lw, &plan)) return 0;
+  return plan.part_bytes + plan.g32_bytes;
+}
+
+int bacs_pixel_loss_lowres(const bacs_pixel_args* a, int32_t lh, int32_t lw, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  BACS_REQUIRE(a && a->logits && a->labels && a->acc, "bacs_pixel_loss_lowres: null argument");
+  BACS_REQUIRE(a->B > 0 && a->K > 0 && a->H > 0 && a->W > 0, "bacs_pixel_loss_lowres: empty shape");
+  BACS_REQUIRE(a->dtype == BACS_F32 || a->dtype == BACS_BF16 || a->dtype == BACS_F16, "bacs_pixel_loss_lowres: dtype");
+  if (a->z) {
+    BACS_REQUIRE(a->T > 0 && a->h > 0 && a->w > 0, "bacs_pixel_loss_lowres: seen logits given without T/h/w");
+    BACS_REQUIRE(a->seen_scale > 0 && a->H == a->h * a->seen_scale && a->W == a->w * a->seen_scale,
+                 "bacs_pixel_loss_lowres: H,W must equal h,w * seen_scale");
+  }
+  if (a->gz)
+    BACS_REQUIRE(a->z && a->focal_head >= 0 && a->focal_head < a->T, "bacs_pixel_loss_lowres: focal head out of range");
+  if (a->mode == BACS_PIX_WEIGHTED_CE)
+    BACS_REQUIRE(a->old_cl >= 1 && (a->z || a->seen_max),
+                 "bacs_pixel_loss_lowres: WEIGHTED_CE needs old_cl >= 1 and the seen logits / probabilities");
+  if (a->mode != BACS_PIX_WEIGHTED_CE && a->dlogits)
+    BACS_REQUIRE(a->hist, "bacs_pixel_loss_lowres: CE-type gradients need the label histogram");
+  if (a->mode == BACS_PIX_SCORE)
+    BACS_REQUIRE(a->score && !a->dlogits, "bacs_pixel_loss_lowres: SCORE mode needs score and no gradient");
+  LowresPlan plan;
+  if (!make_lowres_plan(*a, lh, lw, &plan)) {
+    set_error("bacs_pixel_loss_lowres: unsupported geometry (H=%d W=%d lh=%d lw=%d K=%d): W/lw must be 8 or 16, "
+              "lw <= 256, K <= 255", a->H, a->W, lh, lw, a->K);
+    return BACS_ERR_UNSUPPORTED;
+  }
+  if (!workspace || workspace_bytes < plan.part_bytes + plan.g32_bytes) {
+    set_error("bacs_pixel_loss_lowres: workspace too small (%zu bytes)", workspace_bytes);
+    return BACS_ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n_low = (int64_t)a->B * a->K * lh * lw;
+  LowresParams p;
+  p.a = *a;
+  p.g32 = nullptr;
+  if (a->dlogits) {
+    p.g32 = a->dtype == BACS_F32 ? reinterpret_cast<float*>(a->dlogits)
+                                 : reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + plan.part_bytes);
+    if (cudaMemsetAsync(p.g32, 0, (size_t)n_low * 4, s) != cudaSuccess) {
+      set_error("bacs_pixel_loss_lowres: memset failed");
+      return BACS_ERR_CUDA;
+    }
+  }
+  p.lh = lh;
+  p.lw = lw;
+  p.R = plan.R;
+  p.groups_per_image = plan.groups;
+  p.nsrc_max = plan.nsrc_max;
+  p.hy = hp_scale(lh, a->H);
+  p.inv_n = (float)(1.0 / ((double)a->B * (double)a->H * (double)a->W));
+  p.sy = a->z ? ac_scale(a->h, a->H) : 0.f;
+  p.sx = a->z ? ac_scale(a->w, a->W) : 0.f;
+  p.partials = reinterpret_cast<double*>(workspace);
+#define LAUNCH_LR(SXV)                                                                                          \
+  do {                                                                                                          \
+    auto kern = pixel_lowres_kernel<SXV>;                                                                       \
+    if (plan.smem > 48 * 1024 &&                                                                                \
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess) { \
+      set_error("bacs_pixel_loss_lowres: cannot opt in to %zu bytes of shared memory", plan.smem);              \
+      return BACS_ERR_CUDA;                                                                                     \
+    }                                                                                                           \
+    kern<<<plan.grid, kLowresThreads, plan.smem, s>>>(p);                                                       \
+  } while (0)
+  if (plan.SX == 16) LAUNCH_LR(16);
+  else LAUNCH_LR(8);
+#undef LAUNCH_LR
+  BACS_CHECK_LAUNCH("bacs_pixel_loss_lowres");
+  if (a->dlogits && a->dtype != BACS_F32) {
+    const int nb = (int)((n_low + 255) / 256);
+    if (a->dtype == BACS_BF16)
+      lowres_cast_kernel<__nv_bfloat16><<<nb, 256, 0, s>>>(p.g32, reinterpret_cast<__nv_bfloat16*>(a->dlogits), n_low);
+    else
+      lowres_cast_kernel<__half><<<nb, 256, 0, s>>>(p.g32, reinterpret_cast<__half*>(a->dlogits), n_low);
+    BACS_CHECK_LAUNCH("bacs_pixel_loss_lowres(cast)");
+  }
+  const int nblk = 1 + (a->mode == BACS_PIX_SCORE ? a->B : 0);
+  PixelEpilogue ep;
+  ep.ready = a->ready;
+  ep.focal_scale_out = a->focal_scale_out;
+  ep.loss_out = a->loss_out;
+  ep.focal_weight = a->focal_weight;
+  ep.loss_coef = a->loss_coef;
+  ep.loss_over_wsum = a->loss_over_wsum;
+  pixel_reduce_kernel<<<nblk, 256, 0, s>>>(p.partials, plan.grid, plan.groups, a->acc, a->score,
+                                           1.0 / ((double)a->H * (double)a->W), ep);
+  BACS_CHECK_LAUNCH("bacs_pixel_loss_lowres(reduce)");
+  return BACS_OK;
+}
 
 size_t bacs_pixel_workspace_bytes(const bacs_pixel_args* a) {
   if (!a) return 0;

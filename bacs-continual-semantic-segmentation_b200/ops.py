@@ -209,12 +209,23 @@ def pixel_loss(logits: torch.Tensor, labels: torch.Tensor, mode: int, *, want_gr
                ukd: bool = True, gamma: float = 2.0, threshold: float = 0.5, focal_gamma: float = 2.0,
                focal_alpha: Optional[float] = None, lkd_threshold: float = 0.5, ignore_index: int = 255,
                grad_scale: float = 1.0, seen_scale: int = 16, want_score: bool = False,
-               seen_max: Optional[torch.Tensor] = None, epilogue: Optional[dict] = None) -> dict:
+               seen_max: Optional[torch.Tensor] = None, epilogue: Optional[dict] = None,
+               lowres: bool = False) -> dict:
     """``epilogue`` = {"ready": int32 [1] tensor or None, "focal_weight": float, "loss_coef": float,
-    "over_wsum": bool}: the reduction launch also writes out["focal_scale"] and out["loss"] (fp32 [1])."""
+    "over_wsum": bool}: the reduction launch also writes out["focal_scale"] and out["loss"] (fp32 [1]).
+
+    ``lowres=True``: ``logits`` are the network's low-res ``sem_logits`` [B,K,lh,lw] (``return_sem_logits=True``,
+    networks/deeplab_v3.py:155-156); the x16 / x8 bilinear up-sample (align_corners=False, deeplab_v3.py:157-160) and
+    its adjoint are evaluated inside the kernel, ``out["dlogits"]`` is d loss / d sem_logits."""
     logits = _cuda(logits, "pixel_loss")
     labels = _cuda(labels, "pixel_loss", torch.int64)
-    B, K, H, W = logits.shape
+    B, K = logits.shape[0], logits.shape[1]
+    if lowres:
+        if labels.dim() != 3 or labels.shape[0] != B:
+            raise ValueError("pixel_loss: labels %s do not match sem_logits %s" % (tuple(labels.shape), tuple(logits.shape)))
+        H, W = labels.shape[1], labels.shape[2]
+    else:
+        H, W = logits.shape[2], logits.shape[3]
     if tuple(labels.shape) != (B, H, W):
         raise ValueError("pixel_loss: labels %s do not match logits %s" % (tuple(labels.shape), tuple(logits.shape)))
     dev = logits.device
@@ -267,6 +278,18 @@ def pixel_loss(logits: torch.Tensor, labels: torch.Tensor, mode: int, *, want_gr
         a.focal_weight, a.loss_coef = float(epilogue.get("focal_weight", 0.0)), float(epilogue["loss_coef"])
         a.loss_over_wsum = int(bool(epilogue.get("over_wsum", False)))
     lib = _lib()
+    if lowres:
+        lh, lw = int(logits.shape[2]), int(logits.shape[3])
+        nbytes = lib.bacs_pixel_lowres_workspace_bytes(C.byref(a), lh, lw)
+        if nbytes == 0:
+            raise _cabi.BacsError("bacs_pixel_loss_lowres: unsupported geometry %s -> (%d, %d), K=%d"
+                                  % (tuple(logits.shape), H, W, K))
+        ws = _ws(nbytes, dev)
+        check(lib.bacs_pixel_loss_lowres(C.byref(a), lh, lw, ws.data_ptr(), ws.numel(), _stream()),
+              "bacs_pixel_loss_lowres")
+        out["hist"] = hist
+        out["variant"] = 3
+        return out
     nbytes = lib.bacs_pixel_workspace_bytes(C.byref(a))
     if nbytes == 0:
         raise _cabi.BacsError("bacs_pixel_loss: no tile plan for K=%d" % K)

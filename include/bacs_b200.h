@@ -227,6 +227,19 @@ int bacs_pixel_kernel_variant(const bacs_pixel_args* args_host);
 int bacs_pixel_loss(const bacs_pixel_args* args_host, void* workspace, size_t workspace_bytes,
                     bacs_stream_t stream);
 
+/* The same loss evaluated straight from the network's LOW-RES logits: replaces
+ *   logits = F.interpolate(sem_logits, size=(H,W), mode="bilinear", align_corners=False)
+ * of networks/deeplab_v3.py:154-160 (forward AND its autograd backward) together with the loss it feeds, so no
+ * [B,K,H,W] logit or gradient tensor exists.  Arguments as bacs_pixel_loss except
+ *   args->logits  = sem_logits [B,K,lh,lw]   (model(x, return_sem_logits=True), deeplab_v3.py:155-156)
+ *   args->dlogits = d loss / d sem_logits [B,K,lh,lw], same dtype (or NULL)
+ *   args->H, W    = label resolution; W / lw must be 8 or 16, H a multiple of lh, lw <= 256, K <= 255.
+ * Workspace: bacs_pixel_lowres_workspace_bytes.  Asynchronous on `stream`; gradients are accumulated with fp32
+ * atomics (summation order is not fixed: results agree to fp32 rounding, not bit for bit, between runs). */
+size_t bacs_pixel_lowres_workspace_bytes(const bacs_pixel_args* args_host, int32_t lh, int32_t lw);
+int bacs_pixel_loss_lowres(const bacs_pixel_args* args_host, int32_t lh, int32_t lw, void* workspace,
+                           size_t workspace_bytes, bacs_stream_t stream);
+
 /* ---------------------------------------------------------------------------------
  * Teacher distillation on the last attention map (loss/bacs_loss.py:258-294):
  *   L = lkd * mean_{b,a,y} sqrt( sum_x ( m * (U(old)^2 - U(new)^2) )^2 ),

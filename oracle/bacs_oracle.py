@@ -232,6 +232,13 @@ def bilinear_upsample(x: torch.Tensor, out_hw: Tuple[int, int], align_corners: b
     return rows[..., x0] * (1 - wx) + rows[..., x1] * wx
 
 
+def upsample_sem_logits(sem_logits: torch.Tensor, out_hw: Tuple[int, int]) -> torch.Tensor:
+    """The network's last op (networks/deeplab_v3.py:154-160): F.interpolate(sem_logits, size=input_shape,
+    mode="bilinear", align_corners=False) in fp32.  Oracle of the fused low-res path: every loss of
+    this file applied to the result, gradients through it by autograd."""
+    return bilinear_upsample(sem_logits.float(), out_hw, False)
+
+
 def seen_probs(pen, protos, weight, bias, scale: int = 16) -> torch.Tensor:
     """get_seen_probs (bg_detector.py:141-165): sigmoid of the x16 align_corners=True
     up-sampled low-res logits, all T heads -> [B,T,H,W]."""
