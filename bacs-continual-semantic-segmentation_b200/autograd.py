@@ -38,7 +38,9 @@ class PixelLossFunction(torch.autograd.Function):
         focal_head = cfg.get("focal_head", -1)
         want_grad = bool(cfg.get("want_grad", True)) and ctx.needs_input_grad[0]
         has_focal = z is not None and focal_head >= 0
-        B, _, H, W = logits.shape
+        lowres = bool(cfg.get("lowres", False))      # logits are the network's low-res sem_logits (fused up-sample)
+        B = logits.shape[0]
+        H, W = (labels.shape[-2], labels.shape[-1]) if lowres else (logits.shape[2], logits.shape[3])
         scale = cfg.get("loss_scale", 1.0)
         over_wsum = mode != _cabi.PIX_WEIGHTED_CE
         main_coef = scale if over_wsum else scale / float(B * H * W)            # WEIGHTED_CE: mean over ALL pixels (Q6)
@@ -54,7 +56,7 @@ class PixelLossFunction(torch.autograd.Function):
             focal_gamma=cfg.get("focal_gamma", 2.0), focal_alpha=cfg.get("focal_alpha"),
             lkd_threshold=cfg.get("lkd_threshold", 0.5), ignore_index=cfg.get("ignore_index", 255),
             grad_scale=cfg.get("loss_scale", 1.0), seen_scale=cfg.get("seen_scale", 16),
-            seen_max=cfg.get("seen_max"), epilogue=epilogue)
+            seen_max=cfg.get("seen_max"), epilogue=epilogue, lowres=lowres)
         acc = out["acc"]
         loss = out["loss"].reshape(())
         dweight = dbias = dfeat = None

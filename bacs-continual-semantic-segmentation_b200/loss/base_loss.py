@@ -65,6 +65,9 @@ class BaseLoss:
         self.weighted_ce = None
         self.prev_model = None
         self.init_weighted_loss()
+        # opt-in, not in the reference: evaluate the network's final logit up-sample inside the loss kernel (see
+        # compute_base_loss); False keeps the reference's data flow ([B,K,H,W] logits from the network)
+        self.fused_logit_upsample = False
         # fused-kernel by-products of the last compute_base_loss call
         self._fused_preds = None
         self._fused_logits_id = None
@@ -171,7 +174,13 @@ class BaseLoss:
         seen_net = getattr(model, "seen_fg_network", None)
         train_seen_detector = (seen_net is not None and (self.same_task or not is_experience_replay) and train)
         return_penultimate = train_seen_detector or use_weighted_ce or self._prototypes is not None
-        preds_mask, penultimate_output, attentions = model(img, return_penultimate=True, return_attentions=True)
+        if self.fused_logit_upsample:
+            # opt-in: take the head's low-res sem_logits (deeplab_v3.py:155-156) and evaluate the network's
+            # final bilinear up-sample (deeplab_v3.py:157-160) and its backward inside the loss kernel
+            preds_mask, penultimate_output, attentions = model(img, return_penultimate=True, return_attentions=True,
+                                                               return_sem_logits=True)
+        else:
+            preds_mask, penultimate_output, attentions = model(img, return_penultimate=True, return_attentions=True)
         if self.prev_model is not None and train and return_attentions:
             with torch.no_grad():
                 _, _, old_atts = self.prev_model(img, return_penultimate=True, return_attentions=True)
@@ -181,7 +190,8 @@ class BaseLoss:
         if ready is None:
             train_seen_detector = False
         wce_on = bool(use_weighted_ce and train)
-        cfg = {"ignore_index": self.ignore_index, "loss_scale": float(_loss_scale), "want_grad": True}
+        cfg = {"ignore_index": self.ignore_index, "loss_scale": float(_loss_scale), "want_grad": True,
+               "lowres": bool(self.fused_logit_upsample)}
         head_w = head_b = None
         features = penultimate_output
         if wce_on or train_seen_detector:

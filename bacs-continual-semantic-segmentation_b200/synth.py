@@ -205,7 +205,11 @@ class FixedOutputNetwork(torch.nn.Module):
     def forward(self, x, return_attentions=False, return_penultimate=False, return_sem_logits=False,
                 only_attentions=False):
         if return_sem_logits:
-            return self._sem[id(x)]
+            sem = self._sem[id(x)]
+            if return_penultimate and return_attentions:     # networks/deeplab_v3.py:155-172 with all three flags
+                _, pen, atts = self._full[id(x)]
+                return sem, pen, atts
+            return sem
         logits, pen, atts = self._full[id(x)]
         if return_penultimate and return_attentions:
             return logits, pen, atts

@@ -177,3 +177,50 @@ def test_lowres_rejects_unsupported_geometry(ops):
     lab = torch.zeros(1, 32, 32, dtype=torch.int64).cuda()      # x4: not a network stride of the reference
     with pytest.raises(_cabi.BacsError):
         ops.pixel_loss(sem, lab, _cabi.PIX_CE, want_grad=False, lowres=True)
+
+
+@pytest.mark.parametrize("name,dtype", [("tiny", torch.float32), ("small", torch.float32), ("row512", torch.float32),
+                                        ("row512", torch.bfloat16)])
+def test_full_step_with_fused_logit_upsample(synth, name, dtype):
+    """BACSLoss(fused_logit_upsample=True): the network hands over sem_logits (return_sem_logits=True) and the whole
+    step -- prototypes, seen heads, weighted CE, focal, distill, DER replay, dark++ -- matches the oracle's step fed
+    the up-sampled logits; gradients arrive at the low-res logits."""
+    cfg = synth.CONFIGS[name]
+    inp = synth.make_step_inputs(cfg, seed=11, dtype=dtype)
+    g = torch.Generator().manual_seed(21)
+    sem = (torch.randn(cfg.B, cfg.K, cfg.h, cfg.w, generator=g) * 2).to(dtype)
+    rsem = (torch.randn(cfg.Br, cfg.K, cfg.h, cfg.w, generator=g) * 2).to(dtype)
+    # ---- oracle: the reference's data flow (up-sample, then the step) ----
+    leaf = lambda t: t.float().clone().requires_grad_(True)
+    sem_o, rsem_o, na, hw, hb = leaf(sem), leaf(rsem), leaf(inp.new_att), leaf(inp.head_w), leaf(inp.head_b)
+    rp = inp.replay
+    rdl = leaf(rp["sem_logits"])
+    rp2 = dict(rp, logits=O.upsample_sem_logits(rsem_o, (cfg.H, cfg.W)), sem_logits=rdl, pen=rp["pen"].float(),
+               n_classes=rp["n_classes"].numpy(), memory_logits=rp["memory_logits"].float())
+    want = O.bacs_step(O.upsample_sem_logits(sem_o, (cfg.H, cfg.W)), inp.pen.float(), inp.old_att.float(), na, inp.mask,
+                       inp.protos, inp.counts, hw, hb, initial_classes=cfg.initial_classes, increment=cfg.increment,
+                       old_cl=cfg.old_cl, task_num=cfg.T - 1, first_task=False, epoch=3, max_epochs=30, replay=rp2,
+                       nb_current_classes=cfg.K, proto_mode="exact")
+    want["loss"].backward()
+    # ---- the product path ----
+    loss_fn, net, batch, leaves = synth.build_bacs_step(cfg, inp, fused_logit_upsample=True)
+    sem_g = sem.clone().cuda().requires_grad_(True)
+    rsem_g = rsem.clone().cuda().requires_grad_(True)
+    net.register_sem(batch["main"][0], sem_g)
+    net.register_sem(batch["buffer"][0], rsem_g)
+    loss, preds = loss_fn.compute_loss(batch, net, train=True)
+    loss.backward()
+    close(loss, want["loss"], what="loss")
+    up = O.upsample_sem_logits(sem, (cfg.H, cfg.W))
+    _check_preds(preds, up)
+    close(loss_fn.prototypes, want["protos"], what="prototypes")
+    tol = 2e-5 if dtype == torch.float32 else 2.0 ** -7
+    for got, wnt, what in ((sem_g.grad, sem_o.grad, "d sem_logits"), (rsem_g.grad, rsem_o.grad, "d replay sem_logits"),
+                           (leaves["replay_sem"].grad, rdl.grad, "d DER logits")):
+        w = wnt.to(dtype).float()
+        close(got.float(), w, atol=tol * float(w.abs().max()), what=what)
+    w = na.grad.to(dtype).float()
+    close(leaves["new_att"].grad.float(), w, atol=3 * tol * float(w.abs().max()), what="d new_att")
+    assert leaves["logits"].grad is None          # the full-resolution logits were never touched
+    t = cfg.T - 1
+    close(leaves["head_w"].grad.reshape(-1), hw.grad[t], atol=3e-5 * float(hw.grad[t].abs().max()), what="dhead_w")
