@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="do not also time the CUDA-graph replay of the step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fused-lowres", action="store_true",
+                    help="skip the extra timing of BACSLoss(fused_logit_upsample=True) (low-res logits in, N=1 only)")
     return ap.parse_args()
 
 
@@ -327,6 +329,46 @@ def main():
                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e}
         net.register(img, leaves["logits"], leaves["pen"], [leaves["new_att"]])
 
+    # ---- extra (not the headline): the opt-in fused path -- the network hands over its low-res sem_logits and the
+    # x16 bilinear up-sample, the loss and the adjoint of the up-sample run in one kernel
+    fused = None
+    if world == 1 and not args.no_fused_lowres:
+        try:
+            loss2, net2, batch2, leaves2 = synth.build_bacs_step(cfg, inp, device=dev, fused_logit_upsample=True)
+            gen = torch.Generator().manual_seed(7)
+            sems = []
+            for key, nb in (("main", cfg.B), ("buffer", cfg.Br)):
+                if isinstance(batch2, dict) and key in batch2 or key == "main":
+                    im = batch2[key][0] if isinstance(batch2, dict) else batch2[0]
+                    sem = torch.randn(nb, cfg.K, cfg.h, cfg.w, generator=gen).to(dtype).to(dev).requires_grad_(True)
+                    net2.register_sem(im, sem)
+                    sems.append(sem)
+
+            def step2():
+                for v in list(leaves2.values()) + sems:
+                    v.grad = None
+                loss, preds = loss2.compute_loss(batch2, net2, train=True)
+                loss.backward()
+            ms2 = timed(step2, args.steps, max(args.warmup, 3))
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step2()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph2):
+                step2()
+            ms2g = timed(graph2.replay, args.steps, max(args.warmup, 3))
+            fused = {"what": "BACSLoss(fused_logit_upsample=True): sem_logits [B,K,H/16,W/16] in, up-sample + loss + "
+                             "adjoint in one kernel; no [B,K,H,W] logits or gradient exist",
+                     "ms_per_step_eager": ms2, "ms_per_step_graph": ms2g,
+                     "value": pixels / (min(ms2, ms2g) * 1e-3), "unit": UNIT,
+                     "logit_bytes_per_step": int(sems[0].numel() * es * 2)}
+            graph2 = None
+        except Exception as exc:                                  # noqa: BLE001
+            sys.stderr.write("bench.py: fused low-res timing unavailable: %r\n" % (exc,))
+
     sampler.stop_flag = True
     sampler.join(timeout=2)
     clocks = sampler.summary()
@@ -353,7 +395,7 @@ def main():
                                          else "BACSLoss.compute_loss+backward (eager)"},
                 "ms_per_step_eager": ms_eager, "ms_per_step_graph": ms_graph,
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "fused_lowres": fused}
         print(json.dumps(line), flush=True)
     if world > 1:
         # A captured graph that holds NCCL kernels must be gone before the communicator is torn down; the
