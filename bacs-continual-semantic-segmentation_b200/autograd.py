@@ -22,6 +22,34 @@ def _scaled(grad: Optional[torch.Tensor], g: torch.Tensor) -> Optional[torch.Ten
     return ops.scale_inplace(grad, g.reshape(1))
 
 
+# ---- side stream: the seen-head backward (16 us, small grid) runs next to the teacher-distill chain --------------
+# PixelLossFunction.forward forks after the pixel kernel's reduction launch; whoever needs the head gradients
+# (PixelLossFunction.backward) or ends the step's forward (BACSLoss.compute_loss) joins.  Everything the side
+# kernel reads is kept alive until the join, so the caching allocator cannot hand it to a later main-stream op.
+_SIDE = {}
+_PENDING = {}
+OVERLAP_HEAD_BACKWARD = True
+
+
+def _side_stream(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    ent = _SIDE.get(key)
+    if ent is None:
+        side = torch.cuda.Stream(device=device)
+        ent = (side, torch.cuda.Event(), torch.cuda.Event(), side.cuda_stream)
+        _SIDE[key] = ent
+    return key, ent
+
+
+def join_side_stream():
+    """Make the current stream wait for side-stream work forked by PixelLossFunction (no-op when none is pending)."""
+    if not _PENDING:
+        return
+    for key in list(_PENDING):
+        event, _keep = _PENDING.pop(key)
+        torch.cuda.current_stream().wait_event(event)
+
+
 class PixelLossFunction(torch.autograd.Function):
     """Fused per-pixel CE family (+ seen-detector focal term) + arg-max.
 
@@ -63,9 +91,21 @@ class PixelLossFunction(torch.autograd.Function):
         if has_focal and head_weight is not None and (ctx.needs_input_grad[2] or ctx.needs_input_grad[1]):
             want_df = bool(cfg.get("features_grad", False)) and ctx.needs_input_grad[1]
             proto_t = cfg["proto"][focal_head]
-            dweight, dbias, dfeat = ops.seen_head_backward(
-                features, proto_t, head_weight.detach().reshape(-1).float().contiguous(), out["gz"],
-                out["focal_scale"], want_df)
+            hw_flat = head_weight.detach().reshape(-1).float().contiguous()
+            if OVERLAP_HEAD_BACKWARD and cfg.get("overlap", True):
+                # launched on the side stream by handle (no current-stream switch: that costs ~30 us of CPU); the
+                # outputs live in the current stream's pool and are only touched there after the join
+                key, (side, fork, join, side_handle) = _side_stream(logits.device)
+                join_side_stream()                                 # at most one fork in flight per device
+                fork.record()
+                side.wait_event(fork)
+                dweight, dbias, dfeat = ops.seen_head_backward(features, proto_t, hw_flat, out["gz"],
+                                                               out["focal_scale"], want_df, stream=side_handle)
+                join.record(side)
+                _PENDING[key] = (join, (features, proto_t, hw_flat, out["gz"], out["focal_scale"]))
+            else:
+                dweight, dbias, dfeat = ops.seen_head_backward(features, proto_t, hw_flat, out["gz"],
+                                                               out["focal_scale"], want_df)
         ctx.grads = (out["dlogits"], dfeat, dweight, dbias)
         ctx.shapes = (None if head_weight is None else head_weight.shape, None if head_bias is None else head_bias.shape,
                       None if head_weight is None else head_weight.dtype)
@@ -80,6 +120,7 @@ class PixelLossFunction(torch.autograd.Function):
     def backward(ctx, g, _gp, _gm):
         dlogits, dfeat, dweight, dbias = ctx.grads
         ctx.grads = None
+        join_side_stream()
         if g is None:
             return None, None, None, None, None, None
         wshape, bshape, wdtype = ctx.shapes

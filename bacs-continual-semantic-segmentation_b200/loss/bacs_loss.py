@@ -20,7 +20,7 @@ from copy import deepcopy as copy
 import torch
 
 from .. import ops
-from ..autograd import DerMseFunction, TeacherDistillFunction
+from ..autograd import DerMseFunction, TeacherDistillFunction, join_side_stream
 from .base_loss import BaseLoss, SeenMap
 from .experience_replay import ExperienceReplay
 
@@ -178,6 +178,7 @@ class BACSLoss(ExperienceReplay):
         preds_output = self._argmax(preds_mask)        # produced by the fused kernel, no second read
         if train and self._use_der_loss and (self.alpha > 0 or self.beta > 0):
             loss = loss + self._replay_der_loss(model, batch["buffer"], batch["bufferlogits"])
+        join_side_stream()      # the seen-head backward forked by the pixel-loss op ran next to the distill chain
         return loss, preds_output
 
     def _teacher_distill(self, old_attention, new_attention, seen_prob, mask):

@@ -158,9 +158,11 @@ class BaseLoss:
         against prototypes[0]."""
         clf = seen_fg_network.seen_not_seen_clf
         heads = list(clf)[:n_heads] if isinstance(clf, torch.nn.ModuleList) else [clf]
-        weight = torch.cat([h.conv.weight.detach().reshape(1, -1) for h in heads], 0).float()
-        bias = torch.cat([h.conv.bias.detach().reshape(1) for h in heads], 0).float()
-        return weight, bias
+        # one cat launch for weights and biases together: [w_0 .. w_{T-1} | b_0 .. b_{T-1}]
+        n, d = len(heads), heads[0].conv.weight.numel()
+        flat = torch.cat([h.conv.weight.detach().reshape(-1) for h in heads]
+                         + [h.conv.bias.detach().reshape(-1) for h in heads]).float()
+        return flat[:n * d].view(n, d), flat[n * d:]
 
     def compute_base_loss(self, img, mask, model, task_num=-1, weights=None, train=True, use_weighted_ce=False,
                           return_attentions=False, _loss_scale=1.0):

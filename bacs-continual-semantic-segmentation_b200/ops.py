@@ -165,7 +165,9 @@ def seen_upsample(z: torch.Tensor, scale: int = 16, apply_sigmoid: bool = False)
 
 
 def seen_head_backward(features: torch.Tensor, proto_t: torch.Tensor, weight_t: torch.Tensor, gz: torch.Tensor,
-                       scale_dev: Optional[torch.Tensor], want_dfeatures: bool):
+                       scale_dev: Optional[torch.Tensor], want_dfeatures: bool, stream: Optional[int] = None):
+    """``stream``: raw handle of the stream to launch on (default: the current stream).  The outputs are allocated on
+    the current stream either way; a caller that passes another stream orders it against the current one itself."""
     features = _cuda(features, "seen_head_backward")
     B, D, h, w = features.shape
     dev = features.device
@@ -174,7 +176,8 @@ def seen_head_backward(features: torch.Tensor, proto_t: torch.Tensor, weight_t: 
     dfeat = torch.empty_like(features) if want_dfeatures else None
     check(_lib().bacs_seen_head_backward(features.data_ptr(), _dt(features), B, D, h, w, proto_t.data_ptr(),
                                          weight_t.data_ptr(), gz.data_ptr(), _ptr(scale_dev), dweight.data_ptr(),
-                                         dbias.data_ptr(), _ptr(dfeat), _stream()), "bacs_seen_head_backward")
+                                         dbias.data_ptr(), _ptr(dfeat), _stream() if stream is None else stream),
+          "bacs_seen_head_backward")
     return dweight, dbias, dfeat
 
 
