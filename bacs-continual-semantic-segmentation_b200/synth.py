@@ -74,6 +74,9 @@ CONFIGS = {
     # more classes than fit in registers: the shared-memory kernel with cooperating lane pairs (ADE20K-like)
     "row512_k40": StepConfig("row512_k40", B=2, K=40, old_cl=31, T=2, H=32, W=512, D=32, A=16, initial_classes=31,
                              increment=9),
+    # ADE20K-sized class count: 128-pixel tiles in 128-thread CTAs
+    "row512_k151": StepConfig("row512_k151", B=1, K=151, old_cl=101, T=2, H=32, W=512, D=32, A=16, initial_classes=101,
+                              increment=50),
     "row512_k7": StepConfig("row512_k7", B=1, K=7, old_cl=5, T=3, H=32, W=512, D=32, A=16, initial_classes=3,
                             increment=2),
 }

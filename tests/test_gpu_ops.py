@@ -234,7 +234,8 @@ def test_pixel_weighted_ce(ops, synth, name, dtype, ukd):
     ("row512_k7", torch.bfloat16, True), ("row512_k7", torch.float32, True),
     ("row512_t11", torch.bfloat16, True), ("row512_t11", torch.float32, True), ("row512_k24", torch.bfloat16, True),
     ("row512_k24", torch.float16, False), ("row512_k40", torch.bfloat16, True), ("row512_k40", torch.float32, True),
-    ("row512_k40", torch.float16, False)])
+    ("row512_k40", torch.float16, False), ("row512_k151", torch.bfloat16, True), ("row512_k151", torch.float32, True),
+    ("row512_k151", torch.float16, False)])
 def test_pixel_training_step_kernel(ops, synth, name, dtype, ukd):
     """512-pixel row tiles take the specialised training-step kernel: weighted CE + focal term of one head +
     distill mask + arg-max + both gradients in one launch, incl. padded class counts and invalid labels."""
