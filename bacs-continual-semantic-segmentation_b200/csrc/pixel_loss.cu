@@ -887,13 +887,17 @@ static bool make_lowres_plan(const bacs_pixel_args& a, int lh, int lw, LowresPla
   int R = 1;
   while (2 * R * lw <= kLowresThreads && 2 * R <= a.H) R *= 2;
   const float hy = hp_scale(lh, a.H);
-  const int groups = (a.H + R - 1) / R;
-  int nsrc = 1;
-  for (int g = 0; g < groups; ++g) {
-    int f0, f1, l0, l1;
-    host_half_pixel(g * R, lh, hy, &f0, &f1);
-    host_half_pixel(std::min(g * R + R, a.H) - 1, lh, hy, &l0, &l1);
-    nsrc = std::max(nsrc, l1 - f0 + 1);
+  int groups, nsrc;
+  for (;; R /= 2) {  // a row group may touch at most kLowresMaxSrc source rows
+    groups = (a.H + R - 1) / R;
+    nsrc = 1;
+    for (int g = 0; g < groups; ++g) {
+      int f0, f1, l0, l1;
+      host_half_pixel(g * R, lh, hy, &f0, &f1);
+      host_half_pixel(std::min(g * R + R, a.H) - 1, lh, hy, &l0, &l1);
+      nsrc = std::max(nsrc, l1 - f0 + 1);
+    }
+    if (nsrc <= kLowresMaxSrc || R == 1) break;
   }
   plan->SX = SX;
   plan->R = R;

@@ -38,7 +38,8 @@ struct alignas(16) LowresParams {
 };
 
 constexpr int kLowresThreads = 256;
-constexpr int kLowresChunk = 8;  // channels per gradient-reduction round
+constexpr int kLowresChunk = 8;   // channels per gradient-reduction round
+constexpr int kLowresMaxSrc = 8;  // source rows a row group may touch (the host halves R until it holds)
 
 template <int SX>
 __global__ void __launch_bounds__(kLowresThreads, 2) pixel_lowres_kernel(const __grid_constant__ LowresParams p) {
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(kLowresThreads, 2) pixel_lowres_kernel(const _
 #define BACS_LR_S(i) (((float)(i) + 0.5f) * kInvSX - 0.5f)
 
   // per-thread state that lives from the forward passes to the gradient pass
-  float nm[SX], cg1[SX], cg2[SX];
+  F2 nm2[SX / 2], cg1p[SX / 2], cg2p[SX / 2];  // pixel pairs (2i, 2i+1) as packed fp32 (FFMA2 / FMUL2 / FADD2)
   uint32_t ypk[SX / 4];
   float G0 = 0.f, GL0 = 0.f, GR0 = 0.f;
   int ymin = 256, ymax = -1;
@@ -193,6 +194,45 @@ __global__ void __launch_bounds__(kLowresThreads, 2) pixel_lowres_kernel(const _
       }
     }
 
+    // ---- seen heads: sigmoid(max_t up-sample(z_t)) and the focal head's logit, heads outer / pixels inner ------------
+    // (x16 align_corners=True: the thread's SX pixels touch the low-res columns cb, cb+1, cb+2 only)
+    float Lseen[SX], Lzf[SX], Lwx1[SX];
+    uint32_t fdm = 0;  // bit i: pixel i's left tap is column cb+1 (else cb); its right tap is the next column, clamped
+    const int cb = a.z ? lerp_align_corners(SX * j, a.w, p.sx).i0 : 0;
+    if (a.z) {
+      float wx1[SX], zmx[SX], zf[SX];
+#pragma unroll
+      for (int i = 0; i < SX; ++i) {
+        const Lerp lx = lerp_align_corners(SX * j + i, a.w, p.sx);
+        wx1[i] = lx.w1;
+        fdm |= (uint32_t)(lx.i0 - cb) << i;
+        zmx[i] = -INFINITY;
+        zf[i] = 0.f;
+      }
+      const float* zrow = zr + (size_t)r * a.T * a.w;
+      const int c1 = min(cb + 1, a.w - 1), c2 = min(cb + 2, a.w - 1);
+#pragma unroll 1
+      for (int t = 0; t < a.T; ++t) {
+        const float z0 = zrow[t * a.w + cb], z1 = zrow[t * a.w + c1], z2 = zrow[t * a.w + c2];
+        const bool foc = t == a.focal_head;
+#pragma unroll
+        for (int i = 0; i < SX; ++i) {
+          const bool up = (fdm >> i) & 1u;  // (c1, c2 are clamped like ATen's i1, so the right tap needs no case)
+          const float za = up ? z1 : z0;
+          const float zb = up ? z2 : z1;
+          const float v = __fadd_rn(__fmul_rn(1.f - wx1[i], za), __fmul_rn(wx1[i], zb));
+          zmx[i] = fmaxf(zmx[i], v);
+          if (foc) zf[i] = v;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < SX; ++i) {
+        Lseen[i] = sigmoid_fast(zmx[i]);
+        Lzf[i] = zf[i];
+        Lwx1[i] = wx1[i];
+      }
+    }
+
     // ---- pass 1a: max / arg-max (ties -> lowest channel) ------------------------------------------------------------
     float mx[SX];
     {
@@ -229,27 +269,35 @@ __global__ void __launch_bounds__(kLowresThreads, 2) pixel_lowres_kernel(const _
     }
 
     // ---- pass 1b: exponent sums; channel 0 stays out (S_fg is accumulated directly) -----------------------------
-    float so[SX], sn[SX];
+    F2 so2[SX / 2], sn2[SX / 2];
 #pragma unroll
-    for (int i = 0; i < SX; ++i) {
-      nm[i] = -mx[i] * kLog2e;
-      so[i] = sn[i] = 0.f;
+    for (int ip = 0; ip < SX / 2; ++ip) {
+      nm2[ip] = f2(-mx[2 * ip] * kLog2e, -mx[2 * ip + 1] * kLog2e);
+      so2[ip] = sn2[ip] = f2b(0.f);
     }
+    const F2 l2e2 = f2b(kLog2e);
+    // exp2((v_j + s_i D) log2e - max log2e) of one pixel pair
+    auto exp_pair = [&](int ip, F2 s2, F2 side2, F2 vj2) {
+      const F2 arg = fma2(fma2(s2, side2, vj2), l2e2, nm2[ip]);
+      return f2(ex2_fast(f2lo(arg)), ex2_fast(f2hi(arg)));
+    };
 #pragma unroll 1
     for (int c = 1; c < old_cl; ++c) {
       float vj, dl, dr;
       trio(c, vj, dl, dr);
+      const F2 vj2 = f2b(vj), dl2 = f2b(dl), dr2 = f2b(dr);
 #pragma unroll
-      for (int i = 0; i < SX; ++i)
-        so[i] += ex2_fast(fmaf(fmaf(BACS_LR_S(i), i < SX / 2 ? dl : dr, vj), kLog2e, nm[i]));
+      for (int ip = 0; ip < SX / 2; ++ip)
+        so2[ip] = add2(so2[ip], exp_pair(ip, f2(BACS_LR_S(2 * ip), BACS_LR_S(2 * ip + 1)), ip < SX / 4 ? dl2 : dr2, vj2));
     }
 #pragma unroll 1
     for (int c = max(old_cl, 1); c < K; ++c) {
       float vj, dl, dr;
       trio(c, vj, dl, dr);
+      const F2 vj2 = f2b(vj), dl2 = f2b(dl), dr2 = f2b(dr);
 #pragma unroll
-      for (int i = 0; i < SX; ++i)
-        sn[i] += ex2_fast(fmaf(fmaf(BACS_LR_S(i), i < SX / 2 ? dl : dr, vj), kLog2e, nm[i]));
+      for (int ip = 0; ip < SX / 2; ++ip)
+        sn2[ip] = add2(sn2[ip], exp_pair(ip, f2(BACS_LR_S(2 * ip), BACS_LR_S(2 * ip + 1)), ip < SX / 4 ? dl2 : dr2, vj2));
     }
 
     // ---- per-pixel terms: a rolled loop over dynamically indexed copies (local memory, L1) --------------------------
@@ -258,16 +306,14 @@ __global__ void __launch_bounds__(kLowresThreads, 2) pixel_lowres_kernel(const _
 #pragma unroll
     for (int i = 0; i < SX; ++i) {
       Lmx[i] = mx[i];
-      Lso[i] = so[i];
-      Lsn[i] = sn[i];
+      Lso[i] = (i & 1) ? f2hi(so2[i >> 1]) : f2lo(so2[i >> 1]);
+      Lsn[i] = (i & 1) ? f2hi(sn2[i >> 1]) : f2lo(sn2[i >> 1]);
     }
 #pragma unroll
     for (int q = 0; q < SX / 4; ++q) Ly[q] = ypk[q];
     float v0, dl0, dr0;
     trio(0, v0, dl0, dr0);
-    const float* zrow = zr + (size_t)r * a.T * a.w;
-    const int cb = a.z ? lerp_align_corners(SX * j, a.w, p.sx).i0 : 0;  // first low-res column of the seen heads
-    float f0 = 0.f, f1 = 0.f, f2 = 0.f;                                 // focal gradient at columns cb, cb+1, cb+2
+    float fa0 = 0.f, fa1 = 0.f, fa2 = 0.f;                              // focal gradient at columns cb, cb+1, cb+2
     uint32_t mbits = 0;
 #pragma unroll 1
     for (int i = 0; i < SX; ++i) {
@@ -290,22 +336,15 @@ __global__ void __launch_bounds__(kLowresThreads, 2) pixel_lowres_kernel(const _
         xy = fmaf(sI, left ? dl : dr, vj);
       }
       float seen = 0.f, zfoc = 0.f, wx1 = 0.f;
-      int fd = 0, cdx = 0;
-      if (a.seen_max) seen = __ldg(a.seen_max + pix0 + i);
+      int fd = 0, fhi = 0;
       if (a.z) {
-        const Lerp lx = lerp_align_corners(SX * j + i, a.w, p.sx);
-        const float wx0 = 1.f - lx.w1;
-        float zmax = -INFINITY;
-        for (int t = 0; t < a.T; ++t) {
-          const float v = __fadd_rn(__fmul_rn(wx0, zrow[t * a.w + lx.i0]), __fmul_rn(lx.w1, zrow[t * a.w + lx.i1]));
-          zmax = fmaxf(zmax, v);
-          if (t == a.focal_head) zfoc = v;
-        }
-        fd = lx.i0 - cb;
-        cdx = lx.i1 - lx.i0;
-        wx1 = lx.w1;
-        if (!a.seen_max) seen = sigmoid_fast(zmax);
+        seen = Lseen[i];
+        zfoc = Lzf[i];
+        wx1 = Lwx1[i];
+        fd = (int)((fdm >> i) & 1u);
+        fhi = min(cb + fd + 1, a.w - 1) - cb;
       }
+      if (a.seen_max) seen = __ldg(a.seen_max + pix0 + i);
       PixCoef pc;
       float gfoc;
       uint8_t dm;
@@ -320,22 +359,21 @@ __global__ void __launch_bounds__(kLowresThreads, 2) pixel_lowres_kernel(const _
       else GR0 = fmaf(sI, g0, GR0);
       if (a.gz && gfoc != 0.f) {
         const float c_lo = gfoc * (1.f - wx1), c_hi = gfoc * wx1;
-        const int hi = fd + cdx;
-        f0 += (fd == 0 ? c_lo : 0.f) + (hi == 0 ? c_hi : 0.f);
-        f1 += (fd == 1 ? c_lo : 0.f) + (hi == 1 ? c_hi : 0.f);
-        f2 += (hi == 2 ? c_hi : 0.f);
+        fa0 += (fd == 0 ? c_lo : 0.f) + (fhi == 0 ? c_hi : 0.f);
+        fa1 += (fd == 1 ? c_lo : 0.f) + (fhi == 1 ? c_hi : 0.f);
+        fa2 += (fhi == 2 ? c_hi : 0.f);
       }
     }
 #pragma unroll
-    for (int i = 0; i < SX; ++i) {
-      cg1[i] = Lcg1[i];
-      cg2[i] = Lcg2[i];
+    for (int ip = 0; ip < SX / 2; ++ip) {
+      cg1p[ip] = f2(Lcg1[2 * ip], Lcg1[2 * ip + 1]);
+      cg2p[ip] = f2(Lcg2[2 * ip], Lcg2[2 * ip + 1]);
     }
     if (a.gz) {
       float* grow = gacc + (size_t)r * (a.w + 1) + cb;
-      if (f0 != 0.f) atomicAdd(grow, f0);
-      if (f1 != 0.f) atomicAdd(grow + 1, f1);
-      if (f2 != 0.f) atomicAdd(grow + 2, f2);
+      if (fa0 != 0.f) atomicAdd(grow, fa0);
+      if (fa1 != 0.f) atomicAdd(grow + 1, fa1);
+      if (fa2 != 0.f) atomicAdd(grow + 2, fa2);
     }
     if (a.distill_mask) {
       uint8_t* out = a.distill_mask + pix0;
@@ -367,26 +405,22 @@ __global__ void __launch_bounds__(kLowresThreads, 2) pixel_lowres_kernel(const _
           if (c > 0) {
             float vj, dl, dr;
             trio(c, vj, dl, dr);
-            G = GL = GR = 0.f;
-            if (c < old_cl) {
+            const F2 vj2 = f2b(vj), dl2 = f2b(dl), dr2 = f2b(dr), l2e2 = f2b(kLog2e);
+            const bool is_old = c < old_cl;
+            F2 G2 = f2b(0.f), GL2 = f2b(0.f), GR2 = f2b(0.f);
 #pragma unroll
-              for (int i = 0; i < SX; ++i) {
-                const float e = ex2_fast(fmaf(fmaf(BACS_LR_S(i), i < SX / 2 ? dl : dr, vj), kLog2e, nm[i]));
-                const float g = e * cg1[i];
-                G += g;
-                if (i < SX / 2) GL = fmaf(BACS_LR_S(i), g, GL);
-                else GR = fmaf(BACS_LR_S(i), g, GR);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < SX; ++i) {
-                const float e = ex2_fast(fmaf(fmaf(BACS_LR_S(i), i < SX / 2 ? dl : dr, vj), kLog2e, nm[i]));
-                const float g = e * cg2[i];
-                G += g;
-                if (i < SX / 2) GL = fmaf(BACS_LR_S(i), g, GL);
-                else GR = fmaf(BACS_LR_S(i), g, GR);
-              }
+            for (int ip = 0; ip < SX / 2; ++ip) {
+              const F2 s2 = f2(BACS_LR_S(2 * ip), BACS_LR_S(2 * ip + 1));
+              const F2 arg = fma2(fma2(s2, ip < SX / 4 ? dl2 : dr2, vj2), l2e2, nm2[ip]);
+              const F2 e2 = f2(ex2_fast(f2lo(arg)), ex2_fast(f2hi(arg)));
+              const F2 g2 = mul2(e2, is_old ? cg1p[ip] : cg2p[ip]);
+              G2 = add2(G2, g2);
+              if (ip < SX / 4) GL2 = fma2(s2, g2, GL2);
+              else GR2 = fma2(s2, g2, GR2);
             }
+            G = f2lo(G2) + f2hi(G2);
+            GL = f2lo(GL2) + f2hi(GL2);
+            GR = f2lo(GR2) + f2hi(GR2);
           }
           // -dy at the label's own channel (rare: only channels that occur among the thread's labels)
           if (c >= ymin && c <= ymax) {
@@ -420,22 +454,39 @@ __global__ void __launch_bounds__(kLowresThreads, 2) pixel_lowres_kernel(const _
       }
       __syncthreads();
       // rows -> source rows with their y-weights; one global fp32 RED per low-res cell of the chunk
-      for (int t = wid; t < nsrc * cn; t += kLowresThreads / 32) {
-        const int n = t / cn, cc = t - n * cn;
-        const float* wr = wrow + n * R;
+      // (a warp takes a channel, a lane a column: every row's value is read once and feeds all source rows)
+      for (int cc = wid; cc < cn; cc += kLowresThreads / 32) {
         for (int x = lane; x < lw; x += 32) {
-          float sum = 0.f;
-          for (int rr = 0; rr < rows; ++rr) {
-            const float wv = wr[rr];
-            if (wv != 0.f) {
+          float* gout = gimg + ((int64_t)(c0 + cc) * lh + base) * lw + x;
+          if (nsrc <= 2) {  // the usual case: a row group lies between two source rows
+            float sum0 = 0.f, sum1 = 0.f;
+            for (int rr = 0; rr < rows; ++rr) {
               const float* q = planes + ((size_t)rr * CH + cc) * lw + x;
               float v = q[0];
               if (x + 1 < lw) v += q[plane_sz + 1];
               if (x >= 1) v += q[2 * plane_sz - 1];
-              sum = fmaf(wv, v, sum);
+              sum0 = fmaf(wrow[rr], v, sum0);
+              sum1 = fmaf(wrow[R + rr], v, sum1);
             }
+            if (sum0 != 0.f) atomicAdd(gout, sum0);
+            if (nsrc == 2 && sum1 != 0.f) atomicAdd(gout + lw, sum1);
+          } else {
+            float sum[kLowresMaxSrc];
+#pragma unroll
+            for (int n = 0; n < kLowresMaxSrc; ++n) sum[n] = 0.f;
+            for (int rr = 0; rr < rows; ++rr) {
+              const float* q = planes + ((size_t)rr * CH + cc) * lw + x;
+              float v = q[0];
+              if (x + 1 < lw) v += q[plane_sz + 1];
+              if (x >= 1) v += q[2 * plane_sz - 1];
+#pragma unroll
+              for (int n = 0; n < kLowresMaxSrc; ++n)
+                if (n < nsrc) sum[n] = fmaf(wrow[n * R + rr], v, sum[n]);
+            }
+#pragma unroll
+            for (int n = 0; n < kLowresMaxSrc; ++n)
+              if (n < nsrc && sum[n] != 0.f) atomicAdd(gout + (int64_t)n * lw, sum[n]);
           }
-          if (sum != 0.f) atomicAdd(gimg + ((int64_t)(c0 + cc) * lh + base + n) * lw + x, sum);
         }
       }
       __syncthreads();
