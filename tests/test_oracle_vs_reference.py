@@ -119,6 +119,24 @@ def test_bilinear_matches_interpolate(ref):
     _close(O.bilinear_upsample(x, (80, 112), True), up(x))
 
 
+@pytest.mark.parametrize("shape,stride", [((2, 7, 4, 6), 16), ((1, 21, 33, 33), 16), ((2, 5, 8, 10), 8)])
+def test_upsample_sem_logits_matches_network_op(ref, shape, stride):
+    """networks/deeplab_v3.py:157-160: F.interpolate(sem_logits, size=input_shape, mode="bilinear",
+    align_corners=False) -- values and the gradient autograd sends back to sem_logits (oracle of the fused low-res path)"""
+    g = torch.Generator().manual_seed(shape[1])
+    x = torch.randn(*shape, generator=g)
+    out_hw = (shape[2] * stride, shape[3] * stride)
+    upstream = torch.randn(shape[0], shape[1], *out_hw, generator=g)
+    a = x.clone().requires_grad_(True)
+    want = torch.nn.functional.interpolate(a, size=out_hw, mode="bilinear", align_corners=False)
+    want.backward(upstream)
+    b = x.clone().requires_grad_(True)
+    got = O.upsample_sem_logits(b, out_hw)
+    got.backward(upstream)
+    _close(got, want)
+    _close(b.grad, a.grad, atol=1e-5 * float(a.grad.abs().max()))
+
+
 @pytest.mark.parametrize("ukd", [True, False])
 @pytest.mark.parametrize("name", ["tiny", "small"])
 def test_weighted_ce_matches(ref, name, ukd):
