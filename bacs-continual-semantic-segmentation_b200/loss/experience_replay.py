@@ -81,9 +81,11 @@ class ExperienceReplay(BaseLoss):
     def _score_batch(self, model, images, labels, weights):
         """Per-image importance -(w_y * nll).mean over H*W (experience_replay.py:137-143,
         bacs_loss.py:183-189) from the fused kernel's SCORE mode."""
-        logits = model(images)
+        fused = bool(getattr(self, "fused_logit_upsample", False))
+        # fused: score straight from the head's low-res logits (the up-sample runs inside the kernel)
+        logits = model(images, return_sem_logits=True) if fused else model(images)
         out = ops.pixel_loss(logits.detach(), labels, _cabi.PIX_SCORE, want_grad=False, want_preds=False,
-                             class_w=weights, want_score=True, ignore_index=self.ignore_index)
+                             class_w=weights, want_score=True, ignore_index=self.ignore_index, lowres=fused)
         return logits, out["score"].float()
 
     def on_train_end(self, **kwargs):

@@ -94,6 +94,53 @@ def full_step(ref, name, first_task, seed):
     return out
 
 
+def train_end(ref, backfill):
+    """BACSLoss.on_train_end (loss/bacs_loss.py:133-203): prototype back-fill when a task has no sample yet
+    (loss/prototypes.py:92-125), then one pass over the train loader that fills the replay buffer."""
+    import tempfile
+    import types
+    from fake_net import EndOfTaskAccelerator, EndOfTaskLoader, EndOfTaskNet, end_of_task_case
+    if not hasattr(np, "Inf"):
+        np.Inf = np.inf                                   # the reference predates numpy 2
+    cfg, inps, images, sems, paths, tpaths = end_of_task_case(synth)
+    inp = inps[0]
+    task_num = cfg.T - 1
+    root = tempfile.mkdtemp()
+    os.environ["BACS_REF_CWD"] = root
+    L = ref["loss.bacs_loss"].BACSLoss(name="ref", bg_weighted_ce=True, buffer_size=4)
+    L.init_prototype_compute()
+    L.set_continual_task_size(cfg.initial_classes, cfg.increment)
+    for t in range(cfg.T):
+        L._prototypes._init_prototypes(t, _Accel(), cfg.D)
+    counts = inp.counts.clone()
+    if backfill:
+        counts[task_num] = 0
+    L._prototypes._prototypes_tensors = inp.protos.clone()
+    L._prototypes._count_features = counts
+    L._update_task(task_num)
+    L.old_classes, L.nb_current_classes = cfg.old_cl, cfg.K
+    L.set_device(torch.device("cpu"))
+    L.accelerator = _Accel()
+    bg = ref_seen_net(ref, inp)
+    net = EndOfTaskNet(bg, [i.logits for i in inps], sems, [i.pen for i in inps])
+    loader = EndOfTaskLoader([(im.clone(), i.mask.clone()) for im, i in zip(images, inps)], paths, tpaths)
+    trainer = types.SimpleNamespace(datamodule=types.SimpleNamespace(_sweep=False, debug=False))
+    np.random.seed(0)
+    L.on_train_end(pre_last_tasks=True, model=net, train_dataloader=loader, accelerator=EndOfTaskAccelerator("cpu"),
+                   trainer=trainer)
+    buf = L.buffer
+    out = {"protos": L.prototypes.numpy(), "counts": np.asarray(L._prototypes._count_features.numpy(), np.float64),
+           "examples": np.array(buf.dataset_map["examples"][:]), "logits": np.array(buf.dataset_map["logits"][:]),
+           "labels": np.array(buf.dataset_map["labels"][:]).astype(np.uint8),
+           "seen": np.array(buf.dataset_map["seen"][:]),
+           "importance": np.asarray(buf.importance_score, np.float64), "scores": np.asarray(buf.scores, np.float64),
+           "existing": np.asarray(buf._existing_indices), "n_classes": np.asarray(buf._logits_n_classes),
+           "img_paths": np.asarray([str(buf.img_paths.get(i, "")) for i in range(4)]),
+           "num_seen": np.int64(buf.num_seen_examples),
+           "backfill": np.bool_(backfill)}
+    return out
+
+
 def label_cases(ref):
     TL = __import__("training.utils", fromlist=["TransformLabel"]).TransformLabel
     rng = np.random.RandomState(0)
@@ -135,6 +182,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "step_tiny.npz"), **full_step(ref, "tiny", False, 11))
     np.savez_compressed(os.path.join(HERE, "step_tiny_first_task.npz"), **full_step(ref, "tiny", True, 11))
     np.savez_compressed(os.path.join(HERE, "labels.npz"), **label_cases(ref), **task_and_downsample(ref))
+    np.savez_compressed(os.path.join(HERE, "train_end.npz"), **train_end(ref, False))
+    np.savez_compressed(os.path.join(HERE, "train_end_backfill.npz"), **train_end(ref, True))
     # the reference's only known-answer vector (training/metrics.py:159-183)
     label = np.zeros((1, 4, 4), np.int64)
     pred = np.zeros((1, 4, 4), np.float32)
