@@ -240,7 +240,8 @@ def build_bacs_step(cfg: StepConfig, inp: StepInputs, device="cuda", first_task:
 
     dev = torch.device(device)
     task_num = cfg.T - 1
-    loss_fn = BACSLoss(name="bacs", bg_weighted_ce=True, **loss_kwargs)
+    loss_kwargs.setdefault("bg_weighted_ce", True)
+    loss_fn = BACSLoss(name="bacs", **loss_kwargs)
     loss_fn.init_prototype_compute()
     loss_fn._prototypes.exact = exact_prototypes
     loss_fn.set_continual_task_size(cfg.initial_classes, cfg.increment)

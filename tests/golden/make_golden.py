@@ -42,11 +42,12 @@ def ref_seen_net(ref, inp):
     return bg
 
 
-def full_step(ref, name, first_task, seed):
+def full_step(ref, name, first_task, seed, **loss_kwargs):
     cfg = synth.CONFIGS[name]
     inp = synth.make_step_inputs(cfg, seed=seed)
     task_num = cfg.T - 1
-    L = ref["loss.bacs_loss"].BACSLoss(name="ref", bg_weighted_ce=True)
+    loss_kwargs.setdefault("bg_weighted_ce", True)
+    L = ref["loss.bacs_loss"].BACSLoss(name="ref", **loss_kwargs)
     L.init_prototype_compute()
     L.set_continual_task_size(cfg.initial_classes, cfg.increment)
     for t in range(cfg.T):
@@ -181,6 +182,9 @@ def main():
     ref = ref_shim.install()
     np.savez_compressed(os.path.join(HERE, "step_tiny.npz"), **full_step(ref, "tiny", False, 11))
     np.savez_compressed(os.path.join(HERE, "step_tiny_first_task.npz"), **full_step(ref, "tiny", True, 11))
+    # plain CE + pseudo-labelled background (bacs_loss.py:65,205-210) + distill on mask == 0 alone (282-285)
+    np.savez_compressed(os.path.join(HERE, "step_tiny_pseudo.npz"),
+                        **full_step(ref, "tiny", False, 11, bg_weighted_ce=False, pseudo_label=True))
     np.savez_compressed(os.path.join(HERE, "labels.npz"), **label_cases(ref), **task_and_downsample(ref))
     np.savez_compressed(os.path.join(HERE, "train_end.npz"), **train_end(ref, False))
     np.savez_compressed(os.path.join(HERE, "train_end_backfill.npz"), **train_end(ref, True))

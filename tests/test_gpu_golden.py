@@ -18,13 +18,15 @@ def close(got, want, rtol=1e-5, atol=None, what=""):
     assert torch.allclose(got, want, rtol=rtol, atol=atol), "%s %.3e" % (what, float((got - want).abs().max()))
 
 
-@pytest.mark.parametrize("fixture,first_task", [("step_tiny.npz", False), ("step_tiny_first_task.npz", True)])
-def test_step_matches_reference_fixture(fixture, first_task):
+@pytest.mark.parametrize("fixture,first_task,kwargs", [
+    ("step_tiny.npz", False, {}), ("step_tiny_first_task.npz", True, {}),
+    ("step_tiny_pseudo.npz", False, {"bg_weighted_ce": False, "pseudo_label": True})])
+def test_step_matches_reference_fixture(fixture, first_task, kwargs):
     from bacs_b200 import synth
     gold = np.load(os.path.join(GOLD, fixture))
     cfg = synth.CONFIGS["tiny"]
     inp = synth.make_step_inputs(cfg, seed=int(gold["seed"]))
-    loss_fn, net, batch, leaves = synth.build_bacs_step(cfg, inp, first_task=first_task)
+    loss_fn, net, batch, leaves = synth.build_bacs_step(cfg, inp, first_task=first_task, **kwargs)
     loss, preds = loss_fn.compute_loss(batch, net, train=True)
     loss.backward()
     close(loss, gold["loss"], what="loss")
