@@ -277,27 +277,27 @@ __global__ void __launch_bounds__(kLowresThreads, 2) pixel_lowres_kernel(const _
     }
     const F2 l2e2 = f2b(kLog2e);
     // exp2((v_j + s_i D) log2e - max log2e) of one pixel pair
-    auto exp_pair = [&](int ip, F2 s2, F2 side2, F2 vj2) {
-      const F2 arg = fma2(fma2(s2, side2, vj2), l2e2, nm2[ip]);
+    // (the two up-sampled logits come from scalar FFMAs with immediate s_i -- a packed FFMA2 would need the constant
+    // pair in registers, re-materialised per channel -- and are identical to the values of pass 1a)
+    auto exp_pair = [&](int ip, float s_lo, float s_hi, float side, float vj) {
+      const F2 arg = fma2(f2(fmaf(s_lo, side, vj), fmaf(s_hi, side, vj)), l2e2, nm2[ip]);
       return f2(ex2_fast(f2lo(arg)), ex2_fast(f2hi(arg)));
     };
 #pragma unroll 1
     for (int c = 1; c < old_cl; ++c) {
       float vj, dl, dr;
       trio(c, vj, dl, dr);
-      const F2 vj2 = f2b(vj), dl2 = f2b(dl), dr2 = f2b(dr);
 #pragma unroll
       for (int ip = 0; ip < SX / 2; ++ip)
-        so2[ip] = add2(so2[ip], exp_pair(ip, f2(BACS_LR_S(2 * ip), BACS_LR_S(2 * ip + 1)), ip < SX / 4 ? dl2 : dr2, vj2));
+        so2[ip] = add2(so2[ip], exp_pair(ip, BACS_LR_S(2 * ip), BACS_LR_S(2 * ip + 1), ip < SX / 4 ? dl : dr, vj));
     }
 #pragma unroll 1
     for (int c = max(old_cl, 1); c < K; ++c) {
       float vj, dl, dr;
       trio(c, vj, dl, dr);
-      const F2 vj2 = f2b(vj), dl2 = f2b(dl), dr2 = f2b(dr);
 #pragma unroll
       for (int ip = 0; ip < SX / 2; ++ip)
-        sn2[ip] = add2(sn2[ip], exp_pair(ip, f2(BACS_LR_S(2 * ip), BACS_LR_S(2 * ip + 1)), ip < SX / 4 ? dl2 : dr2, vj2));
+        sn2[ip] = add2(sn2[ip], exp_pair(ip, BACS_LR_S(2 * ip), BACS_LR_S(2 * ip + 1), ip < SX / 4 ? dl : dr, vj));
     }
 
     // ---- per-pixel terms: a rolled loop over dynamically indexed copies (local memory, L1) --------------------------
@@ -405,22 +405,29 @@ __global__ void __launch_bounds__(kLowresThreads, 2) pixel_lowres_kernel(const _
           if (c > 0) {
             float vj, dl, dr;
             trio(c, vj, dl, dr);
-            const F2 vj2 = f2b(vj), dl2 = f2b(dl), dr2 = f2b(dr), l2e2 = f2b(kLog2e);
+            const F2 l2e2 = f2b(kLog2e);
             const bool is_old = c < old_cl;
-            F2 G2 = f2b(0.f), GL2 = f2b(0.f), GR2 = f2b(0.f);
+            F2 G2 = f2b(0.f);
+            float GLa = 0.f, GLb = 0.f, GRa = 0.f, GRb = 0.f;
 #pragma unroll
             for (int ip = 0; ip < SX / 2; ++ip) {
-              const F2 s2 = f2(BACS_LR_S(2 * ip), BACS_LR_S(2 * ip + 1));
-              const F2 arg = fma2(fma2(s2, ip < SX / 4 ? dl2 : dr2, vj2), l2e2, nm2[ip]);
+              const float side = ip < SX / 4 ? dl : dr;
+              const F2 arg = fma2(f2(fmaf(BACS_LR_S(2 * ip), side, vj), fmaf(BACS_LR_S(2 * ip + 1), side, vj)), l2e2,
+                                  nm2[ip]);
               const F2 e2 = f2(ex2_fast(f2lo(arg)), ex2_fast(f2hi(arg)));
               const F2 g2 = mul2(e2, is_old ? cg1p[ip] : cg2p[ip]);
               G2 = add2(G2, g2);
-              if (ip < SX / 4) GL2 = fma2(s2, g2, GL2);
-              else GR2 = fma2(s2, g2, GR2);
+              if (ip < SX / 4) {
+                GLa = fmaf(BACS_LR_S(2 * ip), f2lo(g2), GLa);
+                GLb = fmaf(BACS_LR_S(2 * ip + 1), f2hi(g2), GLb);
+              } else {
+                GRa = fmaf(BACS_LR_S(2 * ip), f2lo(g2), GRa);
+                GRb = fmaf(BACS_LR_S(2 * ip + 1), f2hi(g2), GRb);
+              }
             }
             G = f2lo(G2) + f2hi(G2);
-            GL = f2lo(GL2) + f2hi(GL2);
-            GR = f2lo(GR2) + f2hi(GR2);
+            GL = GLa + GLb;
+            GR = GRa + GRb;
           }
           // -dy at the label's own channel (rare: only channels that occur among the thread's labels)
           if (c >= ymin && c <= ymax) {
