@@ -1,4 +1,5 @@
 // DER logit MSE, confusion matrix + metrics, device-side scalar helpers, state packing.
+#include <algorithm>
 #include "common.cuh"
 
 namespace bacs {
@@ -350,6 +351,21 @@ __global__ void combine_kernel(CombineArgs a, float* __restrict__ out) {
 
 using namespace bacs;
 
+namespace bacs {
+// dst[i] = src[idx[i]] for rows of `row_elems` V's: the replay store's minibatch gather (an index outside [0, n_rows)
+// yields a zero row instead of a fault)
+template <typename V>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const V* __restrict__ src, int64_t n_rows, int64_t row_elems,
+                                                          const int64_t* __restrict__ idx, V* __restrict__ dst) {
+  const int64_t r = idx[blockIdx.y];
+  const bool ok = r >= 0 && r < n_rows;
+  const V* s = src + (ok ? r : 0) * row_elems;
+  V* d = dst + (int64_t)blockIdx.y * row_elems;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < row_elems; i += stride) d[i] = ok ? s[i] : V{};
+}
+}  // namespace bacs
+
 extern "C" {
 
 size_t bacs_der_workspace_bytes(int Br, int K, int hw) {
@@ -464,6 +480,28 @@ int bacs_confmat_metrics(const int64_t* confmat, int K, float* out, bacs_stream_
   BACS_REQUIRE(confmat && out && K > 0, "bacs_confmat_metrics: bad arguments");
   confmat_metrics_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(confmat, K, out);
   BACS_CHECK_LAUNCH("bacs_confmat_metrics");
+  return BACS_OK;
+}
+
+int bacs_gather_rows(const void* src, int64_t n_rows, int64_t row_bytes, const int64_t* idx, int64_t n_idx, void* dst,
+                     bacs_stream_t stream) {
+  BACS_REQUIRE(src && idx && dst && n_rows > 0 && row_bytes > 0 && n_idx >= 0, "bacs_gather_rows: bad arguments");
+  if (n_idx == 0) return BACS_OK;
+  const bool vec = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+  // blocks per row: enough to fill the machine a few times over, rows are MBs (images) or KBs (logits)
+  const int64_t chunk = 256 * 16 * 4;  // bytes a block moves per sweep with 16-byte vectors, 4 in flight per thread
+  int64_t per_row = std::max<int64_t>(1, std::min<int64_t>((row_bytes + chunk - 1) / chunk, 64));
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (per_row * n_idx > cap) per_row = std::max<int64_t>(1, cap / n_idx);
+  dim3 grid((unsigned)per_row, (unsigned)n_idx);
+  if (vec)
+    gather_rows_kernel<uint4><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(src), n_rows,
+                                                                      row_bytes / 16, idx, reinterpret_cast<uint4*>(dst));
+  else
+    gather_rows_kernel<unsigned char><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const unsigned char*>(src), n_rows, row_bytes, idx, reinterpret_cast<unsigned char*>(dst));
+  BACS_CHECK_LAUNCH("bacs_gather_rows");
   return BACS_OK;
 }
 

@@ -433,6 +433,20 @@ def confmat_metrics(confmat: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 # scalar helpers
 # --------------------------------------------------------------------------------------
+def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """out[i] = src[idx[i]] along dim 0 (any dtype; rows are copied as bytes)."""
+    src = _cuda(src, "gather_rows")
+    idx = _cuda(idx, "gather_rows", torch.int64)
+    n = int(idx.numel())
+    out = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    if n and src.shape[0]:
+        row_bytes = src[0].numel() * src.element_size()
+        if row_bytes:
+            check(_lib().bacs_gather_rows(src.data_ptr(), src.shape[0], row_bytes, idx.data_ptr(), n, out.data_ptr(),
+                                          _stream()), "bacs_gather_rows")
+    return out
+
+
 def scale_inplace(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     """x *= g for a device scalar g (fp32 [1] or 0-d); returns immediately on the device when g == 1."""
     if g.dtype != torch.float32:

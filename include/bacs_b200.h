@@ -303,6 +303,14 @@ int bacs_confmat_metrics(const int64_t* confmat, int K, float* out, bacs_stream_
 /* ---------------------------------------------------------------------------------
  * Small device-side helpers so the step stays free of host synchronisation
  * --------------------------------------------------------------------------------- */
+/* Minibatch gather of the HBM-resident replay store: dst[i] = src[idx[i]] for rows of row_bytes bytes.
+ * Replaces the fancy-index read of the reference's memmapped buffer fields in Buffer.get_data
+ * (training/buffer.py:371-381) and BaseMemMapDataset.__getitem__ (dataset/base_segmentation_dataset.py:89-97) plus
+ * the host->device copy of the sampled batch.  idx: device int64[n_idx]; an index outside [0, n_rows) gives a zero
+ * row.  16-byte vector path when row_bytes, src and dst are 16-byte aligned. */
+int bacs_gather_rows(const void* src, int64_t n_rows, int64_t row_bytes, const int64_t* idx, int64_t n_idx, void* dst,
+                     bacs_stream_t stream);
+
 /* In-place x *= *g for a gradient tensor when the upstream gradient is not 1; the kernel
  * exits immediately (uniformly) when *g == 1. */
 int bacs_scale_inplace(void* x, int dtype, int64_t n, const float* g_dev, bacs_stream_t stream);

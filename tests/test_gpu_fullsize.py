@@ -140,3 +140,71 @@ def test_confusion_matrix_cityscapes_eval_size():
     want = torch.bincount(target[valid] * K + preds[valid], minlength=K * K).view(K, K) * 2
     assert torch.equal(cm, want)
     assert int(cm.sum()) == 2 * int(valid.sum())
+
+
+def _device_oracle_pixel_check(cfg, B, dtype, lowres, seed=5):
+    """Whole-batch parity of the fused pixel kernel (full-resolution or low-res-logit variant) against the oracle's
+    formulas evaluated on device tensors, plus checksums; shapes of BASELINE.json's other configs."""
+    from bacs_b200 import _cabi, ops, synth
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    mask = synth.make_labels(cfg, torch.Generator().manual_seed(seed), classes=list(range(1, cfg.K)), B=B).cuda()
+    z = torch.randn(B, cfg.T, cfg.h, cfg.w, device="cuda", generator=g)
+    t = cfg.T - 1
+    if lowres:
+        src = (torch.randn(B, cfg.K, cfg.h, cfg.w, device="cuda", generator=g) * 2).to(dtype)
+    else:
+        src = torch.randn(B, cfg.K, cfg.H, cfg.W, device="cuda", generator=g).to(dtype)
+    out = ops.pixel_loss(src, mask, _cabi.PIX_WEIGHTED_CE, want_grad=True, z=z, want_distill_mask=True,
+                         old_cl=cfg.old_cl, ukd=True, focal_head=t, lowres=lowres)
+    zr = z.clone().requires_grad_(True)
+    up_z = O.bilinear_upsample(zr, (cfg.H, cfg.W), True)
+    smax = torch.sigmoid(up_z).max(1)[0].detach()
+    x = src.float().requires_grad_(True)
+    full = O.upsample_sem_logits(x, (cfg.H, cfg.W)) if lowres else x
+    want = O.weighted_ce(full, mask, smax, cfg.old_cl, 2.0, 0.5, True)
+    want.backward()
+    N = B * cfg.H * cfg.W
+    acc = out["acc"].cpu()
+    close(acc[_cabi.ACC_LOSS] / N, want, what="loss")
+    want_g = x.grad.to(dtype).float()
+    tol = 2e-5 if dtype == torch.float32 else 2.0 ** -7
+    close(out["dlogits"].float(), want_g, atol=tol * float(want_g.abs().max()), what="gradient")
+    kept = int((mask != 255).sum())
+    want_f = O.focal_seen_loss(up_z[:, t:t + 1], mask, 2.0, None)
+    want_f.backward()
+    close(acc[_cabi.ACC_FOCAL] / kept, want_f, what="focal loss")
+    close(out["gz"] / kept, zr.grad[:, t], atol=3e-5 * float(zr.grad.abs().max()), what="gz")
+    lf = full.detach()
+    top2 = lf.topk(2, dim=1)[0]
+    first = torch.where(lf == top2[:, :1], torch.arange(cfg.K, device="cuda").view(1, -1, 1, 1),
+                        torch.full((), cfg.K, device="cuda")).min(1)[0]
+    diff = out["preds"] != first
+    if lowres:      # the kernel's fp32 up-sample differs from torch's in the last bit: near-ties may flip
+        assert int((diff & ((top2[:, 0] - top2[:, 1]) > 1e-5)).sum()) == 0
+        assert int(diff.sum()) <= max(2, N // 100000)
+    else:
+        assert int(diff.sum()) == 0
+    want_m = (mask == 0) & (smax > 0.5)
+    dm = out["distill_mask"].bool() != want_m
+    assert int((dm & ((smax - 0.5).abs() > 1e-6)).sum()) == 0 and int(dm.sum()) <= 8
+    assert int(acc[_cabi.ACC_KEPT]) == kept and int(acc[_cabi.ACC_BG]) == int((mask == 0).sum())
+    assert int(acc[_cabi.ACC_DISTILL_PIX]) == int(out["distill_mask"].sum())
+    return out["variant"]
+
+
+@pytest.mark.parametrize("name,B,dtype,variant", [
+    ("voc10-1_der", 24, torch.bfloat16, 2),       # T = 11 seen heads: the 3-stage ring of the training-step kernel
+    ("cityscapes", 12, torch.bfloat16, 2),        # 512 x 1024 crops, K = 20
+    ("ade100-50", 4, torch.bfloat16, 0),          # K = 151: the shared-memory kernel with cooperating lane pairs
+    ("ade100-50", 2, torch.float32, 0)])
+def test_pixel_kernel_other_baseline_configs(name, B, dtype, variant):
+    from bacs_b200 import synth
+    assert _device_oracle_pixel_check(synth.CONFIGS[name], B, dtype, lowres=False) == variant
+
+
+@pytest.mark.parametrize("name,B,dtype", [("voc15-1_b24", 24, torch.bfloat16), ("cityscapes", 12, torch.float32),
+                                          ("ade100-50", 4, torch.bfloat16)])
+def test_lowres_kernel_baseline_configs(name, B, dtype):
+    """the fused up-sample + loss + adjoint kernel at BASELINE.json's shapes (sem_logits at stride 16)"""
+    from bacs_b200 import synth
+    assert _device_oracle_pixel_check(synth.CONFIGS[name], B, dtype, lowres=True) == 3

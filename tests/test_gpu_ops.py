@@ -562,3 +562,72 @@ def test_transform_label_class(ops):
         got = tl(torch.from_numpy(lbl).cuda()).cpu().numpy()
         assert np.array_equal(got, want)
         assert np.array_equal(tl(torch.from_numpy(lbl[0]).cuda()).cpu().numpy(), want[0])
+
+
+# --------------------------------------------------------------------------------------
+# HBM-resident replay store
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,dtype", [((7, 3, 16, 24), torch.float32), ((5, 9), torch.uint8), ((4, 6, 2, 2), torch.float32),
+                                         ((3, 1, 5, 7), torch.int64), ((6, 13), torch.bfloat16)])
+def test_gather_rows(ops, shape, dtype):
+    g = torch.Generator().manual_seed(shape[0])
+    src = (torch.randn(shape, generator=g) * 50).to(dtype)
+    idx = torch.randint(0, shape[0], (11,), generator=g)
+    got = ops.gather_rows(src.cuda(), idx.cuda()).cpu()
+    assert torch.equal(got, src[idx])
+    assert ops.gather_rows(src.cuda(), idx[:0].cuda()).shape[0] == 0
+    bad = torch.tensor([0, shape[0] + 3, -1])
+    got = ops.gather_rows(src.cuda(), bad.cuda()).cpu()        # out-of-range rows come back as zeros, not a fault
+    assert torch.equal(got[0], src[0]) and float(got[1:].float().abs().sum()) == 0.0
+
+
+def test_device_replay_store_matches_buffer(tmp_path, monkeypatch):
+    """DeviceReplayStore.get_data == Buffer.get_data(device=cuda) for the same np.random stream (bit-exact fields,
+    same indices, same n_classes / task_id), incl. after more data arrived and only the touched slots were refreshed."""
+    monkeypatch.setenv("BACS_BUFFER_ROOT", str(tmp_path))
+    from bacs_b200.training.buffer import Buffer
+    from bacs_b200.training.device_store import DeviceReplayStore
+    rng = np.random.RandomState(3)
+
+    def batch(B=3, K=5):
+        return {"examples": torch.from_numpy(rng.rand(B, 3, 32, 48).astype(np.float32)),
+                "logits": torch.from_numpy(rng.randn(B, K, 2, 3).astype(np.float32)),
+                "labels": torch.from_numpy(rng.randint(0, K, size=(B, 32, 48)).astype(np.int64)),
+                "seen": torch.from_numpy(rng.randn(B, 1, 32, 48).astype(np.float32)),
+                "loss": torch.from_numpy(-rng.rand(B).astype(np.float32))}
+    np.random.seed(0)
+    buf = Buffer(6, "all_tasks")
+    buf.update_task(task_num=0, new_class_size=5)
+    for _ in range(3):
+        buf.add_data(batch())
+    buf.merge_scores()
+    store = DeviceReplayStore(buf, "cuda")
+    for trial in range(3):
+        np.random.seed(10 + trial)
+        want = buf.get_data(4, device="cuda")
+        np.random.seed(10 + trial)
+        got, choice = store.get_data(4, return_indexes=True)
+        assert set(got) == set(want)
+        for key in ("examples", "logits", "labels", "seen"):
+            assert got[key].is_cuda and got[key].dtype == want[key].dtype and torch.equal(got[key], want[key]), key
+        assert np.array_equal(got["n_classes"], want["n_classes"]) and got["task_id"] == want["task_id"]
+    # reservoir replacement, then refresh only what changed
+    before = np.array(buf.dataset_map["examples"][:])
+    buf.add_data(batch())
+    changed = np.where(np.abs(np.array(buf.dataset_map["examples"][:]) - before).reshape(6, -1).sum(1) > 0)[0]
+    store.refresh(changed)
+    np.random.seed(99)
+    want = buf.get_data(5, device="cuda")
+    np.random.seed(99)
+    got = store.get_data(5)
+    for key in ("examples", "logits", "labels", "seen"):
+        assert torch.equal(got[key], want[key]), key
+    # the "bufferlogits" loader: every slot once per epoch, rows intact
+    seen_rows = []
+    for ex, lg, ncl in store.logits_batches(4, length=6, generator=torch.Generator().manual_seed(1)):
+        assert ex.shape[0] == lg.shape[0] == ncl.shape[0]
+        seen_rows.append(lg.cpu())
+    all_rows = torch.cat(seen_rows)
+    ref = torch.from_numpy(np.array(buf.dataset_map["logits"][:]))
+    assert all_rows.shape == ref.shape
+    assert sorted(map(float, all_rows.reshape(6, -1).sum(1))) == sorted(map(float, ref.reshape(6, -1).sum(1)))
