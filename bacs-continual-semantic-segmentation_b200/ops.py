@@ -433,6 +433,31 @@ def confmat_metrics(confmat: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 # scalar helpers
 # --------------------------------------------------------------------------------------
+def class_distance(features: torch.Tensor, class_protos: torch.Tensor, want_nearest: bool = True):
+    """Squared distance of every pixel feature to every class prototype on the tensor cores (bf16 operands, fp32
+    accumulation): features [B,D,h,w], class_protos [Kc,D] -> (dist2 fp32 [B,Kc,h,w], nearest int64 [B,h,w] or None)."""
+    features = _cuda(features, "class_distance")
+    class_protos = _cuda(class_protos, "class_distance")
+    if features.dtype != torch.bfloat16:
+        features = features.to(torch.bfloat16)
+    if class_protos.dtype != torch.bfloat16:
+        class_protos = class_protos.to(torch.bfloat16)
+    B, D, h, w = features.shape
+    Kc = class_protos.shape[0]
+    if class_protos.shape[1] != D:
+        raise ValueError("class_distance: prototypes %s do not match features %s" % (tuple(class_protos.shape),
+                                                                                     tuple(features.shape)))
+    dev = features.device
+    dist2 = torch.empty((B, Kc, h, w), dtype=torch.float32, device=dev)
+    nearest = torch.empty((B, h, w), dtype=torch.int64, device=dev) if want_nearest else None
+    lib = _lib()
+    ws = _ws(lib.bacs_class_distance_workspace_bytes(B, Kc, D, h, w), dev)
+    check(lib.bacs_class_distance(features.data_ptr(), _dt(features), B, D, h, w, class_protos.data_ptr(), Kc,
+                                  dist2.data_ptr(), _ptr(nearest), ws.data_ptr(), ws.numel(), _stream()),
+          "bacs_class_distance")
+    return dist2, nearest
+
+
 def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     """out[i] = src[idx[i]] along dim 0 (any dtype; rows are copied as bytes)."""
     src = _cuda(src, "gather_rows")

@@ -303,6 +303,20 @@ int bacs_confmat_metrics(const int64_t* confmat, int K, float* out, bacs_stream_
 /* ---------------------------------------------------------------------------------
  * Small device-side helpers so the step stays free of host synchronisation
  * --------------------------------------------------------------------------------- */
+/* ---------------------------------------------------------------------------------
+ * OPTIONAL per-class prototype family (BASELINE.json north_star): squared distance of every pixel's
+ * feature vector to every class prototype on the tcgen05 tensor cores,
+ *   dist2[b,k,y,x] = max(|f|^2 + |c_k|^2 - 2 <f, c_k>, 0),   nearest[b,y,x] = argmin_k (ties -> lowest class).
+ * Not reference arithmetic (the reference's heads are a weighted L1 of sigmoids, networks/bg_detector.py:17-40; SDR,
+ * loss/sdr.py:120-200, only ever touches a pixel's own class): the building block for nearest-class-prototype maps
+ * at ADE20K sizes (150 x 512 prototypes).  features [B,D,h,w] and protos [Kc,D] are bf16 (dtype = BACS_BF16), fp32
+ * accumulation; h*w and D multiples of 8, Kc <= 256; nearest may be NULL.
+ * --------------------------------------------------------------------------------- */
+size_t bacs_class_distance_workspace_bytes(int32_t B, int32_t Kc, int32_t D, int32_t h, int32_t w);
+int bacs_class_distance(const void* features, int dtype, int32_t B, int32_t D, int32_t h, int32_t w, const void* protos,
+                        int32_t Kc, float* dist2, int64_t* nearest, void* workspace, size_t workspace_bytes,
+                        bacs_stream_t stream);
+
 /* Minibatch gather of the HBM-resident replay store: dst[i] = src[idx[i]] for rows of row_bytes bytes.
  * Replaces the fancy-index read of the reference's memmapped buffer fields in Buffer.get_data
  * (training/buffer.py:371-381) and BaseMemMapDataset.__getitem__ (dataset/base_segmentation_dataset.py:89-97) plus

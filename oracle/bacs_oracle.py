@@ -410,6 +410,16 @@ def unbiased_kd(logits, old_logits, alpha: float = 1.0, mask: Optional[torch.Ten
 # Rows 12/14 -- arg-max and confusion matrix / metrics
 #   bacs_loss.py:255; training/metrics.py:38-88 over torchmetrics 0.6.0 ConfusionMatrix/IoU
 # --------------------------------------------------------------------------------------
+def class_distance(features: torch.Tensor, class_protos: torch.Tensor):
+    """Optional per-class prototype family (no counterpart in the reference's arithmetic): squared
+    Euclidean distance of every pixel feature [B,D,h,w] to every class prototype [Kc,D], evaluated directly as
+    sum_d (f_d - c_d)^2 in fp64 (no |f|^2 + |c|^2 - 2 f.c expansion), and the nearest class (ties -> lowest)."""
+    f = features.double().permute(0, 2, 3, 1)                       # [B,h,w,D]
+    c = class_protos.double()                                       # [Kc,D]
+    d2 = ((f.unsqueeze(3) - c) ** 2).sum(-1).permute(0, 3, 1, 2)    # [B,Kc,h,w]
+    return d2, d2.argmin(1)
+
+
 def argmax_first(logits: torch.Tensor) -> torch.Tensor:
     return logits.float().argmax(dim=1)
 

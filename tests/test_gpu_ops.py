@@ -631,3 +631,26 @@ def test_device_replay_store_matches_buffer(tmp_path, monkeypatch):
     ref = torch.from_numpy(np.array(buf.dataset_map["logits"][:]))
     assert all_rows.shape == ref.shape
     assert sorted(map(float, all_rows.reshape(6, -1).sum(1))) == sorted(map(float, ref.reshape(6, -1).sum(1)))
+
+
+# --------------------------------------------------------------------------------------
+# optional per-class prototype family: pixel x class-prototype distance on the tensor cores
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,D,h,w,Kc", [(2, 64, 8, 16, 10), (1, 72, 4, 6, 3), (3, 512, 32, 32, 150), (2, 256, 33, 40, 21)])
+def test_class_distance_tensor_cores(ops, B, D, h, w, Kc):
+    """bf16 operands are exact products in the fp32 accumulator: against the oracle fed the same bf16-rounded inputs the
+    squared distances agree to fp32 rounding of the |f|^2 + |c|^2 - 2 f.c expansion (1e-5 of the largest distance)."""
+    g = torch.Generator().manual_seed(Kc)
+    f = torch.randn(B, D, h, w, generator=g).to(torch.bfloat16)
+    c = torch.randn(Kc, D, generator=g).to(torch.bfloat16)
+    c[0] = f[0, :, 1, 2]                                   # a pixel that coincides with a prototype: distance 0
+    want, want_near = O.class_distance(f.float(), c.float())
+    got, near = ops.class_distance(f.cuda(), c.cuda())
+    assert tuple(got.shape) == (B, Kc, h, w) and got.dtype == torch.float32
+    close(got, want, atol=1e-5 * float(want.max()), what="dist2")
+    assert float(got.min()) >= 0.0 and float(got[0, 0, 1, 2]) <= 1e-5 * float(want.max())
+    top2 = want.topk(2, dim=1, largest=False)[0]
+    diff = near.cpu() != want_near
+    assert int((diff & ((top2[:, 1] - top2[:, 0]) > 2e-5 * float(want.max()))).sum()) == 0
+    d2, none = ops.class_distance(f.cuda(), c.cuda(), want_nearest=False)
+    assert none is None and torch.equal(d2, got)
