@@ -486,6 +486,7 @@ int bacs_confmat_metrics(const int64_t* confmat, int K, float* out, bacs_stream_
 int bacs_gather_rows(const void* src, int64_t n_rows, int64_t row_bytes, const int64_t* idx, int64_t n_idx, void* dst,
                      bacs_stream_t stream) {
   BACS_REQUIRE(src && idx && dst && n_rows > 0 && row_bytes > 0 && n_idx >= 0, "bacs_gather_rows: bad arguments");
+  BACS_REQUIRE(n_idx <= 65535, "bacs_gather_rows: at most 65535 rows per call (got %lld)", (long long)n_idx);
   if (n_idx == 0) return BACS_OK;
   const bool vec = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
