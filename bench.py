@@ -260,10 +260,14 @@ def main():
         z = ops.seen_logits(leaves["pen"].detach(), P._prototypes_tensors, w, b)
         lg, mk = leaves["logits"].detach(), batch["main"][1] if isinstance(batch, dict) else batch[1]
 
+        variant = {}
+
         def pixel_only():
-            ops.pixel_loss(lg, mk, _cabi.PIX_WEIGHTED_CE, want_grad=True, z=z, want_distill_mask=True,
-                           focal_head=cfg.T - 1, old_cl=cfg.old_cl)
+            variant["v"] = ops.pixel_loss(lg, mk, _cabi.PIX_WEIGHTED_CE, want_grad=True, z=z, want_distill_mask=True,
+                                          focal_head=cfg.T - 1, old_cl=cfg.old_cl)["variant"]
         ms_pix = timed(pixel_only, args.steps, max(args.warmup, 3))
+    kernel_name = {2: "pixel_wce_kernel", 1: "pixel_fast_kernel", 0: "pixel_loss_kernel (shared-memory tiles)"}.get(
+        variant.get("v"), "pixel kernel")
     alg_bytes = pixels * (2 * cfg.K * es + 8 + 8 + 1) + z.numel() * 4
     peak, peak_src = peaks()
     achieved = alg_bytes / (ms_pix * 1e-3) / 1e9
@@ -272,7 +276,7 @@ def main():
     if os.path.exists(tpath) and args.config == "voc15-1_b24" and args.dtype == "bf16":
         with open(tpath) as f:
             traffic = json.load(f).get("traffic_bytes_per_launch")   # dram read + write of one launch (ncu --set full)
-    roofline = {"bound": "hbm", "kernel": "pixel_wce_kernel (weighted CE + focal + argmax + distill mask + dlogits)",
+    roofline = {"bound": "hbm", "kernel": kernel_name + " (weighted CE + focal + argmax + distill mask + dlogits)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_pix,
                 "share_of_step": ms_pix / ms_step}
