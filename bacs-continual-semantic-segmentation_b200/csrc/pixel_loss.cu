@@ -861,8 +861,34 @@ static bool make_plan(const bacs_pixel_args& a, PixelPlan* plan) {
 }  // namespace bacs
 
 #include "pixel_lowres.cuh"  // the same loss evaluated from low-res logits (up-sample + adjoint fused)
+#include "pixel_stream.cuh"  // large class counts: two streaming passes instead of shared-memory tiles
 
 namespace bacs {
+
+struct StreamPlan {
+  int blocks_x;
+  size_t part_bytes, coef_bytes;
+};
+
+// K >= 64 on 16-byte aligned, vector-divisible images (everything else stays on the tile kernel)
+static bool make_stream_plan(const bacs_pixel_args& a, StreamPlan* plan) {
+  if (getenv("BACS_NO_STREAM")) return false;
+  const int64_t HW = (int64_t)a.H * a.W;
+  const int n = a.dtype == BACS_F32 ? 4 : 8;
+  auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
+  if (a.K < 64 || HW % n != 0 || !al(a.logits, 16) || !al(a.labels, 16)) return false;
+  if (a.dlogits && !al(a.dlogits, 16)) return false;
+  if (a.preds && !al(a.preds, 16)) return false;
+  if (a.distill_mask && !al(a.distill_mask, 4)) return false;
+  const int64_t groups = HW / n;
+  int64_t bx = (groups + kStreamThreads - 1) / kStreamThreads;
+  const int64_t cap = std::max<int64_t>(1, (int64_t)sm_count() * 16 / std::max(1, a.B));
+  if (bx > cap) bx = cap;
+  plan->blocks_x = (int)bx;
+  plan->part_bytes = align_up((size_t)bx * a.B * BACS_NACC * sizeof(double), 256);
+  plan->coef_bytes = a.dlogits ? align_up((size_t)6 * HW * a.B * sizeof(float), 256) : 0;
+  return true;
+}
 
 struct LowresPlan {
   int SX, R, groups, nsrc_max, grid;
@@ -1014,6 +1040,8 @@ int bacs_pixel_loss_lowres(const bacs_pixel_args* a, int32_t lh, int32_t lw, voi
 
 size_t bacs_pixel_workspace_bytes(const bacs_pixel_args* a) {
   if (!a) return 0;
+  StreamPlan sp;
+  if (make_stream_plan(*a, &sp)) return sp.part_bytes + sp.coef_bytes;
   PixelPlan plan;
   if (!make_plan(*a, &plan)) return 0;
   const int64_t HW = (int64_t)a->H * a->W;
@@ -1029,6 +1057,8 @@ static bool wce_eligible(const bacs_pixel_args& a, const PixelPlan& plan) {
 
 int bacs_pixel_kernel_variant(const bacs_pixel_args* a) {
   PixelPlan plan;
+  StreamPlan sp;
+  if (a && make_stream_plan(*a, &sp)) return 4;
   if (!a || !make_plan(*a, &plan)) return -1;
   return wce_eligible(*a, plan) ? 2 : (plan.fast ? 1 : 0);
 }
@@ -1053,6 +1083,41 @@ int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_
     BACS_REQUIRE(a->hist, "bacs_pixel_loss: CE-type gradients need the label histogram");
   if (a->mode == BACS_PIX_SCORE)
     BACS_REQUIRE(a->score && !a->dlogits, "bacs_pixel_loss: SCORE mode needs score and no gradient");
+  StreamPlan sp;
+  if (make_stream_plan(*a, &sp)) {  // large K: two streaming passes (pixel_stream.cuh)
+    if (!workspace || workspace_bytes < sp.part_bytes + sp.coef_bytes) {
+      set_error("bacs_pixel_loss: workspace too small (%zu bytes)", workspace_bytes);
+      return BACS_ERR_WORKSPACE;
+    }
+    StreamParams q;
+    q.a = *a;
+    q.partials = reinterpret_cast<double*>(workspace);
+    q.coef = a->dlogits ? reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + sp.part_bytes) : nullptr;
+    q.blocks_x = sp.blocks_x;
+    q.inv_n = (float)(1.0 / ((double)a->B * (double)a->H * (double)a->W));
+    q.sy = a->z ? ac_scale(a->h, a->H) : 0.f;
+    q.sx = a->z ? ac_scale(a->w, a->W) : 0.f;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)sp.blocks_x, (unsigned)a->B);
+    BACS_DISPATCH_DTYPE(a->dtype, TT, { pixel_stream_stats_kernel<TT><<<grid, kStreamThreads, 0, st>>>(q); });
+    BACS_CHECK_LAUNCH("bacs_pixel_loss(stream stats)");
+    if (a->dlogits) {
+      BACS_DISPATCH_DTYPE(a->dtype, TT, { pixel_stream_grad_kernel<TT><<<grid, kStreamThreads, 0, st>>>(q); });
+      BACS_CHECK_LAUNCH("bacs_pixel_loss(stream grad)");
+    }
+    const int nblk = 1 + (a->mode == BACS_PIX_SCORE ? a->B : 0);
+    PixelEpilogue ep;
+    ep.ready = a->ready;
+    ep.focal_scale_out = a->focal_scale_out;
+    ep.loss_out = a->loss_out;
+    ep.focal_weight = a->focal_weight;
+    ep.loss_coef = a->loss_coef;
+    ep.loss_over_wsum = a->loss_over_wsum;
+    pixel_reduce_kernel<<<nblk, 256, 0, st>>>(q.partials, sp.blocks_x * a->B, sp.blocks_x, a->acc, a->score,
+                                              1.0 / ((double)a->H * (double)a->W), ep);
+    BACS_CHECK_LAUNCH("bacs_pixel_loss(reduce)");
+    return BACS_OK;
+  }
   PixelPlan plan;
   if (!make_plan(*a, &plan)) {
     set_error("bacs_pixel_loss: K=%d too large for a shared-memory tile", a->K);
