@@ -266,7 +266,8 @@ def main():
             variant["v"] = ops.pixel_loss(lg, mk, _cabi.PIX_WEIGHTED_CE, want_grad=True, z=z, want_distill_mask=True,
                                           focal_head=cfg.T - 1, old_cl=cfg.old_cl)["variant"]
         ms_pix = timed(pixel_only, args.steps, max(args.warmup, 3))
-    kernel_name = {2: "pixel_wce_kernel", 1: "pixel_fast_kernel", 0: "pixel_loss_kernel (shared-memory tiles)"}.get(
+    kernel_name = {2: "pixel_wce_kernel", 1: "pixel_fast_kernel", 0: "pixel_loss_kernel (shared-memory tiles)",
+                   4: "pixel_stream_stats_kernel + pixel_stream_grad_kernel"}.get(
         variant.get("v"), "pixel kernel")
     alg_bytes = pixels * (2 * cfg.K * es + 8 + 8 + 1) + z.numel() * 4
     peak, peak_src = peaks()
