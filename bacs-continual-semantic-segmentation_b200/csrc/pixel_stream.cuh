@@ -10,8 +10,9 @@
 //   pass B  reads the logits a second time and writes the gradient  e_k * cg[group(k)] - [k==0] d0 - [k==y] dy.
 // HBM traffic is 3 K s + 64 bytes per pixel instead of the algorithmic 2 K s + 17 (one extra read of the logits), but
 // both passes are plain coalesced streams.  Measured at B=24, 512x512, K=151 (one B200): pass B 717 us (5.5 TB/s),
-// pass A 764 us (11 warp instructions per logit, issue slots 40 % busy: latency-bound, not yet HBM-bound);
-// fp32 logits 2.07 ms against 2.90 ms for the tile kernel, bf16 1.53 ms against 1.57 ms.
+// pass A 610 us with four pixels per thread (80 registers, three CTAs per SM; 764 us with eight pixels and two CTAs,
+// 43 % of the warp samples waiting on a just-issued load): issue slots 60 % busy, DRAM 44 %;
+// fp32 logits 2.08 ms against 2.90 ms for the tile kernel, bf16 1.35 ms against 1.57 ms.
 #pragma once
 #include "pixel_common.cuh"
 
@@ -77,13 +78,20 @@ template <> struct StreamVec<__half> {
   }
 };
 
+template <int BYTES> struct StreamWord;
+template <> struct StreamWord<16> { using type = uint4; };
+template <> struct StreamWord<8> { using type = uint2; };
+template <> struct StreamWord<4> { using type = uint32_t; };
+
 constexpr int kStreamThreads = 256;
+constexpr int kStreamStatsPx = 4;  // pixels per thread of the statistics pass (8- or 16-byte loads): its state fits 80 registers
 constexpr int kStreamChunk = 4;  // channels (16-byte loads) in flight per thread
 
 // ---- pass A: statistics, loss terms, coefficients, arg-max, distill mask, focal gradient ---------------------------
 template <typename T>
-__global__ void __launch_bounds__(kStreamThreads, 2) pixel_stream_stats_kernel(const __grid_constant__ StreamParams p) {
-  constexpr int N = StreamVec<T>::N, CH = kStreamChunk;
+__global__ void __launch_bounds__(kStreamThreads, 3) pixel_stream_stats_kernel(const __grid_constant__ StreamParams p) {
+  constexpr int N = kStreamStatsPx, CH = kStreamChunk;
+  using vec_t = typename StreamWord<sizeof(T) * N>::type;
   __shared__ float red_scratch[kStreamThreads / 32][BACS_NACC];
   __shared__ float s_norm_sh;
   const bacs_pixel_args& a = p.a;
@@ -119,12 +127,12 @@ __global__ void __launch_bounds__(kStreamThreads, 2) pixel_stream_stats_kernel(c
     constexpr int W = N / 2;
     using R = Raw<T>;
     using reg_t = typename R::reg_t;
-    static_assert(sizeof(reg_t) * W == sizeof(uint4), "a 16-byte vector is W packed pixel pairs");
+    static_assert(sizeof(reg_t) * W == sizeof(vec_t), "a vector is W packed pixel pairs");
     float m[N], so[N], sn[N], x0[N], nr[N];  // nr = -reference * log2e
     int am[N];
     typename R::Max mt[W];
     {
-      const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(base));
+      const vec_t r4 = __ldg(reinterpret_cast<const vec_t*>(base));
       const reg_t* rw = reinterpret_cast<const reg_t*>(&r4);
 #pragma unroll
       for (int w = 0; w < W; ++w) {
@@ -138,7 +146,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) pixel_stream_stats_kernel(c
       nr[j] = -x0[j] * kLog2e;
       so[j] = sn[j] = 0.f;
     }
-    auto one_channel = [&](const uint4& r4, int c, float* sum) {
+    auto one_channel = [&](const vec_t& r4, int c, float* sum) {
       const reg_t* rw = reinterpret_cast<const reg_t*>(&r4);
 #pragma unroll
       for (int w = 0; w < W; ++w) {
@@ -172,15 +180,15 @@ __global__ void __launch_bounds__(kStreamThreads, 2) pixel_stream_stats_kernel(c
     auto range = [&](int cbeg, int cend, float* sum) {
       int c = cbeg;
       for (; c + 2 * CH <= cend; c += 2 * CH) {  // 8 independent 16-byte loads in flight per thread
-        uint4 raw[2 * CH];
+        vec_t raw[2 * CH];
 #pragma unroll
-        for (int i = 0; i < 2 * CH; ++i) raw[i] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(c + i) * HW));
+        for (int i = 0; i < 2 * CH; ++i) raw[i] = __ldg(reinterpret_cast<const vec_t*>(base + (int64_t)(c + i) * HW));
 #pragma unroll
         for (int i = 0; i < 2 * CH; ++i) one_channel(raw[i], c + i, sum);
         lift_reference();
       }
       for (; c < cend; ++c) {
-        const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)c * HW));
+        const vec_t r4 = __ldg(reinterpret_cast<const vec_t*>(base + (int64_t)c * HW));
         one_channel(r4, c, sum);
       }
       lift_reference();
@@ -280,8 +288,10 @@ __global__ void __launch_bounds__(kStreamThreads, 2) pixel_stream_stats_kernel(c
       uint8_t dm;
       pixel_terms(a, p.inv_n, s_norm, old_cl, y, is_ign, m[j], S, S_old, S_fg, e0, x0[j], xy, seen, have_seen, zfoc, acc,
                   pc, gfoc, dm);
-      mbits |= (uint32_t)dm << (8 * (j & 3)) << 0;
-      if ((j & 3) == 3 || j == N - 1) {
+      mbits |= (uint32_t)dm << (8 * (j & 3));
+      if (N == 2) {
+        if (j == 1 && a.distill_mask) *reinterpret_cast<uint16_t*>(a.distill_mask + pix0) = (uint16_t)mbits;
+      } else if ((j & 3) == 3) {
         if (a.distill_mask) *reinterpret_cast<uint32_t*>(a.distill_mask + pix0 + (j & ~3)) = mbits;
         mbits = 0;
       }
