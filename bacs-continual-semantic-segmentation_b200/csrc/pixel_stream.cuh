@@ -23,6 +23,7 @@ struct alignas(16) StreamParams {
   float* coef;        // [6][B*H*W]: nm = -max*log2e, cg0, cg1, cg2, d0, dy   (nullptr: no gradient pass)
   double* partials;   // [B * blocks_x][BACS_NACC]
   int blocks_x;       // blocks per image
+  int b0;             // first image of this launch
   float inv_n, sy, sx;
 };
 
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(kStreamThreads, 3) pixel_stream_stats_kernel(c
   __shared__ float s_norm_sh;
   const bacs_pixel_args& a = p.a;
   const int K = a.K, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int b = blockIdx.y;
+  const int b = p.b0 + (int)blockIdx.y;
   const int64_t HW = (int64_t)a.H * a.W, NPIX = HW * a.B;
   const int old_cl = min(max(a.old_cl, 0), K);
   const bool have_seen = (a.z != nullptr) || (a.seen_max != nullptr);
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) pixel_stream_grad_kernel(co
   constexpr int N = StreamVec<T>::N, CH = kStreamChunk;
   const bacs_pixel_args& a = p.a;
   const int K = a.K, tid = threadIdx.x;
-  const int b = blockIdx.y;
+  const int b = p.b0 + (int)blockIdx.y;
   const int64_t HW = (int64_t)a.H * a.W, NPIX = HW * a.B;
   const int old_cl = min(max(a.old_cl, 0), K);
   const T* img = reinterpret_cast<const T*>(a.logits) + (int64_t)b * K * HW;
