@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(kStreamThreads, 3) pixel_stream_stats_kernel(c
     using R = Raw<T>;
     using reg_t = typename R::reg_t;
     static_assert(sizeof(reg_t) * W == sizeof(vec_t), "a vector is W packed pixel pairs");
-    float m[N], so[N], sn[N], x0[N], nr[N];  // nr = -reference * log2e
+    float m[N], so[N], sn[N], x0[N];
+    F2 so2[W], sn2[W], nr2[W];  // packed pixel pairs: exponent sums, nr = -reference * log2e
     int am[N];
     typename R::Max mt[W];
     {
@@ -143,19 +144,20 @@ __global__ void __launch_bounds__(kStreamThreads, 3) pixel_stream_stats_kernel(c
       }
     }
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      nr[j] = -x0[j] * kLog2e;
-      so[j] = sn[j] = 0.f;
+    for (int w = 0; w < W; ++w) {
+      nr2[w] = f2(-x0[2 * w] * kLog2e, -x0[2 * w + 1] * kLog2e);
+      so2[w] = sn2[w] = f2b(0.f);
     }
-    auto one_channel = [&](const vec_t& r4, int c, float* sum) {
+    const F2 l2e2 = f2b(kLog2e);
+    auto one_channel = [&](const vec_t& r4, int c, F2* sum) {
       const reg_t* rw = reinterpret_cast<const reg_t*>(&r4);
 #pragma unroll
       for (int w = 0; w < W; ++w) {
         R::update(mt[w], rw[w], c);
         float v0, v1;
         R::unpack(rw[w], v0, v1);
-        sum[2 * w] += ex2_fast(fmaf(v0, kLog2e, nr[2 * w]));
-        sum[2 * w + 1] += ex2_fast(fmaf(v1, kLog2e, nr[2 * w + 1]));
+        const F2 arg = fma2(f2(v0, v1), l2e2, nr2[w]);
+        sum[w] = add2(sum[w], f2(ex2_fast(f2lo(arg)), ex2_fast(f2hi(arg))));
       }
     };
     auto lift_reference = [&]() {
@@ -164,21 +166,17 @@ __global__ void __launch_bounds__(kStreamThreads, 3) pixel_stream_stats_kernel(c
         float m0, m1;
         int a0, a1;
         R::finish(mt[w], m0, m1, a0, a1);
-        const float mm[2] = {m0, m1};
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int j = 2 * w + q;
-          const float ahead = fmaf(mm[q], kLog2e, nr[j]);  // (max - reference) * log2e
-          if (ahead > 32.f * kLog2e) {
-            const float f = ex2_fast(-ahead);
-            so[j] *= f;
-            sn[j] *= f;
-            nr[j] = -mm[q] * kLog2e;
-          }
+        const float a0h = fmaf(m0, kLog2e, f2lo(nr2[w])), a1h = fmaf(m1, kLog2e, f2hi(nr2[w]));  // (max - ref) * log2e
+        const bool l0 = a0h > 32.f * kLog2e, l1 = a1h > 32.f * kLog2e;
+        if (l0 || l1) {
+          const F2 f = f2(l0 ? ex2_fast(-a0h) : 1.f, l1 ? ex2_fast(-a1h) : 1.f);
+          so2[w] = mul2(so2[w], f);
+          sn2[w] = mul2(sn2[w], f);
+          nr2[w] = f2(l0 ? -m0 * kLog2e : f2lo(nr2[w]), l1 ? -m1 * kLog2e : f2hi(nr2[w]));
         }
       }
     };
-    auto range = [&](int cbeg, int cend, float* sum) {
+    auto range = [&](int cbeg, int cend, F2* sum) {
       int c = cbeg;
       for (; c + 2 * CH <= cend; c += 2 * CH) {  // 8 independent 16-byte loads in flight per thread
         vec_t raw[2 * CH];
@@ -196,8 +194,8 @@ __global__ void __launch_bounds__(kStreamThreads, 3) pixel_stream_stats_kernel(c
     };
     // (a logit more than 32 above the reference inside one block of 8 channels still cannot overflow: 2^(1.44*(32+d))
     //  needs d > 56 on top, i.e. logits jumping by ~90 between neighbouring channels)
-    range(1, old_cl, so);
-    range(max(old_cl, 1), K, sn);
+    range(1, old_cl, so2);
+    range(max(old_cl, 1), K, sn2);
 #pragma unroll
     for (int w = 0; w < W; ++w) {
       int a0, a1;
@@ -207,9 +205,10 @@ __global__ void __launch_bounds__(kStreamThreads, 3) pixel_stream_stats_kernel(c
     }
 #pragma unroll
     for (int j = 0; j < N; ++j) {  // sums against the reference -> sums against the max
-      const float f = ex2_fast(-fmaf(m[j], kLog2e, nr[j]));
-      so[j] *= f;
-      sn[j] *= f;
+      const float nrj = (j & 1) ? f2hi(nr2[j >> 1]) : f2lo(nr2[j >> 1]);
+      const float f = ex2_fast(-fmaf(m[j], kLog2e, nrj));
+      so[j] = f * ((j & 1) ? f2hi(so2[j >> 1]) : f2lo(so2[j >> 1]));
+      sn[j] = f * ((j & 1) ? f2hi(sn2[j >> 1]) : f2lo(sn2[j >> 1]));
     }
     // ---- per-pixel terms ----------------------------------------------------------------------------------------------
     const int64_t pix0 = (int64_t)b * HW + p0;
