@@ -149,11 +149,18 @@ __global__ void __launch_bounds__(kStreamThreads, 3) pixel_stream_stats_kernel(c
       so2[w] = sn2[w] = f2b(0.f);
     }
     const F2 l2e2 = f2b(kLog2e);
-    auto one_channel = [&](const vec_t& r4, int c, F2* sum) {
+    // a block of channels is first folded into the running max, then the reference is lifted if the max has run ahead,
+    // and only then are the exponents taken: no logit of the block is more than 32 above the reference (no overflow,
+    // whatever the jumps between neighbouring channels)
+    auto track = [&](const vec_t& r4, int c) {
+      const reg_t* rw = reinterpret_cast<const reg_t*>(&r4);
+#pragma unroll
+      for (int w = 0; w < W; ++w) R::update(mt[w], rw[w], c);
+    };
+    auto accumulate = [&](const vec_t& r4, F2* sum) {
       const reg_t* rw = reinterpret_cast<const reg_t*>(&r4);
 #pragma unroll
       for (int w = 0; w < W; ++w) {
-        R::update(mt[w], rw[w], c);
         float v0, v1;
         R::unpack(rw[w], v0, v1);
         const F2 arg = fma2(f2(v0, v1), l2e2, nr2[w]);
@@ -183,17 +190,18 @@ __global__ void __launch_bounds__(kStreamThreads, 3) pixel_stream_stats_kernel(c
 #pragma unroll
         for (int i = 0; i < 2 * CH; ++i) raw[i] = __ldg(reinterpret_cast<const vec_t*>(base + (int64_t)(c + i) * HW));
 #pragma unroll
-        for (int i = 0; i < 2 * CH; ++i) one_channel(raw[i], c + i, sum);
+        for (int i = 0; i < 2 * CH; ++i) track(raw[i], c + i);
         lift_reference();
+#pragma unroll
+        for (int i = 0; i < 2 * CH; ++i) accumulate(raw[i], sum);
       }
       for (; c < cend; ++c) {
         const vec_t r4 = __ldg(reinterpret_cast<const vec_t*>(base + (int64_t)c * HW));
-        one_channel(r4, c, sum);
+        track(r4, c);
+        lift_reference();
+        accumulate(r4, sum);
       }
-      lift_reference();
     };
-    // (a logit more than 32 above the reference inside one block of 8 channels still cannot overflow: 2^(1.44*(32+d))
-    //  needs d > 56 on top, i.e. logits jumping by ~90 between neighbouring channels)
     range(1, old_cl, so2);
     range(max(old_cl, 1), K, sn2);
 #pragma unroll

@@ -655,3 +655,53 @@ def test_class_distance_tensor_cores(ops, B, D, h, w, Kc):
     assert int((diff & ((top2[:, 1] - top2[:, 0]) > 2e-5 * float(want.max()))).sum()) == 0
     d2, none = ops.class_distance(f.cuda(), c.cuda(), want_nearest=False)
     assert none is None and torch.equal(d2, got)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pixel_modes_on_the_streaming_path(ops, dtype):
+    """K >= 64 takes the two streaming passes (variant 4): plain / class-weighted CE, unbiased CE and the per-image score"""
+    from bacs_b200 import _cabi
+    B, K, H, W, old_cl = 3, 70, 16, 64, 41
+    g = torch.Generator().manual_seed(70)
+    x0 = (torch.randn(B, K, H, W, generator=g) * 3).to(dtype)
+    y = torch.randint(0, K, (B, H, W), generator=g)
+    y[torch.rand(B, H, W, generator=g) < 0.15] = 255
+    y[1, 3, 5:9] = K + 7                                   # invalid, not ignore
+    clean = torch.where((y >= K) & (y != 255), torch.full_like(y, 255), y)
+    w = torch.rand(K, generator=g)
+    tol = 1e-5 if dtype == torch.float32 else 2.0 ** -7
+    for weight in (None, w):
+        x = x0.float().clone().requires_grad_(True)
+        want = O.cross_entropy(x, clean, weight)
+        want.backward()
+        out = ops.pixel_loss(x0.cuda(), y.cuda(), _cabi.PIX_CE, want_grad=True,
+                             class_w=None if weight is None else weight.cuda())
+        assert out["variant"] == 4
+        acc = out["acc"]
+        close(acc[_cabi.ACC_LOSS] / acc[_cabi.ACC_WSUM], want, what="ce")
+        wg = x.grad.to(dtype).float()
+        close(out["dlogits"].float(), wg, atol=tol * float(wg.abs().max()), what="ce grad")
+        assert torch.equal(out["preds"].cpu(), O.argmax_first(x0.float()))
+        assert int(acc[_cabi.ACC_INVALID]) == 4
+    x = x0.float().clone().requires_grad_(True)
+    want = O.unbiased_ce(x, clean, old_cl)
+    want.backward()
+    out = ops.pixel_loss(x0.cuda(), y.cuda(), _cabi.PIX_UNBIASED_CE, want_grad=True, old_cl=old_cl)
+    close(out["acc"][_cabi.ACC_LOSS] / out["acc"][_cabi.ACC_WSUM], want, what="uce")
+    wg = x.grad.to(dtype).float()
+    close(out["dlogits"].float(), wg, atol=tol * float(wg.abs().max()), what="uce grad")
+    w2 = torch.ones(K)
+    w2[0] = 0
+    out = ops.pixel_loss(x0.cuda(), y.cuda(), _cabi.PIX_SCORE, want_grad=False, class_w=w2.cuda(), want_score=True,
+                         want_preds=False)
+    assert out["variant"] == 4
+    close(out["score"], O.cross_entropy_per_image_score(x0.float(), clean, w2), what="score")
+    # confident logits: the exponent reference is lifted when the running max runs ahead (|x| up to ~60)
+    xb = (x0.float() * 6).to(dtype)
+    x = xb.float().clone().requires_grad_(True)
+    want = O.cross_entropy(x, clean, None)
+    want.backward()
+    out = ops.pixel_loss(xb.cuda(), y.cuda(), _cabi.PIX_CE, want_grad=True)
+    close(out["acc"][_cabi.ACC_LOSS] / out["acc"][_cabi.ACC_WSUM], want, rtol=2e-5, what="ce (large logits)")
+    wg = x.grad.to(dtype).float()
+    close(out["dlogits"].float(), wg, atol=tol * float(wg.abs().max()), what="ce grad (large logits)")
