@@ -224,3 +224,29 @@ def test_full_step_with_fused_logit_upsample(synth, name, dtype):
     assert leaves["logits"].grad is None          # the full-resolution logits were never touched
     t = cfg.T - 1
     close(leaves["head_w"].grad.reshape(-1), hw.grad[t], atol=3e-5 * float(hw.grad[t].abs().max()), what="dhead_w")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_lowres_confident_logits(ops, synth, dtype):
+    """|logit| up to ~80 (far beyond random init): finite, and loss / gradient still match the oracle"""
+    from bacs_b200 import _cabi
+    cfg = synth.CONFIGS["row512"]
+    inp = synth.make_step_inputs(cfg, seed=9, dtype=torch.float32)
+    g = torch.Generator().manual_seed(5)
+    mask = synth.make_labels(cfg, g, classes=list(range(1, cfg.K)))
+    z = _seen_z(inp)
+    smax = torch.sigmoid(O.bilinear_upsample(z, (cfg.H, cfg.W), True)).max(1)[0]
+    sem = _sem(cfg, 16, 13, dtype, 20.0)
+    x = sem.float().clone().requires_grad_(True)
+    up = O.upsample_sem_logits(x, (cfg.H, cfg.W))
+    want = O.weighted_ce(up, mask, smax, cfg.old_cl, 2.0, 0.5, True)
+    want.backward()
+    out = ops.pixel_loss(sem.cuda(), mask.cuda(), _cabi.PIX_WEIGHTED_CE, want_grad=True, z=z.cuda(),
+                         want_distill_mask=True, old_cl=cfg.old_cl, ukd=True, lowres=True)
+    assert bool(torch.isfinite(out["acc"]).all()) and bool(torch.isfinite(out["dlogits"].float()).all())
+    N = cfg.B * cfg.H * cfg.W
+    close(out["acc"][_cabi.ACC_LOSS] / N, want, rtol=2e-5, what="loss")
+    want_g = x.grad.to(dtype).float()
+    tol = 3e-5 if dtype == torch.float32 else 2.0 ** -7
+    close(out["dlogits"].float(), want_g, atol=tol * float(want_g.abs().max()), what="d sem_logits")
+    _check_preds(out["preds"], up.detach())
