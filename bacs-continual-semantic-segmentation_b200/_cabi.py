@@ -71,6 +71,7 @@ _SIGNATURES = {
     "bacs_scale_inplace_multi": (i32, [i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(i64), vp, vp]),
     "bacs_peer_allreduce": (i32, [vp, i32, i32, i32, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), vp, vp, vp, vp, i32,
                                   i32, i32, vp, vp]),
+    "bacs_peer_set_timeout_ms": (i32, [i64]),
     "bacs_pack_state": (i32, [vp, vp, i32, i32, vp, i32, vp, vp]),
     "bacs_unpack_state": (i32, [vp, i32, i32, vp, vp, vp, i32, vp]),
     "bacs_combine_scalars": (i32, [i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(vp), C.POINTER(i32),

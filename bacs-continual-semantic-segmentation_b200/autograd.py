@@ -16,6 +16,21 @@ import torch
 from . import _cabi, ops
 
 
+_TWICE = ("bacs_b200: backward through this loss a second time: the gradient was computed in the forward launch and "
+          "is scaled in place by the first backward; call the loss again instead of retain_graph=True")
+
+
+def _take(ctx, name):
+    """The gradient stored by forward, exactly once (torch raises for a second backward through a freed graph; a
+    retained graph must not silently hand out None gradients)."""
+    if getattr(ctx, "_consumed", False):
+        raise RuntimeError(_TWICE)
+    ctx._consumed = True
+    value = getattr(ctx, name)
+    setattr(ctx, name, None)
+    return value
+
+
 def _scaled(grad: Optional[torch.Tensor], g: torch.Tensor) -> Optional[torch.Tensor]:
     if grad is None:
         return None
@@ -92,6 +107,9 @@ class PixelLossFunction(torch.autograd.Function):
             want_df = bool(cfg.get("features_grad", False)) and ctx.needs_input_grad[1]
             proto_t = cfg["proto"][focal_head]
             hw_flat = head_weight.detach().reshape(-1).float().contiguous()
+            # everything the side-stream kernel reads must exist BEFORE the fork event and stay alive until the join:
+            # a channels_last / sliced feature map is made contiguous here, on the main stream
+            features = features.contiguous()
             if OVERLAP_HEAD_BACKWARD and cfg.get("overlap", True):
                 # launched on the side stream by handle (no current-stream switch: that costs ~30 us of CPU); the
                 # outputs live in the current stream's pool and are only touched there after the join
@@ -118,8 +136,7 @@ class PixelLossFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, _gp, _gm):
-        dlogits, dfeat, dweight, dbias = ctx.grads
-        ctx.grads = None
+        dlogits, dfeat, dweight, dbias = _take(ctx, "grads")
         join_side_stream()
         if g is None:
             return None, None, None, None, None, None
@@ -146,7 +163,7 @@ class TeacherDistillFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        dnew, ctx.dnew = ctx.dnew, None
+        dnew = _take(ctx, "dnew")
         return _scaled(dnew, g), None, None, None, None
 
 
@@ -164,7 +181,7 @@ class DerMseFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        dsem, ctx.dsem = ctx.dsem, None
+        dsem = _take(ctx, "dsem")
         return _scaled(dsem, g), None, None, None, None, None
 
 
@@ -181,5 +198,5 @@ class UnbiasedKDFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        dx, ctx.dx = ctx.dx, None
+        dx = _take(ctx, "dx")
         return _scaled(dx, g), None, None, None

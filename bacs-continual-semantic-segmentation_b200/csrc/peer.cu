@@ -6,9 +6,13 @@
 // (loss/prototypes.py:158-163) in the same launch:
 //   1. copy my packed fp64 state into my slot of the symmetric buffer (double-buffered by step parity),
 //   2. publish: fence.sys + release-store of the step number into every peer's flag row,
-//   3. wait until every peer's flag for me shows this step (acquire loads, bounded spin),
+//   3. wait until every peer's flag for me shows this step (acquire loads; the spin is bounded in wall-clock time
+//      (bacs_peer_set_timeout_ms, default 30 s) so a missing rank can never hang the GPU for good),
 //   4. sum the W peer buffers in RANK ORDER (bit-identical result on every rank), write it back to `packed`,
 //   5. (optional) proto[g] = (S[g] + cnt[g] proto[g]) / (cnt[g] + N[g]), cnt[g] += N[g]; ready flag.
+// On a time-out NOTHING is combined: `packed`, the prototypes and the counts keep their values, the sticky error
+// word receives the step number and the ready flag is cleared; the host raises at its next check
+// (distributed.PeerReducer.check).  A rank never applies a sum that may contain a stale or half-written peer slot.
 // A peer can only be one step ahead (it needs my flag of step e+1 to finish step e+1), and it then writes the
 // OTHER parity slot, so reads of step e never race with writes of step e+1.
 #include "common.cuh"
@@ -35,7 +39,16 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
   return v;
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+static unsigned long long g_peer_timeout_ns = 30ull * 1000ull * 1000ull * 1000ull;
+
 __global__ void __launch_bounds__(1024) peer_allreduce_update_kernel(PeerPtrs pp, int rank, int world, int n, int n_max,
+                                                                     unsigned long long timeout_ns,
                                                                      double* __restrict__ packed,
                                                                      unsigned int* __restrict__ step_dev,
                                                                      int* __restrict__ error_dev,
@@ -55,24 +68,29 @@ __global__ void __launch_bounds__(1024) peer_allreduce_update_kernel(PeerPtrs pp
     st_release_sys(pp.flag[threadIdx.x] + rank, step);  // tell peer threadIdx.x that my slot is filled
     // wait for that peer's slot (bounded: a missing peer must not hang the GPU)
     const unsigned int* f = pp.flag[rank] + threadIdx.x;
-    const long long t0 = clock64();
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int polls = 0;
     while ((int)(ld_acquire_sys(f) - step) < 0) {
-      if (clock64() - t0 > 4000000000LL) {  // ~2 s
+      if ((++polls & 1023u) == 0 && global_timer_ns() - t0 > timeout_ns) {
         s_timeout = 1;
         break;
       }
     }
   }
   __syncthreads();
-  if (s_timeout) {
-    if (threadIdx.x == 0 && error_dev) *error_dev = 1;
+  if (threadIdx.x == 0) *step_dev = step;  // the step counter advances either way (flags stay monotonic)
+  if (s_timeout) {  // uniform: leave every output untouched, report, and let the host raise
+    if (threadIdx.x == 0) {
+      if (error_dev) *error_dev = (int)step;
+      if (ready) *ready = 0;
+    }
+    return;
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     double s = 0.0;
     for (int r = 0; r < world; ++r) s += ld_relaxed_sys_f64(pp.buf[r] + (size_t)slot * n_max + i);
     packed[i] = s;
   }
-  if (threadIdx.x == 0) *step_dev = step;
   if (proto == nullptr) return;
   __syncthreads();  // packed[] (global, this block) is complete
   // ---- fused running-mean update (same arithmetic as proto_update_kernel) ----
@@ -127,6 +145,12 @@ using namespace bacs;
 
 extern "C" {
 
+int bacs_peer_set_timeout_ms(int64_t ms) {
+  BACS_REQUIRE(ms > 0, "bacs_peer_set_timeout_ms: the time-out must be positive");
+  g_peer_timeout_ns = (unsigned long long)ms * 1000000ull;
+  return BACS_OK;
+}
+
 int bacs_peer_allreduce(double* packed, int n, int n_max, int rank, int world, const uint64_t* peer_buf_host,
                         const uint64_t* peer_flag_host, uint32_t* step_dev, int32_t* error_dev, float* proto,
                         void* count, int count_is_int64, int T, int D, int32_t* ready, bacs_stream_t stream) {
@@ -139,7 +163,7 @@ int bacs_peer_allreduce(double* packed, int n, int n_max, int rank, int world, c
     pp.buf[r] = r < world ? reinterpret_cast<double*>(peer_buf_host[r]) : nullptr;
     pp.flag[r] = r < world ? reinterpret_cast<unsigned int*>(peer_flag_host[r]) : nullptr;
   }
-  peer_allreduce_update_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pp, rank, world, n, n_max, packed, step_dev, error_dev,
+  peer_allreduce_update_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pp, rank, world, n, n_max, g_peer_timeout_ns, packed, step_dev, error_dev,
                                                                     proto, count, count_is_int64, T, D, ready);
   BACS_CHECK_LAUNCH("bacs_peer_allreduce");
   return BACS_OK;

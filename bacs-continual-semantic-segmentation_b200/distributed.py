@@ -68,6 +68,11 @@ class PeerReducer:
         self.error = torch.zeros(1, dtype=torch.int32, device=device)
         dist.barrier(group)                # every rank has zeroed its flags before anybody publishes
         torch.cuda.synchronize(device)
+        import os
+        from . import _cabi
+        ms = os.environ.get("BACS_PEER_TIMEOUT_MS")
+        if ms:
+            _cabi.check(_cabi.load().bacs_peer_set_timeout_ms(int(ms)), "bacs_peer_set_timeout_ms")
 
     @classmethod
     def create(cls, n_max: int, device: torch.device, group=None) -> "Optional[PeerReducer]":
@@ -80,6 +85,18 @@ class PeerReducer:
             import warnings
             warnings.warn("bacs_b200: peer-memory all-reduce unavailable (%r); using the NCCL all-reduce" % (exc,))
             return None
+
+    def check(self) -> None:
+        """Host synchronisation point: raises when any exchange since the last check timed out (the kernel then left
+        prototypes / counts untouched on THIS rank while the peers may have advanced, so the run cannot continue).
+        Called by Prototypes at the end of an epoch / task and by bench.py's N > 1 verification step."""
+        step = int(self.error.item())
+        if step != 0:
+            self.error.zero_()
+            raise RuntimeError(
+                "bacs_b200: NVLink peer all-reduce timed out on rank %d at exchange %d (a peer did not publish its "
+                "state within the time-out, see bacs_peer_set_timeout_ms / BACS_PEER_TIMEOUT_MS); prototypes are no "
+                "longer identical across ranks" % (self.rank, step))
 
     def allreduce(self, packed: torch.Tensor, proto: Optional[torch.Tensor] = None,
                   count: Optional[torch.Tensor] = None, T: int = 0, D: int = 0) -> Optional[torch.Tensor]:
@@ -112,6 +129,13 @@ def peer_reducer(n: int, device: torch.device) -> "Optional[PeerReducer]":
         _peer_reducers[key] = PeerReducer.create(max(int(n), 64 * 2048 + 64), device)
     red = _peer_reducers[key]
     return red if (red is not None and n <= red.n_max) else None
+
+
+def check_peer_errors() -> None:
+    """Raise if any peer exchange of this process timed out (no-op without a peer reducer)."""
+    for red in _peer_reducers.values():
+        if red is not None:
+            red.check()
 
 
 def allreduce_state(sums: Optional[torch.Tensor], counts: Optional[torch.Tensor],

@@ -10,6 +10,7 @@ What differs under the hood (results are the reference's):
 from __future__ import annotations
 
 import math
+import weakref
 from typing import Optional
 
 import numpy as np
@@ -70,7 +71,7 @@ class BaseLoss:
         self.fused_logit_upsample = False
         # fused-kernel by-products of the last compute_base_loss call
         self._fused_preds = None
-        self._fused_logits_id = None
+        self._fused_logits_ref = None
         self._fused_distill_mask = None
 
     # ---- configuration ------------------------------------------------------------------
@@ -139,12 +140,23 @@ class BaseLoss:
         pass
 
     def on_train_end(self, **kwargs):
+        self._check_cross_rank_state()
         if self._prototypes is not None:
             self._prototypes.on_train_end(**kwargs)
 
     def on_train_batch_start(self, **kwargs):
+        if kwargs.get("batch_idx") == 0 and self.epoch_number is not None and kwargs.get("epoch") != self.epoch_number:
+            self._check_cross_rank_state()                 # once per epoch: a cheap host read of one device word
         self.epoch_number = kwargs.get("epoch")
         self.max_epochs = kwargs.get("max_epochs")
+
+    @staticmethod
+    def _check_cross_rank_state():
+        """Surface a timed-out NVLink prototype exchange (distributed.PeerReducer) as a Python exception at the
+        host synchronisation points of the loop (epoch start, end of task).  No-op in single-process runs."""
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            from ..distributed import check_peer_errors
+            check_peer_errors()
 
     # ---- the hot path -------------------------------------------------------------------------
     @staticmethod
@@ -230,7 +242,10 @@ class BaseLoss:
         if not train:
             cfg["want_grad"] = False
         loss, preds, dmask = PixelLossFunction.apply(preds_mask, features, head_w, head_b, mask, cfg)
-        self._fused_preds, self._fused_logits_id = preds, id(preds_mask)
+        # the arg-max belongs to THIS logits tensor: remember the object itself (weakly) and its version, never id()
+        # (CPython reuses the id of a freed tensor, e.g. the replay pass's logits)
+        self._fused_preds = preds
+        self._fused_logits_ref = (weakref.ref(preds_mask), preds_mask._version, preds_mask.data_ptr())
         dmask = dmask if dmask.numel() else None
         self._fused_distill_mask = dmask
         if wce_on:
@@ -241,7 +256,9 @@ class BaseLoss:
 
     def _argmax(self, preds_mask):
         """arg-max of the logits; free when the fused kernel already produced it (bacs_loss.py:255)."""
-        if self._fused_preds is not None and self._fused_logits_id == id(preds_mask):
+        ref = getattr(self, "_fused_logits_ref", None)
+        if (self._fused_preds is not None and ref is not None and ref[0]() is preds_mask
+                and ref[1] == preds_mask._version and ref[2] == preds_mask.data_ptr()):
             return self._fused_preds
         out = ops.pixel_loss(preds_mask.detach(), torch.zeros(preds_mask.shape[0], *preds_mask.shape[2:],
                                                               dtype=torch.int64, device=preds_mask.device),

@@ -346,13 +346,19 @@ int bacs_combine_scalars(int n, const double* const* src_host, const int* idx_ho
  *   peer_flag_host[r] : device address of rank r's flag row of >= 16 zero-initialised uint32
  *   step_dev          : device uint32 step counter of this rank (0 at start; the kernel increments it, so
  *                       the call can be replayed from a CUDA graph)
- *   error_dev         : set to 1 when a peer did not show up within ~2 s (the kernel never hangs), or NULL
+ *   error_dev         : sticky device int32 (or NULL): receives the step number when a peer did not show up
+ *                       within the time-out (bacs_peer_set_timeout_ms, default 30 s; the kernel never hangs).
+ *                       On a time-out NOTHING is combined: packed, proto, count are left untouched and
+ *                       *ready = 0 -- the caller must check error_dev at its next synchronisation point and fail.
  * Every rank must make the same sequence of calls.  packed is summed in rank order: all ranks obtain
  * bit-identical results. */
 int bacs_peer_allreduce(double* packed, int n, int n_max, int rank, int world,
                         const uint64_t* peer_buf_host, const uint64_t* peer_flag_host, uint32_t* step_dev,
                         int32_t* error_dev, float* proto, void* count, int count_is_int64, int T, int D,
                         int32_t* ready, bacs_stream_t stream);
+
+/* Wall-clock bound (milliseconds, > 0) of the peer wait of bacs_peer_allreduce; process-wide. */
+int bacs_peer_set_timeout_ms(int64_t ms);
 
 /* Pack / unpack the per-step cross-rank state into ONE fp64 buffer for a single
  * all-reduce: [T*D prototype sums | T counts | K*K confusion matrix (optional)]. */
