@@ -57,6 +57,8 @@ _SIGNATURES = {
     "bacs_pixel_loss_lowres": (i32, [C.POINTER(PixelArgs), i32, i32, vp, sz, vp]),
     "bacs_distill_workspace_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
     "bacs_teacher_distill": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, f32, vp, vp, vp, vp, sz, vp]),
+    "bacs_distill_set_mode": (i32, [i32]),
+    "bacs_distill_kernel_variant": (i32, [i32, i32, i32, i32, i32, i32, i32]),
     "bacs_der_workspace_bytes": (sz, [i32, i32, i32]),
     "bacs_der_mse": (i32, [vp, i32, vp, i32, i32, vp, i32, i32, i32, i32, f32, vp, vp, vp, sz, vp]),
     "bacs_unbiased_kd_workspace_bytes": (sz, [i64]),

@@ -614,6 +614,14 @@ static DistillLayout distill_layout(int B, int A, int h, int w, int H, int W) {
   return l;
 }
 
+// tensor-core path (distill_tc.cu)
+bool distill_tc_shape_ok(int dtype, int B, int A, int h, int w, int H, int W);
+size_t distill_tc_workspace_bytes(int dtype, int B, int A, int h, int w, int H, int W);
+int distill_tc_launch(const void* old_att, const void* new_att, int dtype, int B, int A, int h, int w, const uint8_t* mask, int H,
+                      int W, float grad_coef, double* loss_sum, float* loss_scaled, void* dnew, void* workspace,
+                      size_t workspace_bytes, cudaStream_t s);
+static int g_distill_mode = 0;  // 0: tensor cores where they apply, 1: FMA kernel only, 2: tensor cores or error
+
 }  // namespace bacs
 
 using namespace bacs;
@@ -622,7 +630,21 @@ extern "C" {
 
 size_t bacs_distill_workspace_bytes(int B, int A, int h, int w, int H, int W) {
   if (B <= 0 || A <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return 0;
-  return distill_layout(B, A, h, w, H, W).total;
+  size_t need = distill_layout(B, A, h, w, H, W).total;
+  // the tensor-core path keeps boundary rows and loss partials per CTA; sized for the widest storage type
+  need = std::max(need, distill_tc_workspace_bytes(BACS_F32, B, A, h, w, H, W));
+  need = std::max(need, distill_tc_workspace_bytes(BACS_BF16, B, A, h, w, H, W));
+  return need;
+}
+
+int bacs_distill_set_mode(int mode) {
+  BACS_REQUIRE(mode >= 0 && mode <= 2, "bacs_distill_set_mode: mode must be 0 (auto), 1 (FMA kernel) or 2 (tensor cores)");
+  g_distill_mode = mode;
+  return BACS_OK;
+}
+
+int bacs_distill_kernel_variant(int dtype, int B, int A, int h, int w, int H, int W) {
+  return (g_distill_mode != 1 && distill_tc_shape_ok(dtype, B, A, h, w, H, W)) ? 1 : 0;
 }
 
 int bacs_teacher_distill(const void* old_att, const void* new_att, int dtype, int B, int A, int h, int w,
@@ -631,6 +653,15 @@ int bacs_teacher_distill(const void* old_att, const void* new_att, int dtype, in
   BACS_REQUIRE(old_att && new_att && loss_sum && workspace, "bacs_teacher_distill: null pointer");
   BACS_REQUIRE(B > 0 && B < 65536 && A > 0 && h > 0 && w > 0, "bacs_teacher_distill: bad shape");
   BACS_REQUIRE(H >= h && W >= w, "bacs_teacher_distill: the mask must be at least as large as the attention map");
+  if (g_distill_mode != 1) {
+    const int rc = distill_tc_launch(old_att, new_att, dtype, B, A, h, w, mask, H, W, grad_coef, loss_sum, loss_scaled, dnew,
+                                     workspace, workspace_bytes, (cudaStream_t)stream);
+    if (rc <= 0) return rc;  // done, or a real error
+    if (g_distill_mode == 2) {
+      set_error("bacs_teacher_distill: the tensor-core path does not apply to this shape / alignment");
+      return BACS_ERR_UNSUPPORTED;
+    }
+  }
   if (w > 128) {
     set_error("bacs_teacher_distill: attention width %d > 128 not supported", w);
     return BACS_ERR_UNSUPPORTED;

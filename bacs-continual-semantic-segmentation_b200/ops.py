@@ -333,6 +333,17 @@ def teacher_distill(old_att: torch.Tensor, new_att: torch.Tensor, mask: Optional
     return loss_sum, dnew
 
 
+def distill_set_mode(mode: int) -> None:
+    """0: tensor-core kernel where it applies (default), 1: FMA kernel only, 2: tensor-core kernel or an error."""
+    check(_lib().bacs_distill_set_mode(int(mode)), "bacs_distill_set_mode")
+
+
+def distill_kernel_variant(att: torch.Tensor, out_hw) -> int:
+    """1 when bacs_teacher_distill serves this shape on the tensor cores, 0 for the packed-fp32 kernel."""
+    B, A, h, w = att.shape
+    return int(_lib().bacs_distill_kernel_variant(_dt(att), B, A, h, w, int(out_hw[0]), int(out_hw[1])))
+
+
 def der_transplant_cut(n_classes, K: int) -> np.ndarray:
     """Host restatement of the transplant index quirk (loss/bacs_loss.py:415-425): for i, n
     in enumerate(unique(n_classes)) the sample touched is inverse[i], not the samples whose

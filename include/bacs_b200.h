@@ -248,8 +248,15 @@ int bacs_pixel_loss_lowres(const bacs_pixel_args* args_host, int32_t lh, int32_t
  * loss_sum fp64[1] OVERWRITTEN with sum over rows of the row norms (caller scales by
  * lkd / (B*A*H)); loss_scaled fp32[1] OVERWRITTEN with grad_coef * that sum (the loss term itself when
  * grad_coef = lkd / (B*A*H)), or NULL; dnew (dtype, [B,A,h,w]) OVERWRITTEN with grad_coef * d(sum)/dnew, or NULL.
+ * Two kernels serve the call: the GEMM form on the 5th-generation tensor cores (csrc/distill_tc.cu: tcgen05.mma,
+ * TMEM operands, split-tf32; attention rows of 32 / 64 / 128 bytes, w <= 32, 16-byte aligned pointers) and the
+ * generic packed-fp32 kernel (csrc/distill.cu) for every other shape.  bacs_distill_kernel_variant tells which one
+ * a shape gets (1 = tensor cores, 0 = FMA kernel); bacs_distill_set_mode(0 auto | 1 FMA only | 2 tensor cores or
+ * BACS_ERR_UNSUPPORTED) is a process-wide switch for A/B measurements and tests.
  * --------------------------------------------------------------------------------- */
 size_t bacs_distill_workspace_bytes(int B, int A, int h, int w, int H, int W);
+int bacs_distill_set_mode(int mode);
+int bacs_distill_kernel_variant(int dtype, int B, int A, int h, int w, int H, int W);
 int bacs_teacher_distill(const void* old_att, const void* new_att, int dtype, int B, int A,
                          int h, int w, const uint8_t* mask, int H, int W, float grad_coef,
                          double* loss_sum, float* loss_scaled, void* dnew, void* workspace,
