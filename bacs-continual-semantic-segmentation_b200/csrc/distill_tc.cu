@@ -66,6 +66,7 @@ struct Params {
   int n_att;
   int want_grad;
   int box_chan;       // channels per TMA box: min(256, B*A)
+  int fast_mask;      // mask rows staged in shared memory by bulk copies + basis table (needs 16-byte aligned rows)
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -108,6 +109,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+#endif
+#ifdef BACS_DTC_PROFILE
+__device__ long long g_dtc_prof[160 * 3 * 16];
+#define PROF_DECL long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long prof_t0 = clock64(); (void)prof_t0
+#define PROF_WAIT(cat, bar, par) do { const long long t__ = clock64(); mbar_wait(bar, par); prof_acc[cat] += clock64() - t__; } while (0)
+#define PROF_MARK(cat) do { const long long t__ = clock64(); prof_acc[cat] += t__ - prof_t0; prof_t0 = t__; } while (0)
+#define PROF_DUMP(role) do { if ((threadIdx.x & 31) == 0) for (int k__ = 0; k__ < 16; ++k__) g_dtc_prof[(blockIdx.x * 3 + role) * 16 + k__] = prof_acc[k__]; } while (0)
+#else
+#define PROF_DECL
+#define PROF_WAIT(cat, bar, par) mbar_wait(bar, par)
+#define PROF_MARK(cat)
+#define PROF_DUMP(role)
 #endif
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -224,9 +237,9 @@ __device__ __forceinline__ void bern4(float t, float* o) {
 __host__ __device__ inline int mom_buffers(int w) { return w >= 24 ? 1 : 2; }
 struct SmemPlan {
   int att_off, att_slot_bytes;   // n_att slots x {old rows, new rows}: 256 rows of row_bytes each
-  int ring_off, carry_off, mom_off, yw_off, xw_off, rowstart_off, colstart_off, blkpfx_off, bar_off, total;
+  int ring_off, carry_off, mom_off, yw_off, xw_off, rowstart_off, colstart_off, blkpfx_off, bar_off, phi_off, mrow_off, total;
 };
-__host__ __device__ inline SmemPlan make_plan(int n_att, int row_bytes, int H, int W, int h, int w) {
+__host__ __device__ inline SmemPlan make_plan(int n_att, int fast_mask, int row_bytes, int H, int W, int h, int w) {
   SmemPlan s;
   int o = 0;
   s.att_off = o;
@@ -252,6 +265,10 @@ __host__ __device__ inline SmemPlan make_plan(int n_att, int row_bytes, int H, i
   o = (o + 15) & ~15;
   s.bar_off = o;
   o += 64 * 8;
+  s.phi_off = o;
+  if (fast_mask) o += 5 * W * 4;
+  s.mrow_off = o;
+  if (fast_mask) o += 2 * kRows * (W + 16);
   s.total = o;
   return s;
 }
@@ -268,7 +285,8 @@ enum {
   BAR_BFREE = 28,  // [slot]     MMAs that read the slot are done (commit)
   BAR_ATT = 36,    // [slot]     attention rows landed (TMA tx)
   BAR_ITEM = 40,   //            an item is finished by all 256 builder threads
-  BAR_COUNT = 41
+  BAR_MASK = 41,   // [2]        mask rows of a unit landed (bulk copy tx)
+  BAR_COUNT = 43
 };
 
 // attention-row slots: which slot holds the upper / lower source row of an item (same state machine on both sides)
@@ -392,6 +410,44 @@ struct RowIO<__nv_bfloat16> : RowIO16<__nv_bfloat16> {};
 template <>
 struct RowIO<__half> : RowIO16<__half> {};
 
+
+// Packed corner pairs of 8 consecutive cells straight from the swizzled row: L[m] = (c[2m], c[2m+1]), R[m] = (c[2m+1], c[2m+2]);
+// the column after the last one of the map is the last column itself.
+template <typename T>
+struct PairIO {
+  __device__ static __forceinline__ void load(const uint8_t* arr, int r, int j0, bool last, int rb, uint32_t swz, F2* L, F2* R) {
+    float c[9];
+    RowIO<T>::load8(arr, r, j0, rb, swz, c);
+    c[8] = last ? c[7] : RowIO<T>::load1(arr, r, j0 + 8, rb, swz);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      L[m] = f2(c[2 * m], c[2 * m + 1]);
+      R[m] = f2(c[2 * m + 1], c[2 * m + 2]);
+    }
+  }
+};
+template <>
+struct PairIO<__nv_bfloat16> {  // bf16 -> fp32 is a shift: both pair sets come from the packed words with no moves
+  __device__ static __forceinline__ void load(const uint8_t* arr, int r, int j0, bool last, int rb, uint32_t swz, F2* L, F2* R) {
+    const uint32_t off = (uint32_t)r * rb + (uint32_t)j0 * 2;
+    const uint4 a = *reinterpret_cast<const uint4*>(arr + (off ^ (((off >> 7) & swz) << 4)));
+    const uint32_t wv[4] = {a.x, a.y, a.z, a.w};
+    uint32_t nxt;
+    if (last) {
+      nxt = a.w >> 16;
+    } else {
+      const uint32_t o2 = off + 16;
+      nxt = *reinterpret_cast<const uint16_t*>(arr + (o2 ^ (((o2 >> 7) & swz) << 4)));
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const uint32_t right = m < 3 ? wv[m < 3 ? m + 1 : 3] << 16 : nxt << 16;
+      L[m] = pack32(wv[m] << 16, wv[m] & 0xffff0000u);
+      R[m] = pack32(wv[m] & 0xffff0000u, right);
+    }
+  }
+};
+
 // ================================================================== the kernel
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_constant__ CUtensorMap map_old,
@@ -404,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
   const int h = P.h, w = P.w, H = P.H, W = P.W;
   const int row_bytes = w * (int)sizeof(T);
   const uint32_t swz = row_bytes == 128 ? 7u : (row_bytes == 64 ? 3u : 1u);
-  const SmemPlan sp = make_plan(P.n_att, row_bytes, H, W, h, w);
+  const SmemPlan sp = make_plan(P.n_att, P.fast_mask, row_bytes, H, W, h, w);
   float* s_carry = reinterpret_cast<float*>(smem + sp.carry_off);
   float* s_mom = reinterpret_cast<float*>(smem + sp.mom_off);
   float* s_yw = reinterpret_cast<float*>(smem + sp.yw_off);
@@ -425,9 +481,21 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
     s_xw[X] = (l.i1 == l.i0) ? 0.f : l.w1;
     if (X == 0 || lerp_half_pixel(X - 1, w, P.sx).i0 != l.i0) s_colstart[l.i0] = X;
   }
+  if (P.fast_mask) {
+    float* phi = reinterpret_cast<float*>(smem + sp.phi_off);
+    for (int X = tid; X < W; X += kThreads) {
+      const Lerp l = lerp_half_pixel(X, w, P.sx);
+      float ph[5];
+      bern4((l.i1 == l.i0) ? 0.f : l.w1, ph);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) phi[k * W + X] = ph[k];
+    }
+  }
   if (tid == 0) {
     s_rowstart[h] = H;
     s_colstart[w] = W;
+    mbar_init(&bars[BAR_MASK], 1);
+    mbar_init(&bars[BAR_MASK + 1], 1);
     for (int k = 0; k < 2; ++k)
       for (int b = 0; b < 2; ++b) {
         mbar_init(&bars[BAR_VFULL + 2 * k + b], 128);
@@ -495,8 +563,9 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
     const uint32_t tm = tmem + ((uint32_t)((warp & 3) * 32) << 16) + wg * kColsWg;
     float* carry = s_carry + lrow * kCarryStride;
     float* scr = P.mb_scratch + ((size_t)blockIdx.x * 2 * kChanCta + lrow) * kMaxW;  // [0]: own, [+256*32]: low
-    uint32_t n_vchunk[2] = {0, 0}, n_wgrp[2] = {0, 0}, n_unit = 0, n_att_use[4] = {0, 0, 0, 0};
+    uint32_t n_unit = 0, n_att0 = 0, n_att1 = 0, n_att2 = 0;   // completed units; loads seen per attention slot
     float loss_f = 0.f;
+    PROF_DECL;
     const float gscale = -2.f * P.grad_coef;
     AttPlan ap{0, 0, -1, -1};
     for (int it = it0; it < it1; ++it) {
@@ -504,8 +573,13 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
       const int ch = cb * kChanCta + lrow;
       const bool active = ch < P.A;
       ap = att_next(ap, it == it0, i, h, P.n_att);
-      if (ap.newU >= 0) { mbar_wait(&bars[BAR_ATT + ap.newU], n_att_use[ap.newU] & 1); ++n_att_use[ap.newU]; }
-      if (ap.newW >= 0) { mbar_wait(&bars[BAR_ATT + ap.newW], n_att_use[ap.newW] & 1); ++n_att_use[ap.newW]; }
+      auto wait_att = [&](int slot) {
+        uint32_t& n = slot == 0 ? n_att0 : (slot == 1 ? n_att1 : n_att2);
+        PROF_WAIT(0, &bars[BAR_ATT + slot], n & 1);
+        ++n;
+      };
+      if (ap.newU >= 0) wait_att(ap.newU);
+      if (ap.newW >= 0) wait_att(ap.newW);
       const uint8_t* oU = smem + sp.att_off + ap.slotU * sp.att_slot_bytes;
       const uint8_t* nU = oU + kChanCta * row_bytes;
       const uint8_t* oW = smem + sp.att_off + ap.slotW * sp.att_slot_bytes;
@@ -516,31 +590,28 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
       if (i == 0 || boundary_start) {
         for (int j = 0; j < w; ++j) carry[j] = 0.f;
       }
-      // load 9 columns (8 cells + right neighbour) of the four source rows and form p, q (and n for the backward)
-      auto load_cols = [&](int j0, float* pU, float* qU, float* pW, float* qW, float* nUv, float* nWv) {
-        float a[9], c[9], d[9], e[9];
-        RowIO<T>::load8(oU, lrow, j0, row_bytes, swz, a);
-        RowIO<T>::load8(nU, lrow, j0, row_bytes, swz, c);
-        RowIO<T>::load8(oW, lrow, j0, row_bytes, swz, d);
-        RowIO<T>::load8(nW, lrow, j0, row_bytes, swz, e);
-        if (j0 + 8 < w) {
-          a[8] = RowIO<T>::load1(oU, lrow, j0 + 8, row_bytes, swz);
-          c[8] = RowIO<T>::load1(nU, lrow, j0 + 8, row_bytes, swz);
-          d[8] = RowIO<T>::load1(oW, lrow, j0 + 8, row_bytes, swz);
-          e[8] = RowIO<T>::load1(nW, lrow, j0 + 8, row_bytes, swz);
-        } else {  // the last column is its own right neighbour
-          a[8] = a[7]; c[8] = c[7]; d[8] = d[7]; e[8] = e[7];
-        }
+      // 8 cells + the right neighbour column of the four source rows as packed pairs: L[m] = (col 2m, col 2m+1) is the
+      // left corner of the cell pair (2m, 2m+1), R[m] = (col 2m+1, col 2m+2) its right corner; p = old - new, q = old + new
+      struct Corners { F2 p00[4], p01[4], p10[4], p11[4], q00[4], q01[4], q10[4], q11[4], n00[4], n01[4], n10[4], n11[4]; };
+      auto load_corners = [&](int j0, Corners& c, bool want_n) {
+        F2 oUL[4], oUR[4], nUL[4], nUR[4], oWL[4], oWR[4], nWL[4], nWR[4];
+        const bool last = j0 + 8 >= w;
+        PairIO<T>::load(oU, lrow, j0, last, row_bytes, swz, oUL, oUR);
+        PairIO<T>::load(nU, lrow, j0, last, row_bytes, swz, nUL, nUR);
+        PairIO<T>::load(oW, lrow, j0, last, row_bytes, swz, oWL, oWR);
+        PairIO<T>::load(nW, lrow, j0, last, row_bytes, swz, nWL, nWR);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          const float ov = active ? a[k] : 0.f, nv = active ? c[k] : 0.f, ow = active ? d[k] : 0.f, nw = active ? e[k] : 0.f;
-          pU[k] = ov - nv; qU[k] = ov + nv; pW[k] = ow - nw; qW[k] = ow + nw;
-          nUv[k] = nv; nWv[k] = nw;
+        for (int m = 0; m < 4; ++m) {
+          c.p00[m] = sub2(oUL[m], nUL[m]); c.q00[m] = add2(oUL[m], nUL[m]);
+          c.p01[m] = sub2(oUR[m], nUR[m]); c.q01[m] = add2(oUR[m], nUR[m]);
+          c.p10[m] = sub2(oWL[m], nWL[m]); c.q10[m] = add2(oWL[m], nWL[m]);
+          c.p11[m] = sub2(oWR[m], nWR[m]); c.q11[m] = add2(oWR[m], nWR[m]);
+          if (want_n) { c.n00[m] = nUL[m]; c.n01[m] = nUR[m]; c.n10[m] = nWL[m]; c.n11[m] = nWR[m]; }
         }
       };
-      auto make_E = [&](const float* pU, const float* qU, const float* pW, const float* qW, int a, F2* E) {
-        const F2 p00 = f2(pU[a], pU[a + 1]), p01 = f2(pU[a + 1], pU[a + 2]), p10 = f2(pW[a], pW[a + 1]), p11 = f2(pW[a + 1], pW[a + 2]);
-        const F2 q00 = f2(qU[a], qU[a + 1]), q01 = f2(qU[a + 1], qU[a + 2]), q10 = f2(qW[a], qW[a + 1]), q11 = f2(qW[a + 1], qW[a + 2]);
+      auto make_E = [&](const Corners& c, int m, F2* E) {
+        const F2 p00 = c.p00[m], p01 = c.p01[m], p10 = c.p10[m], p11 = c.p11[m];
+        const F2 q00 = c.q00[m], q01 = c.q01[m], q10 = c.q10[m], q11 = c.q11[m];
         E[0] = mul2(p00, q00);
         E[1] = fma2(p00, q01, mul2(p01, q00));
         E[2] = mul2(p01, q01);
@@ -555,18 +626,15 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
       for (int blk = 0; blk < nblk; ++blk) {
         // ------------------------------------------------ forward: V chunks -> tensor memory
         for (int j0 = 0; j0 < w; j0 += 8) {
-          float pU[9], qU[9], pW[9], qW[9], nUv[9], nWv[9];
-          load_cols(j0, pU, qU, pW, qW, nUv, nWv);
+          Corners cn;
+          load_corners(j0, cn, false);
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
             const int cidx = (j0 >> 1) + m, buf = cidx & 1;
             F2 E[9], E2[9];
-            make_E(pU, qU, pW, qW, 2 * m, E);
+            make_E(cn, m, E);
 #pragma unroll
             for (int k = 0; k < 9; ++k) E2[k] = add2(E[k], E[k]);
-            if (n_vchunk[buf] > 0) mbar_wait(&bars[BAR_VFREE + 2 * wg + buf], (n_vchunk[buf] - 1) & 1);
-            ++n_vchunk[buf];
-            TC_FENCE_AFTER();
             const uint32_t vb = tm + buf * kColVB;
             uint32_t hi[32], lo[32];
 #define BACS_V(e, Q, K)                         \
@@ -583,6 +651,14 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
             BACS_V(5, 1, 0) BACS_V(6, 1, 1) BACS_V(7, 1, 2) BACS_V(8, 1, 3) BACS_V(9, 1, 4)
             BACS_V(10, 2, 0) BACS_V(11, 2, 1) BACS_V(12, 2, 2) BACS_V(13, 2, 3) BACS_V(14, 2, 4)
             BACS_V(15, 3, 0)
+            {
+              // the buffer is free when the MMAs of the chunk two before this one are done; waiting HERE lets the 16
+              // coefficients above overlap the tensor core's turnaround.  Chunk number on this buffer since the kernel
+              // started: units * NCH/2 + cidx/2 (NCH is even)
+              const uint32_t nvc = n_unit * (uint32_t)(NCH >> 1) + (uint32_t)(cidx >> 1);
+              if (nvc > 0) PROF_WAIT(1, &bars[BAR_VFREE + 2 * wg + buf], (nvc - 1) & 1);
+              TC_FENCE_AFTER();
+            }
             tmem_st32(vb, hi);
             tmem_st32(vb + kPairK, lo);
             BACS_V(16, 3, 1) BACS_V(17, 3, 2) BACS_V(18, 3, 3) BACS_V(19, 3, 4)
@@ -601,7 +677,8 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
           }
         }
         // ------------------------------------------------ epilogue: row norms, rs -> tensor memory (A of the backward)
-        mbar_wait(&bars[BAR_SFULL + wg], n_unit & 1);
+        PROF_MARK(8);   // forward phase (incl. its waits)
+        PROF_WAIT(2, &bars[BAR_SFULL + wg], n_unit & 1);
         TC_FENCE_AFTER();
         {
           uint32_t d[32], r[32];
@@ -611,7 +688,7 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
           for (int y = 0; y < kRows; ++y) {
             const float S = __uint_as_float(d[y]) + __uint_as_float(d[kRows + y]);
             const float rs = S > 1e-37f ? rsqrt_fast_tc(S) : 0.f;  // zero row: norm 0, sub-gradient 0 (torch)
-            loss_f = fmaf(S, rs, loss_f);
+            if (active) loss_f = fmaf(S, rs, loss_f);
             const float rh = tf32_hi(rs);
             r[y] = __float_as_uint(rh);
             r[kRows + y] = __float_as_uint(rs - rh);
@@ -624,20 +701,20 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
           }
         }
         ++n_unit;
+        PROF_MARK(9);   // S wait + epilogue
         if (!want_grad) continue;
         // ------------------------------------------------ backward: chain rule on dV groups
         const bool last_blk = (blk == nblk - 1);
         float pend_own = 0.f, pend_low = 0.f;
         for (int j0 = 0; j0 < w; j0 += 8) {
-          float pU[9], qU[9], pW[9], qW[9], nUv[9], nWv[9];
-          load_cols(j0, pU, qU, pW, qW, nUv, nWv);
+          Corners cn;
+          load_corners(j0, cn, true);
           float own8[8], low8[8];
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
             const int gq = ((j0 >> 1) + m) >> 1, buf = gq & 1;
             if ((m & 1) == 0) {
-              mbar_wait(&bars[BAR_WREADY + 2 * wg + buf], n_wgrp[buf] & 1);
-              ++n_wgrp[buf];
+              PROF_WAIT(3, &bars[BAR_WREADY + 2 * wg + buf], ((n_unit - 1) * (uint32_t)(NG >> 1) + (uint32_t)(gq >> 1)) & 1);
               TC_FENCE_AFTER();
             }
             uint32_t wr[56];
@@ -654,13 +731,12 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
 #pragma unroll
             for (int e = 0; e < 25; ++e) Wv[e] = pack32(wr[2 * e], wr[2 * e + 1]);
             F2 E[9], dE[9];
-            make_E(pU, qU, pW, qW, 2 * m, E);
+            make_E(cn, m, E);
             dE[0] = decoef<0, 0>(Wv, E); dE[1] = decoef<0, 1>(Wv, E); dE[2] = decoef<0, 2>(Wv, E);
             dE[3] = decoef<1, 0>(Wv, E); dE[4] = decoef<1, 1>(Wv, E); dE[5] = decoef<1, 2>(Wv, E);
             dE[6] = decoef<2, 0>(Wv, E); dE[7] = decoef<2, 1>(Wv, E); dE[8] = decoef<2, 2>(Wv, E);
             const int a = 2 * m;
-            const F2 n00 = f2(nUv[a], nUv[a + 1]), n01 = f2(nUv[a + 1], nUv[a + 2]);
-            const F2 n10 = f2(nWv[a], nWv[a + 1]), n11 = f2(nWv[a + 1], nWv[a + 2]);
+            const F2 n00 = cn.n00[m], n01 = cn.n01[m], n10 = cn.n10[m], n11 = cn.n11[m];
             // d new_cd = sum_{c',d'} dE[(c+c')*3 + d+d'] * n_c'd'   (scaled by -2 coef at the row store)
             const F2 g00 = fma2(dE[4], n11, fma2(dE[3], n10, fma2(dE[1], n01, mul2(dE[0], n00))));
             const F2 g01 = fma2(dE[5], n11, fma2(dE[4], n10, fma2(dE[2], n01, mul2(dE[1], n00))));
@@ -717,14 +793,41 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
         float* bl = P.bnd_low + ((size_t)blockIdx.x * kChanCta + lrow) * kMaxW;
         for (int j = 0; j < w; ++j) bl[j] = carry[j];
       }
+      PROF_MARK(10);  // backward phase (incl. its waits)
       mbar_arrive(&bars[BAR_ITEM]);
     }
+    if (warp == 0) PROF_DUMP(0);
     loss_d = (double)loss_f;
   } else if (warp < 11) {
     // =================================================== Bm operand builders (mask moments x row basis)
     const int aw = warp - 8;
     const int Yl = lane & 15, par = lane >> 4;
     uint32_t job = 0, unit = 0;
+    PROF_DECL;
+    const bool staged = P.fast_mask != 0;     // mask rows of a unit arrive by bulk copy one unit ahead; basis table in smem
+    const int mpitch = W + 16;                // staged row pitch (bank spread)
+    uint8_t* s_mrows = smem + sp.mrow_off;
+    const float* s_phi = reinterpret_cast<const float*>(smem + sp.phi_off);
+    // rows of the unit that starts at (item, block): image, first row, number of rows
+    auto unit_rows = [&](int it, int blk, int& b, int& Y0, int& nr) {
+      const int seg = it / h, i = it - seg * h;
+      b = seg / P.ncb;
+      Y0 = s_rowstart[i] + blk * kRows;
+      nr = min(kRows, s_rowstart[i + 1] - Y0);
+    };
+    auto stage_unit = [&](int it, int blk, uint32_t u) {  // one elected lane: bulk copies of the unit's mask rows
+      if (!staged || P.mask == nullptr || aw != 0 || lane != 0) return;
+      int b, Y0, nr;
+      unit_rows(it, blk, b, Y0, nr);
+      uint64_t* bar = &bars[BAR_MASK + (u & 1)];
+      mbar_expect_tx(bar, (uint32_t)(nr * W));
+      uint8_t* dst = s_mrows + (size_t)(u & 1) * kRows * mpitch;
+      for (int r = 0; r < nr; ++r)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst + r * mpitch)),
+                     "l"(P.mask + ((size_t)b * H + Y0 + r) * W), "r"((uint32_t)W), "r"(smem_u32(bar))
+                     : "memory");
+    };
+    if (it0 < it1) stage_unit(it0, 0, 0);
     for (int it = it0; it < it1; ++it) {
       const int seg = it / h, i = it - seg * h, b = seg / P.ncb;
       const int Ybeg = s_rowstart[i], Yend = s_rowstart[i + 1];
@@ -735,12 +838,18 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
         float py[5];
         bern4(rowok ? s_yw[Y] : 0.f, py);
         float* mom = s_mom + (((mom_buffers(w) == 2 ? (unit & 1) : 0) * kRows + Yl) * w) * 5;
+        // the buffer of unit+1 was last read by unit-1, whose forward jobs every warp finished before the barrier below
+        if (blk + 1 < nblk) stage_unit(it, blk + 1, unit + 1);
+        else if (it + 1 < it1) stage_unit(it + 1, 0, unit + 1);
+        if (staged && P.mask) PROF_WAIT(2, &bars[BAR_MASK + (unit & 1)], (unit >> 1) & 1);
+        const uint8_t* mrow_s = s_mrows + ((size_t)(unit & 1) * kRows + Yl) * mpitch;
         for (int jl = 0; jl < jobs_per_unit; ++jl, ++job) {
+          PROF_MARK(8);
           if (jl == NCH) asm volatile("bar.sync 1, 96;" ::: "memory");  // every moment of the unit is in shared memory
+          PROF_MARK(4);
           if ((int)(job % 3) != aw) continue;
           const int slot = aw;              // job % kRing
           const uint32_t use = job / kRing;
-          if (use > 0) mbar_wait(&bars[BAR_BFREE + slot], (use - 1) & 1);
           uint8_t* sl = smem + sp.ring_off + slot * kSlotBytes;
           if (jl < NCH) {
             // ---- forward chunk: cells (2c, 2c+1); this lane: row Yl, cell 2c + par ----
@@ -748,26 +857,53 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
             float M[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
             if (rowok) {
               const int x0 = s_colstart[cell], x1 = s_colstart[cell + 1];
-              const uint8_t* mrow = P.mask ? P.mask + ((size_t)b * H + Y) * W : nullptr;
-              auto add = [&](int X) {
-                float ph[5];
-                bern4(s_xw[X], ph);
+              if (staged) {
+                // branch-free: M_k += m * phi_k[X], mask bytes from the staged row, basis values from the table
+                if (P.mask == nullptr) {
+                  for (int X = x0; X < x1; ++X) {
 #pragma unroll
-                for (int k = 0; k < 5; ++k) M[k] += ph[k];
-              };
-              if (mrow && ((reinterpret_cast<uintptr_t>(mrow + x0) & 7) == 0) && ((x1 - x0) & 7) == 0) {
-                for (int X = x0; X < x1; X += 8) {
-                  const uint2 v = *reinterpret_cast<const uint2*>(mrow + X);
-                  if ((v.x | v.y) == 0) continue;
+                    for (int k = 0; k < 5; ++k) M[k] += s_phi[k * W + X];
+                  }
+                } else if (((x0 | (x1 - x0)) & 7) == 0) {
+                  for (int X = x0; X < x1; X += 8) {
+                    const uint2 v = *reinterpret_cast<const uint2*>(mrow_s + X);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    if ((v.x >> (8 * k)) & 0xffu) add(X + k);
-                    if ((v.y >> (8 * k)) & 0xffu) add(X + 4 + k);
+                    for (int t = 0; t < 8; ++t) {
+                      const uint32_t byte = ((t < 4 ? v.x : v.y) >> (8 * (t & 3))) & 0xffu;
+                      const float mf = byte ? 1.f : 0.f;
+#pragma unroll
+                      for (int k = 0; k < 5; ++k) M[k] = fmaf(mf, s_phi[k * W + X + t], M[k]);
+                    }
+                  }
+                } else {
+                  for (int X = x0; X < x1; ++X) {
+                    const float mf = mrow_s[X] ? 1.f : 0.f;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) M[k] = fmaf(mf, s_phi[k * W + X], M[k]);
                   }
                 }
               } else {
-                for (int X = x0; X < x1; ++X)
-                  if (mrow == nullptr || mrow[X]) add(X);
+                const uint8_t* mrow = P.mask ? P.mask + ((size_t)b * H + Y) * W : nullptr;
+                auto add = [&](int X) {
+                  float ph[5];
+                  bern4(s_xw[X], ph);
+#pragma unroll
+                  for (int k = 0; k < 5; ++k) M[k] += ph[k];
+                };
+                if (mrow && ((reinterpret_cast<uintptr_t>(mrow + x0) & 7) == 0) && ((x1 - x0) & 7) == 0) {
+                  for (int X = x0; X < x1; X += 8) {
+                    const uint2 v = *reinterpret_cast<const uint2*>(mrow + X);
+                    if ((v.x | v.y) == 0) continue;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      if ((v.x >> (8 * k)) & 0xffu) add(X + k);
+                      if ((v.y >> (8 * k)) & 0xffu) add(X + 4 + k);
+                    }
+                  }
+                } else {
+                  for (int X = x0; X < x1; ++X)
+                    if (mrow == nullptr || mrow[X]) add(X);
+                }
               }
             }
 #pragma unroll
@@ -776,6 +912,8 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
             float v[28];
 #pragma unroll
             for (int e = 0; e < 28; ++e) v[e] = e < 25 ? py[e / 5] * M[e % 5] : 0.f;
+            if (use > 0) PROF_WAIT(1, &bars[BAR_BFREE + slot], (use - 1) & 1);   // the slot is written from here on
+            PROF_MARK(8);
             // 16-byte groups [a_e, b_e, a_e+1, b_e+1] (e even): even groups are stored by the lane of cell a, odd
             // groups by the lane of cell b; the partner's pair of values comes by one exchange per value
 #pragma unroll
@@ -797,6 +935,8 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
           } else {
             // ---- backward group: cells 4g .. 4g+3 as two pairs; rows along K ----
             const int g = jl - NCH;
+            if (use > 0) PROF_WAIT(1, &bars[BAR_BFREE + slot], (use - 1) & 1);
+            PROF_MARK(8);
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp) {
               const int cell = 4 * g + 2 * pp + par;
@@ -818,21 +958,25 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[BAR_BFULL + slot]);
+          PROF_MARK(jl < NCH ? 9 : 10);   // build time of a forward / backward job
         }
+        if (!want_grad) asm volatile("bar.sync 1, 96;" ::: "memory");   // forward-only: the unit's mask rows are consumed
       }
     }
+    if (aw == 0) PROF_DUMP(1);
   } else {
     // =================================================== warp 11: MMA issue + TMA loads of the attention rows
     const bool leader = elect_one();
     const uint32_t ring = smem_u32(smem + sp.ring_off);
+    PROF_DECL;
     uint32_t job = 0;
-    uint32_t n_vchunk[2][2] = {{0, 0}, {0, 0}}, n_wgrp[2][2] = {{0, 0}, {0, 0}}, n_unit = 0, n_item_done = 0;
+    uint32_t n_unit = 0, n_item_done = 0;
     constexpr uint32_t id32 = make_idesc(32), id16 = make_idesc(16), id112 = make_idesc(112);
     const uint32_t att_bytes = (uint32_t)(2 * P.box_chan * row_bytes);
     AttPlan ap{0, 0, -1, -1};
     auto wait_items = [&](uint32_t need) {  // phases of BAR_ITEM are consumed strictly one by one
       while (n_item_done < need) {
-        mbar_wait(&bars[BAR_ITEM], n_item_done & 1);
+        PROF_WAIT(0, &bars[BAR_ITEM], n_item_done & 1);
         ++n_item_done;
       }
     };
@@ -878,13 +1022,14 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
         // ---------------- forward: S[128 x 16] += V[128 x 8] * Bm^T per k-step; [hi|lo] rows of Bm as one N = 32 operand
         for (int c = 0; c < NCH; ++c, ++job) {
           const int slot = job % kRing;
-          mbar_wait(&bars[BAR_BFULL + slot], (job / kRing) & 1);
+          PROF_MARK(8);
+          PROF_WAIT(1, &bars[BAR_BFULL + slot], (job / kRing) & 1);
           const uint32_t sb = ring + slot * kSlotBytes;
           for (int wg = 0; wg < 2; ++wg) {
             const int buf = c & 1;
-            mbar_wait(&bars[BAR_VFULL + 2 * wg + buf], n_vchunk[wg][buf] & 1);
-            ++n_vchunk[wg][buf];
+            PROF_WAIT(2, &bars[BAR_VFULL + 2 * wg + buf], (n_unit * (uint32_t)(NCH >> 1) + (uint32_t)(c >> 1)) & 1);
             TC_FENCE_AFTER();
+            PROF_MARK(11);
             if (leader) {
               const uint32_t tw = tmem + wg * kColsWg, va = tw + buf * kColVB;
 #pragma unroll
@@ -898,22 +1043,26 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
               umma_commit(&bars[BAR_VFREE + 2 * wg + buf]);
               if (c == NCH - 1) umma_commit(&bars[BAR_SFULL + wg]);
             }
+            PROF_MARK(12);   // issue of 14 MMAs + commits (leader lane)
             __syncwarp();
+            PROF_MARK(13);
           }
           if (leader) umma_commit(&bars[BAR_BFREE + slot]);
           __syncwarp();
+          PROF_MARK(14);
         }
         if (!want_grad) continue;
         // ---------------- backward: dV[128 x 112] = rs[128 x 16] * Bm[16 x 112], three split products
         for (int g = 0; g < NG; ++g, ++job) {
           const int slot = job % kRing;
-          mbar_wait(&bars[BAR_BFULL + slot], (job / kRing) & 1);
+          PROF_MARK(9);
+          PROF_WAIT(3, &bars[BAR_BFULL + slot], (job / kRing) & 1);
           const uint32_t sb = ring + slot * kSlotBytes;
           for (int wg = 0; wg < 2; ++wg) {
             const int buf = g & 1;
-            if (g == 0) mbar_wait(&bars[BAR_RFULL + wg], n_unit & 1);
-            if (n_wgrp[wg][buf] > 0) mbar_wait(&bars[BAR_WDONE + 2 * wg + buf], (n_wgrp[wg][buf] - 1) & 1);
-            ++n_wgrp[wg][buf];
+            if (g == 0) PROF_WAIT(4, &bars[BAR_RFULL + wg], n_unit & 1);
+            const uint32_t nwg = n_unit * (uint32_t)(NG >> 1) + (uint32_t)(g >> 1);   // group number on this buffer
+            if (nwg > 0) PROF_WAIT(5, &bars[BAR_WDONE + 2 * wg + buf], (nwg - 1) & 1);
             TC_FENCE_AFTER();
             if (leader) {
               const uint32_t tw = tmem + wg * kColsWg, dv = tw + buf * kColVB, rs = tw + kColDS;
@@ -943,6 +1092,7 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
         ap = nx;
       }
     }
+    PROF_DUMP(2);
   }
 
   // ---- teardown: loss partial of the CTA, tensor memory ----
@@ -1016,7 +1166,7 @@ static DtcEncodeTiledFn dtc_encode_fn() {
 }
 
 struct DtcConfig {
-  int n_att, grid;
+  int n_att, grid, fast_mask;
   size_t smem;
   size_t off_partials, off_own, off_low, off_info, off_scratch, ws_total;
 };
@@ -1029,10 +1179,14 @@ static bool dtc_config(int dtype, int B, int A, int h, int w, int H, int W, DtcC
   if ((int64_t)B * A > 0x3fffffff || (int64_t)B * A * h > 0x3fffffff) return false;
   const size_t cap = 227 * 1024 - 1024 - 512;  // dynamic limit minus alignment slack and static shared memory
   bool ok = false;
-  for (int n_att = 3; n_att >= 2 && !ok; --n_att) {   // three row slots prefetch a whole item ahead
-    const dtc::SmemPlan sp = dtc::make_plan(n_att, rb, H, W, h, w);
+  // preference: three attention-row slots (prefetch a whole item ahead), staged mask rows + basis table
+  static const int tries[4][2] = {{3, 1}, {3, 0}, {2, 1}, {2, 0}};
+  for (int t = 0; t < 4 && !ok; ++t) {
+    if (tries[t][1] && (W % 16) != 0) continue;
+    const dtc::SmemPlan sp = dtc::make_plan(tries[t][0], tries[t][1], rb, H, W, h, w);
     if ((size_t)sp.total <= cap) {
-      cfg->n_att = n_att;
+      cfg->n_att = tries[t][0];
+      cfg->fast_mask = tries[t][1];
       cfg->smem = (size_t)sp.total + 1024;
       ok = true;
     }
@@ -1114,6 +1268,7 @@ int distill_tc_launch(const void* old_att, const void* new_att, int dtype, int B
   P.bnd_info = reinterpret_cast<int*>(ws + cfg.off_info);
   P.mb_scratch = reinterpret_cast<float*>(ws + cfg.off_scratch);
   P.n_att = cfg.n_att;
+  P.fast_mask = (cfg.fast_mask && (mask == nullptr || a16(mask))) ? 1 : 0;
   P.want_grad = dnew != nullptr;
   P.box_chan = box_chan;
 #define BACS_DTC_LAUNCH(TT)                                                                                         \
@@ -1131,6 +1286,20 @@ int distill_tc_launch(const void* old_att, const void* new_att, int dtype, int B
   } while (0)
   BACS_DISPATCH_DTYPE(dtype, TT, BACS_DTC_LAUNCH(TT));
 #undef BACS_DTC_LAUNCH
+#ifdef BACS_DTC_PROFILE
+  {
+    cudaStreamSynchronize(s);
+    static long long prof[160 * 3 * 16];
+    cudaMemcpyFromSymbol(prof, dtc::g_dtc_prof, sizeof(prof));
+    const char* roles[3] = {"builder", "aux    ", "mma    "};
+    for (int cta = 0; cta < std::min(cfg.grid, 148); cta += 49)
+      for (int r = 0; r < 3; ++r) {
+        fprintf(stderr, "cta %3d %s:", cta, roles[r]);
+        for (int k = 0; k < 16; ++k) fprintf(stderr, " [%d]%lld", k, prof[(cta * 3 + r) * 16 + k]);
+        fprintf(stderr, "\n");
+      }
+  }
+#endif
 #ifdef BACS_DTC_DEBUG
   {
     cudaStreamSynchronize(s);

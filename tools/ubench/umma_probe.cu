@@ -299,6 +299,54 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(long long* __restrict__ cy
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512));
 }
 
+// ---- issue cost of the forward pattern of distill_tc: 7 x (N=32, N=16) + commit per block ----
+__global__ void __launch_bounds__(128, 1) pattern_kernel(long long* __restrict__ cyc, int reps, int with_commit, int wait_each) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  float* bs = reinterpret_cast<float*>(smem);
+  for (int k = tid; k < 16384; k += blockDim.x) bs[k] = 0.f;
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  TC_FENCE_BEFORE(); __syncthreads(); TC_FENCE_AFTER();
+  const uint32_t tb = tmem_base_s;
+  if (warp == 0) {
+    const bool leader = elect_one();
+    const uint32_t sb = smem_u32(smem);
+    long long issue = 0;
+    const long long t0 = clock64();
+    uint32_t ph = 0;
+    for (int r = 0; r < reps; ++r) {
+      const long long ta = clock64();
+      if (leader) {
+        const uint32_t tw = tb + (r & 1) * 256, va = tw + ((r >> 1) & 1) * 112;
+#pragma unroll
+        for (int s = 0; s < 7; ++s) {
+          const uint64_t bd = make_desc(sb + s * 1024, 512, 128);
+          umma_tf32_ts(tw + 224, va + 8 * s, bd, make_idesc(32, 0), (r | s) != 0);
+          umma_tf32_ts(tw + 224 + 16, va + 56 + 8 * s, bd, make_idesc(16, 0), 1);
+        }
+        if (with_commit) umma_commit(&bar[0]);
+      }
+      __syncwarp();
+      issue += clock64() - ta;
+      if (with_commit && wait_each) { mbar_wait(&bar[0], ph); ph ^= 1; }
+    }
+    if (leader) umma_commit(&bar[1]);
+    __syncwarp();
+    mbar_wait(&bar[1], 0);
+    const long long t2 = clock64();
+    if (leader) { cyc[0] = issue; cyc[1] = t2 - t0; }
+  }
+  TC_FENCE_BEFORE(); __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512));
+}
+
 static float tf32r(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
 
 int main() {
@@ -386,6 +434,19 @@ int main() {
       CK(cudaMemcpy(h, dc2, 16, cudaMemcpyDeviceToHost)); \
       printf("rate N=%3d: 1024 MMAs issue %lld done %lld cyc -> %.1f cyc/MMA\n", NN, h[0], h[1], h[1] / 1024.0); }
     RATE(16) RATE(32) RATE(48) RATE(64) RATE(112) RATE(128) RATE(256)
+  }
+
+  {
+    long long* dc3; CK(cudaMalloc(&dc3, 64));
+    long long h[2];
+    CK(cudaFuncSetAttribute(pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    for (int mode = 0; mode < 3; ++mode) {
+      const int wc = mode > 0, we = mode > 1;
+      pattern_kernel<<<1, 128, 65536>>>(dc3, 256, wc, we); CK(cudaDeviceSynchronize());
+      pattern_kernel<<<1, 128, 65536>>>(dc3, 256, wc, we); CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(h, dc3, 16, cudaMemcpyDeviceToHost));
+      printf("pattern (7 x (N=32,N=16)%s%s): issue %.1f cyc per block, total %.1f cyc per block\n", wc ? " + commit" : "", we ? ", wait each" : "", h[0] / 256.0, h[1] / 256.0);
+    }
   }
   printf("%s\n", (e1 < 1e-4 && e2 < 1e-4) ? "PROBE OK" : "PROBE MISMATCH");
   return 0;
