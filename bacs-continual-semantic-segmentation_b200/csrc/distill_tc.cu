@@ -31,6 +31,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -66,6 +67,8 @@ struct Params {
   int n_att;
   int want_grad;
   int box_chan;       // channels per TMA box: min(256, B*A)
+  int knock;          // diagnostics only (BACS_DTC_KNOCK): 1 = operand builders skip their arithmetic, 2 = no MMAs are issued,
+                      // 4 = builders skip the V / dE arithmetic; results are wrong, the timing shows the critical role
   int fast_mask;      // mask rows staged in shared memory by bulk copies + basis table (needs 16-byte aligned rows)
 };
 
@@ -637,6 +640,17 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
             for (int k = 0; k < 9; ++k) E2[k] = add2(E[k], E[k]);
             const uint32_t vb = tm + buf * kColVB;
             uint32_t hi[32], lo[32];
+            if (P.knock & 4) {
+              const uint32_t nvc = n_unit * (uint32_t)(NCH >> 1) + (uint32_t)(cidx >> 1);
+              if (nvc > 0) mbar_wait(&bars[BAR_VFREE + 2 * wg + buf], (nvc - 1) & 1);
+              TC_FENCE_AFTER();
+              for (int k = 0; k < 32; ++k) hi[k] = lo[k] = lo32(E[k % 9]);
+              tmem_st32(vb, hi);
+              TC_WAIT_ST();
+              TC_FENCE_BEFORE();
+              mbar_arrive(&bars[BAR_VFULL + 2 * wg + buf]);
+              continue;
+            }
 #define BACS_V(e, Q, K)                         \
   {                                             \
     const F2 v = vcoef<Q, K>(E, E2);            \
@@ -855,7 +869,7 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
             // ---- forward chunk: cells (2c, 2c+1); this lane: row Yl, cell 2c + par ----
             const int cell = 2 * jl + par;
             float M[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-            if (rowok) {
+            if (rowok && !(P.knock & 1)) {
               const int x0 = s_colstart[cell], x1 = s_colstart[cell + 1];
               if (staged) {
                 // branch-free: M_k += m * phi_k[X], mask bytes from the staged row, basis values from the table
@@ -1032,6 +1046,7 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
             PROF_MARK(11);
             if (leader) {
               const uint32_t tw = tmem + wg * kColsWg, va = tw + buf * kColVB;
+              if (!(P.knock & 2))
 #pragma unroll
               for (int s = 0; s < 7; ++s) {
                 const uint64_t bd = make_desc(sb + s * 1024, 512, 128);
@@ -1066,6 +1081,7 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
             TC_FENCE_AFTER();
             if (leader) {
               const uint32_t tw = tmem + wg * kColsWg, dv = tw + buf * kColVB, rs = tw + kColDS;
+              if (!(P.knock & 2))
 #pragma unroll
               for (int t = 0; t < 2; ++t) {
                 const uint64_t bh = make_desc(sb + t * 2 * kBwdLbo, kBwdLbo, 128);
@@ -1271,6 +1287,7 @@ int distill_tc_launch(const void* old_att, const void* new_att, int dtype, int B
   P.fast_mask = (cfg.fast_mask && (mask == nullptr || a16(mask))) ? 1 : 0;
   P.want_grad = dnew != nullptr;
   P.box_chan = box_chan;
+  P.knock = getenv("BACS_DTC_KNOCK") ? atoi(getenv("BACS_DTC_KNOCK")) : 0;
 #define BACS_DTC_LAUNCH(TT)                                                                                         \
   do {                                                                                                              \
     auto kern = dtc::distill_tc_kernel<TT>;                                                                         \
