@@ -352,6 +352,10 @@ def main():
 
     collective, nranks_checked = "none (single process)", 1
     if world > 1:
+        # data-parallel replicas start from identical prototype state (the per-rank seed only varies the batch)
+        dist.broadcast(loss_fn._prototypes._prototypes_tensors, 0)
+        dist.broadcast(loss_fn._prototypes._count_features, 0)
+        loss_fn._prototypes.refresh_ready()
         collective = verify_ranks(loss_fn, leaves, batch, cfg, dev, world, rank)
         nranks_checked = world
 

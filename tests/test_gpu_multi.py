@@ -18,3 +18,13 @@ def test_peer_allreduce_matches_nccl():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("peer all-reduce ok") == 2, out.stdout[-2000:]
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_peer_allreduce_timeout_is_loud():
+    """a rank that arrives later than the time-out: the waiting rank keeps its state and raises at the next check"""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29543", os.path.join(ROOT, "tests", "multigpu", "peer_timeout_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("peer time-out ok") == 2, out.stdout[-2000:]
