@@ -70,84 +70,86 @@ class BACSLoss(ExperienceReplay):
         self.dark_criterion = "mse"
 
     # ---- lifecycle ------------------------------------------------------------------------------
+    def _attach_replay_loaders(self, trainer, datamodule):
+        """From the second task on the training loop iterates three loaders in lock-step (reference
+        bacs_loss.py:97-124): the task's own batches, replayed (image, label) pairs and replayed (image, stored
+        low-res logits, class count) triples, the latter with torchvision's RandomAutocontrast on the images."""
+        from pytorch_lightning.trainer.supporters import CombinedLoader   # the caller's Lightning
+        from torchvision import transforms as tv
+        buf = self._get_current_buffer()
+        autocontrast = tv.RandomAutocontrast(p=0.5)
+        loaders = {
+            "main": trainer.train_dataloader.loaders,
+            "buffer": datamodule.get_buffer_loader(buf.img_paths, buf.target_paths, target_trsf=buf.target_trsf),
+            "bufferlogits": datamodule.get_logits_loader(
+                buf.dataset_map["examples"], buf.dataset_map["logits"], buf._logits_n_classes, length=len(buf.img_paths),
+                transforms=tv.Compose([tv.Lambda(lambda x: torch.from_numpy(x)), autocontrast])),
+        }
+        trainer.train_dataloader = CombinedLoader(loaders, "max_size_cycle")
+        self.logit_transforms = autocontrast
+
     def on_train_start(self, task_num, **kwargs):
-        """bacs_loss.py:82-131: buffer, the combined (main, buffer, bufferlogits) loader and
-        the frozen previous model."""
+        """Start of a task (reference bacs_loss.py:82-131): open the replay buffer for the task's class count, switch
+        the replay terms on after the first task, and keep the teacher frozen on the training device."""
         self.accelerator = kwargs.get("accelerator")
-        self._init_dark_criterion(device=self.accelerator.root_device)
+        device = self.accelerator.root_device
+        self._init_dark_criterion(device=device)
         self._init_buffer(task_num=task_num)
+        self._iter_indx = 0
+        self.update_buffer_every = kwargs.get("accumulate_grad_batches", 1)
         if task_num > 0:
+            assert self.same_task is False
             self._use_der_loss = True
             datamodule = kwargs.get("datamodule")
-            assert self.same_task is False
-            if (self.alpha > 0 or self.beta > 0) and datamodule is not None:
-                from torchvision import transforms as tvtransforms
-                buffer = self._get_current_buffer()
-                buffer_loader = datamodule.get_buffer_loader(buffer.img_paths, buffer.target_paths,
-                                                             target_trsf=buffer.target_trsf)
-                buffer_logits_loader = datamodule.get_logits_loader(
-                    buffer.dataset_map["examples"], buffer.dataset_map["logits"], buffer._logits_n_classes,
-                    length=len(buffer.img_paths),
-                    transforms=tvtransforms.Compose([tvtransforms.Lambda(lambda x: torch.from_numpy(x)),
-                                                     tvtransforms.RandomAutocontrast(p=0.5)]))
-                trainer = kwargs.get("trainer")
-                from pytorch_lightning.trainer.supporters import CombinedLoader   # the caller's Lightning
-                trainer.train_dataloader = CombinedLoader(
-                    {"main": trainer.train_dataloader.loaders, "buffer": buffer_loader,
-                     "bufferlogits": buffer_logits_loader}, "max_size_cycle")
-                self.logit_transforms = tvtransforms.RandomAutocontrast(p=0.5)
-        self.update_buffer_every = kwargs.get("accumulate_grad_batches", 1)
-        self._iter_indx = 0
+            if datamodule is not None and (self.alpha > 0 or self.beta > 0):
+                self._attach_replay_loaders(kwargs.get("trainer"), datamodule)
         if self.prev_model is not None:
-            self.prev_model = self.prev_model.to(self.accelerator.root_device)
+            self.prev_model = self.prev_model.to(device)
             freeze_network(self.prev_model)
 
+    @staticmethod
+    def _train_set_files(loader, trainer):
+        """(dataset, image paths, label paths) in loader order; sweeps / debug runs wrap the dataset in a Subset"""
+        datamodule = getattr(trainer, "datamodule", None)
+        if datamodule is not None and (getattr(datamodule, "_sweep", False) or getattr(datamodule, "debug", False)):
+            subset = loader.dataset.base_dataset
+            return subset.dataset, subset.dataset._x[subset.indices], subset.dataset._y[subset.indices]
+        return loader.dataset, loader.dataset._x, loader.dataset._y
+
     def on_train_end(self, **kwargs):
-        """bacs_loss.py:133-203: freeze a copy of the model as teacher, then one pass over the
-        task's train set to fill the replay buffer with (image, low-res logits, labels,
-        importance, seen map)."""
+        """End of a task (reference bacs_loss.py:133-203): the trained model becomes the frozen teacher, then one
+        un-shuffled pass over the task's training set offers every image to the replay buffer together with its
+        low-res logits, the importance score (SCORE mode of the fused kernel), the seen map and its file paths."""
         BaseLoss.on_train_end(self, **kwargs)
         if not kwargs.get("pre_last_tasks"):
             return
-        model = kwargs.get("model", None)
-        train_dataloader = kwargs.get("train_dataloader", None)
+        model, loader = kwargs.get("model"), kwargs.get("train_dataloader")
         if self.buffer is None:
             self._init_buffer()
         self.prev_model = model.clone()
         freeze_network(self.prev_model)
-        populate_buffer = self.alpha > 0 or self.beta > 0
-        if model is not None and train_dataloader is not None and populate_buffer:
-            accelerator = kwargs.get("accelerator")
-            trainer = kwargs.get("trainer")
-            model = model.to(accelerator.root_device)
-            train_dataloader.shuffle = False
-            datamodule = getattr(trainer, "datamodule", None)
-            if datamodule is not None and (getattr(datamodule, "_sweep", False) or getattr(datamodule, "debug", False)):
-                train_dataset = train_dataloader.dataset.base_dataset.dataset
-                indices = train_dataloader.dataset.base_dataset.indices
-                img_paths, target_paths = train_dataset._x[indices], train_dataset._y[indices]
-            else:
-                train_dataset = train_dataloader.dataset
-                img_paths, target_paths = train_dataset._x, train_dataset._y
-            target_trsf = train_dataset.target_trsf
-            train_dataloader = accelerator.process_dataloader(train_dataloader)
-            classes_weights = torch.ones(self.nb_current_classes, device=accelerator.root_device)
-            classes_weights[0] = 0
-            start_idx = end_idx = 0
-            with torch.no_grad():
-                for batch in train_dataloader:
-                    end_idx += batch[0].shape[0]
-                    batch = accelerator.to_device(batch)
-                    images, labels = batch[0], batch[1].long()
-                    model.enable_caching_sem_logits()
-                    _, losses = self._score_batch(model, images, labels, classes_weights)
-                    sem_logits = model.pop_sem_logits()
-                    seen_detector = self._get_seen_detector(images, model)
-                    self._add_to_buffer(images, sem_logits, labels, losses, seen_detector=seen_detector,
-                                        paths=img_paths[start_idx:end_idx],
-                                        target_paths=target_paths[start_idx:end_idx], target_trsf=copy(target_trsf))
-                    start_idx += batch[0].shape[0]
-            self.update_buffer_scores()
+        if model is None or loader is None or not (self.alpha > 0 or self.beta > 0):
+            return
+        accelerator = kwargs.get("accelerator")
+        device = accelerator.root_device
+        model = model.to(device)
+        loader.shuffle = False
+        dataset, images_on_disk, labels_on_disk = self._train_set_files(loader, kwargs.get("trainer"))
+        class_w = torch.ones(self.nb_current_classes, device=device)
+        class_w[0] = 0
+        seen = 0
+        with torch.no_grad():
+            for batch in accelerator.process_dataloader(loader):
+                images, labels = accelerator.to_device(batch)[:2]
+                labels = labels.long()
+                files = slice(seen, seen + images.shape[0])
+                model.enable_caching_sem_logits()
+                score = self._score_batch(model, images, labels, class_w)[1]
+                self._add_to_buffer(images, model.pop_sem_logits(), labels, score,
+                                    seen_detector=self._get_seen_detector(images, model), paths=images_on_disk[files],
+                                    target_paths=labels_on_disk[files], target_trsf=copy(dataset.target_trsf))
+                seen = files.stop
+        self.update_buffer_scores()
 
     # ---- step ------------------------------------------------------------------------------------
     def post_process_mask(self, img, mask):

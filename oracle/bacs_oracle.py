@@ -111,8 +111,8 @@ def nearest_src_index(out_size: int, in_size: int) -> np.ndarray:
 
 def downsample_labels(target: torch.Tensor, h: int, w: int) -> torch.Tensor:
     """[B,H,W] int64 -> [B,h,w] int64 (loss/prototypes.py:181-186)."""
-    ri = torch.from_numpy(nearest_src_index(h, target.shape[1]))
-    ci = torch.from_numpy(nearest_src_index(w, target.shape[2]))
+    ri = torch.from_numpy(nearest_src_index(h, target.shape[1])).to(target.device)
+    ci = torch.from_numpy(nearest_src_index(w, target.shape[2])).to(target.device)
     return target[:, ri][:, :, ci].contiguous()
 
 
@@ -152,12 +152,12 @@ def proto_accumulate(features: torch.Tensor, target: torch.Tensor, initial_class
     B, D, h, w = features.shape
     feats = features.detach().float()
     ld = downsample_labels(target, h, w)
-    lut = torch.from_numpy(class_task_lut(initial_classes, increment, ignore_index))
+    lut = torch.from_numpy(class_task_lut(initial_classes, increment, ignore_index)).to(ld.device)
     valid = (ld >= 0) & (ld < 256)
     task = torch.full_like(ld, -1)
     task[valid] = lut[ld[valid]]
-    sums = torch.zeros(n_tasks, D, dtype=torch.float32)
-    counts = torch.zeros(n_tasks, dtype=torch.int64)
+    sums = torch.zeros(n_tasks, D, dtype=torch.float32, device=feats.device)   # (the full-size GPU tests run this file on device tensors)
+    counts = torch.zeros(n_tasks, dtype=torch.int64, device=feats.device)
     for g in range(n_tasks):
         m = task == g                                   # [B,h,w]
         n_g = int(m.sum())
@@ -311,7 +311,7 @@ def cross_entropy(logits, target, weight: Optional[torch.Tensor] = None,
     keep = target != ignore_index
     y = torch.where(keep, target, torch.zeros_like(target))
     nll = lse - x.gather(1, y.unsqueeze(1)).squeeze(1)
-    wy = torch.ones(K) if weight is None else weight.float()
+    wy = torch.ones(K, device=x.device) if weight is None else weight.float().to(x.device)
     wpix = wy[y] * keep
     return (wpix * nll).sum() / wpix.sum()
 
@@ -323,7 +323,7 @@ def cross_entropy_per_image_score(logits, target, weight, ignore_index: int = IG
     keep = target != ignore_index
     y = torch.where(keep, target, torch.zeros_like(target))
     nll = lse - x.gather(1, y.unsqueeze(1)).squeeze(1)
-    per = weight.float()[y] * keep * nll
+    per = weight.float().to(x.device)[y] * keep * nll
     return -per.view(x.shape[0], -1).mean(1)
 
 
@@ -491,7 +491,7 @@ def bacs_step(logits, pen, old_att, new_att, mask, protos, counts, head_w, head_
         loss = loss + teacher_distill(old_att, new_att, mask, smax, lkd, lkd_threshold)
     if replay is not None:
         K = logits.shape[1] if nb_current_classes is None else nb_current_classes
-        cw = torch.zeros(K)
+        cw = torch.zeros(K, device=logits.device)
         cw[(1 if ignore_rep_bg else 0):old_cl] = 1
         if beta != 0:
             rs, rn = proto_accumulate(replay["pen"], replay["mask"], initial_classes, increment, T,
