@@ -95,14 +95,31 @@ __global__ void __launch_bounds__(256) remap_presence_kernel(const int64_t* __re
   __syncthreads();
   const int64_t* src = in + (int64_t)img * ppi;
   int last = INT_MIN;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ppi; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t l = src[i];
+  auto mark = [&](int64_t l) {
     const int64_t r = l - lo;
     const int slot = r < 0 ? kMaxDom : (r >= n_dom ? kMaxDom + 1 : (int)r);
     if (slot != last) {
       sh[slot] = 1;
       last = slot;
     }
+  };
+  if ((ppi & 1) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    // 16-byte loads, four in flight per thread
+    const longlong2* v = reinterpret_cast<const longlong2*>(src);
+    const int64_t nv = ppi >> 1, step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += 4 * step) {
+      longlong2 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = (i + u * step < nv) ? __ldg(v + i + u * step) : make_longlong2(lo, lo);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        mark(x[u].x);
+        mark(x[u].y);
+      }
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ppi; i += (int64_t)gridDim.x * blockDim.x)
+      mark(src[i]);
   }
   __syncthreads();
   int32_t* pres = presence + (int64_t)img * kPresStride;
@@ -172,10 +189,26 @@ __global__ void __launch_bounds__(256) remap_apply_kernel(const int64_t* __restr
   __syncthreads();
   const int64_t* src = in + (int64_t)img * ppi;
   int64_t* dst = out + (int64_t)img * ppi;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ppi; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t l = src[i];
+  auto look = [&](int64_t l) -> int64_t {
     const int64_t r = l - lo;
-    dst[i] = r < 0 ? (int64_t)oob_final[0] : (r >= n_dom ? (int64_t)oob_final[1] : (int64_t)lut[r]);
+    return r < 0 ? (int64_t)oob_final[0] : (r >= n_dom ? (int64_t)oob_final[1] : (int64_t)lut[r]);
+  };
+  if ((ppi & 1) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    const longlong2* v = reinterpret_cast<const longlong2*>(src);
+    longlong2* o = reinterpret_cast<longlong2*>(dst);
+    const int64_t nv = ppi >> 1, step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += 4 * step) {
+      longlong2 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u * step < nv) x[u] = __ldg(v + i + u * step);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u * step < nv) o[i + u * step] = make_longlong2(look(x[u].x), look(x[u].y));
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ppi; i += (int64_t)gridDim.x * blockDim.x)
+      dst[i] = look(src[i]);
   }
 }
 

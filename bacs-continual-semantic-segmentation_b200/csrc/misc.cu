@@ -222,6 +222,69 @@ __global__ void __launch_bounds__(256) confmat_kernel(const P* __restrict__ pred
   }
 }
 
+
+// int64 predictions, 16-byte aligned: coalesced 16-byte loads (a lane owns two adjacent pixels per load, four loads of
+// each tensor in flight) and warp-level aggregation -- a warp inside a uniform region (the usual case in a
+// segmentation map) issues ONE shared-memory atomic per pixel slot: the lanes that agree with the first valid lane
+// are counted by a ballot, only the others (region borders, wrong pixels) add on their own.
+__device__ __forceinline__ void confmat_warp_add(unsigned int* sh, int bin, int lane) {
+  constexpr unsigned kFull = 0xffffffffu;
+  const unsigned valid = __ballot_sync(kFull, bin >= 0);
+  if (valid == 0) return;
+  const int leader = __ffs(valid) - 1;
+  const int first = __shfl_sync(kFull, bin, leader);
+  const unsigned same = __ballot_sync(kFull, bin == first);   // the leader's bin: one atomic for all its lanes
+  if (lane == leader) atomicAdd(&sh[first], (unsigned int)__popc(same));
+  else if (bin >= 0 && bin != first) atomicAdd(&sh[bin], 1u);  // the others (region borders, wrong pixels) on their own
+}
+
+__global__ void __launch_bounds__(256) confmat_vec_kernel(const longlong2* __restrict__ preds,
+                                                          const longlong2* __restrict__ target, int64_t nvec, int K,
+                                                          unsigned long long* __restrict__ confmat,
+                                                          unsigned long long* __restrict__ oob) {
+  extern __shared__ unsigned int sh[];
+  const int KK = K * K, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < KK; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  unsigned int n_oob = 0;
+  constexpr int U = 4;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x * U;
+  for (int64_t v0 = (int64_t)blockIdx.x * blockDim.x * U; v0 < nvec; v0 += step) {  // warp-uniform trip count
+    longlong2 t[U], p[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + (int64_t)u * blockDim.x + threadIdx.x;
+      if (v < nvec) {
+        t[u] = __ldg(target + v);
+        p[u] = __ldg(preds + v);
+      } else {
+        t[u] = make_longlong2(-1, -1);
+        p[u] = make_longlong2(0, 0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      // metrics.py:45-46 casts both to int32 before the range test
+      const int t0 = (int)t[u].x, t1 = (int)t[u].y, p0 = (int)p[u].x, p1 = (int)p[u].y;
+      int b0 = -1, b1 = -1;
+      if (t0 >= 0 && t0 < K) {
+        if (p0 >= 0 && p0 < K) b0 = t0 * K + p0;
+        else ++n_oob;
+      }
+      if (t1 >= 0 && t1 < K) {
+        if (p1 >= 0 && p1 < K) b1 = t1 * K + p1;
+        else ++n_oob;
+      }
+      confmat_warp_add(sh, b0, lane);
+      confmat_warp_add(sh, b1, lane);
+    }
+  }
+  if (n_oob && oob) atomicAdd(oob, (unsigned long long)n_oob);
+  __syncthreads();
+  for (int i = threadIdx.x; i < KK; i += blockDim.x)
+    if (sh[i]) atomicAdd(&confmat[i], (unsigned long long)sh[i]);
+}
+
 // metrics.py:52-88 (the reference's fp/fn naming is kept: "fn" = column sum - tp,
 // "fp" = row sum - tp) + torchmetrics' IoU from the matrix (absent -> 0, reduction none).
 __global__ void __launch_bounds__(256) confmat_metrics_kernel(const int64_t* __restrict__ cm, int K,
@@ -452,6 +515,19 @@ int bacs_confmat_accumulate(const void* preds, int preds_is_float, const int64_t
   if (blocks > cap) blocks = cap;
   unsigned long long* cm = reinterpret_cast<unsigned long long*>(confmat);
   unsigned long long* ob = reinterpret_cast<unsigned long long*>(oob);
+  if (!preds_is_float && smem <= 48 * 1024 && n >= 2 && ((reinterpret_cast<uintptr_t>(preds) | reinterpret_cast<uintptr_t>(target)) & 15) == 0) {
+    const int64_t nvec = n >> 1;
+    int64_t vb = (nvec + 256 * 4 - 1) / (256 * 4);
+    vb = std::min<int64_t>(vb, (int64_t)sm_count() * 8);
+    confmat_vec_kernel<<<(unsigned)vb, 256, smem, s>>>(reinterpret_cast<const longlong2*>(preds),
+                                                       reinterpret_cast<const longlong2*>(target), nvec, K, cm, ob);
+    BACS_CHECK_LAUNCH("bacs_confmat_accumulate");
+    if (n & 1) {  // the odd last pixel
+      confmat_kernel<int64_t, false><<<1, 32, 0, s>>>(reinterpret_cast<const int64_t*>(preds) + (n - 1), target + (n - 1), 1, K, cm, ob);
+      BACS_CHECK_LAUNCH("bacs_confmat_accumulate(tail)");
+    }
+    return BACS_OK;
+  }
 #define LAUNCH_CM(PT)                                                                                          \
   do {                                                                                                         \
     if (use_smem) {                                                                                            \

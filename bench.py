@@ -183,10 +183,15 @@ def workload_name(cfg):
 
 
 def integer_rows(timed_fn, dev, peak, shape=(4, 1024, 2048), K=20):
-    """The integer rows of the path, each timed alone on inputs larger than L2: the confusion-matrix histogram at the
-    Cityscapes evaluation shape (training/metrics.py:38-50; 16 B of int64 preds + targets per pixel), the label remap
-    (training/utils.py:225-261; 8 B in + 8 B out) and the nearest label down-sample + class->task map
-    (loss/prototypes.py:177-205; 8 B in, output 1/256 of that).  -> list of {name, us, GB/s, frac}."""
+    """The integer rows of the path, each timed alone on inputs larger than L2:
+    * confusion-matrix histogram at the Cityscapes evaluation shape (training/metrics.py:38-50): 16 B of int64
+      predictions + targets per pixel; on uniformly random classes (every lane a different bin: the worst case for
+      the shared-memory histogram) and on a blocky map with 10 % wrong pixels (what an evaluation pass looks like);
+    * label remap (training/utils.py:225-261): the labels present decide the mapping (sequential aliasing, Q13), so
+      the image is read twice (presence, remap) and written once: 24 B per pixel;
+    * nearest label down-sample + class -> task + raster rank (loss/prototypes.py:177-205): only one pixel in 256 is
+      read -- one 32-byte sector per low-res pixel -- so the row is latency-bound, not bandwidth-bound.
+    -> list of {name, us, algorithmic_bytes, GB/s, frac_of_hbm_peak, limiter}."""
     import torch
     from bacs_b200 import ops
     g = torch.Generator(device=dev).manual_seed(5)
@@ -195,6 +200,9 @@ def integer_rows(timed_fn, dev, peak, shape=(4, 1024, 2048), K=20):
     target = torch.randint(0, K, (B, H, W), device=dev, generator=g, dtype=torch.int64)
     target[:, :8] = 255                                                # ignored border
     preds = torch.randint(0, K, (B, H, W), device=dev, generator=g, dtype=torch.int64)
+    blocky = torch.randint(0, K, (B, H // 64, W // 64), device=dev, generator=g, dtype=torch.int64)
+    blocky = blocky.repeat_interleave(64, 1).repeat_interleave(64, 2).contiguous()
+    noisy = torch.where(torch.rand(B, H, W, device=dev, generator=g) < 0.1, preds, blocky)
     confmat = torch.zeros(K, K, dtype=torch.int64, device=dev)
     lut = torch.arange(256, dtype=torch.int32, device=dev)
     lut[K:] = 0
@@ -202,15 +210,21 @@ def integer_rows(timed_fn, dev, peak, shape=(4, 1024, 2048), K=20):
     task_lut[1:K] = torch.arange(K - 1, dtype=torch.int32, device=dev) % 4
     out = torch.empty_like(target)
     rows = []
-    for name, fn, nbytes in (
-            ("confmat_accumulate [%d,%d,%d] K=%d" % (B, H, W, K),
-             lambda: ops.confmat_accumulate(preds, target, K, confmat), 16 * px),
-            ("label_remap [%d,%d,%d]" % (B, H, W), lambda: ops.label_remap(target, lut, 0, out=out), 16 * px),
+    for name, fn, nbytes, limiter in (
+            ("confmat_accumulate [%d,%d,%d] K=%d, random classes" % (B, H, W, K),
+             lambda: ops.confmat_accumulate(preds, target, K, confmat), 16 * px,
+             "shared-memory atomics: 32 distinct bins per warp instruction"),
+            ("confmat_accumulate [%d,%d,%d] K=%d, blocky map with 10%% errors" % (B, H, W, K),
+             lambda: ops.confmat_accumulate(noisy, blocky, K, confmat), 16 * px, "HBM"),
+            ("label_remap [%d,%d,%d]" % (B, H, W), lambda: ops.label_remap(target, lut, 0, out=out), 24 * px,
+             "HBM (two passes: the label set must be known before a pixel can be mapped)"),
             ("label_downsample_task [%d,%d,%d] -> /16" % (B, H, W),
-             lambda: ops.label_downsample_task(target, H // 16, W // 16, task_lut, 4), 8 * px + 13 * px // 256)):
+             lambda: ops.label_downsample_task(target, H // 16, W // 16, task_lut, 4), (32 + 13) * (px // 256),
+             "latency: one 32-byte sector per low-res pixel + block scan; 1/256 of the labels are read")):
         ms = timed_fn(fn, 20, 3)
         gbs = nbytes / (ms * 1e-3) / 1e9
-        rows.append({"name": name, "us": ms * 1e3, "algorithmic_bytes": nbytes, "GB/s": gbs, "frac_of_hbm_peak": gbs / peak})
+        rows.append({"name": name, "us": ms * 1e3, "algorithmic_bytes": nbytes, "GB/s": gbs,
+                     "frac_of_hbm_peak": gbs / peak, "limiter": limiter})
     return rows
 
 
@@ -231,7 +245,7 @@ def run_integer_rows(args, dev, world, rank):
         return e0.elapsed_time(e1) / steps
     peak, peak_src = peaks()
     rows = integer_rows(timed, dev, peak, shape=(8, 1024, 2048), K=20)
-    cm = rows[0]
+    cm = rows[1]                      # the evaluation-like input
     px = 8 * 1024 * 2048
     if rank == 0:
         print(json.dumps({"metric": "confusion-matrix pixels/sec (Cityscapes 1024x2048 evaluation)", "value": px / (cm["us"] * 1e-6),
