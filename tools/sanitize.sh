@@ -1,0 +1,29 @@
+#!/bin/bash
+# compute-sanitizer targets for the kernels that synchronise through mbarriers / TMA rings / tensor memory
+# (race detection).  One tool per gpurun call (B200_PROFILING.md), on small shapes:
+#   gpurun -- 'bash tools/sanitize.sh racecheck'      (or memcheck / synccheck)
+# The pixel kernel (pixel_wce: 4-stage TMA ring, rotating tile ownership), the tensor-core distill kernel
+# (distill_tc: operand ring, tcgen05 commit barriers, bulk-copied mask rows) and the label / prototype chain.
+set -e
+TOOL=${1:-racecheck}
+cd "$(dirname "$0")/.."
+compute-sanitizer --tool "$TOOL" --print-limit 20 python - <<'PY'
+import sys, torch
+sys.path.insert(0, ".")
+from bacs_b200 import ops, synth, _cabi
+gen = torch.Generator().manual_seed(0)
+# tensor-core distill, two row blocks per interval, boundary rows between CTA ranges
+old = torch.randn(2, 130, 5, 16, generator=gen).bfloat16().cuda()
+new = torch.randn(2, 130, 5, 16, generator=gen).bfloat16().cuda()
+m = (torch.rand(2, 120, 256, generator=gen) > 0.4).to(torch.uint8).cuda()
+assert ops.distill_kernel_variant(new, (120, 256)) == 1
+s, d = ops.teacher_distill(old, new, m, (120, 256), 1.0, True)
+# the training-step pixel kernel on 512-pixel row tiles, with the seen heads
+cfg = synth.CONFIGS["row512"]
+inp = synth.make_step_inputs(cfg, seed=1, dtype=torch.bfloat16)
+loss_fn, net, batch, leaves = synth.build_bacs_step(cfg, inp)
+loss, preds = loss_fn.compute_loss(batch, net, train=True)
+loss.backward()
+torch.cuda.synchronize()
+print("sanitize target ran: distill %.4f, step loss %.5f" % (float(s), float(loss)))
+PY
