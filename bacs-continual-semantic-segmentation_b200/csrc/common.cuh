@@ -36,6 +36,33 @@ extern unsigned long long g_launch_count;
 
 int sm_count();
 
+// ---- programmatic dependent launch ---------------------------------------------------
+// The kernels of a training step run back to back on one stream.  Launched through launch_pdl() a kernel may become
+// resident while its predecessor drains: everything before pdl_wait() (shared-memory tables, barrier and tensor-memory
+// set-up, index arithmetic) overlaps the predecessor's tail; pdl_wait() returns once the predecessor has completed and
+// flushed, so every access to memory another kernel of the stream produces or still reads comes after it.  EVERY
+// thread of a kernel launched this way calls pdl_wait() exactly once before its first such access -- a kernel that
+// completed without waiting would let its own successor overtake the predecessor.  pdl_trigger() (optional) lets the
+// successor start becoming resident before this grid has exited.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- storage dtype <-> float ---------------------------------------------------------

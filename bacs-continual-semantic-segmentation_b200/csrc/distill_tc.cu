@@ -547,6 +547,8 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
     return seg * h + i;
   };
   const int it0 = range_start(blockIdx.x), it1 = (blockIdx.x + 1 == gridDim.x) ? P.total_items : range_start(blockIdx.x + 1);
+  pdl_wait();      // tables, barriers and tensor memory are set up while the kernel before this one drains
+  pdl_trigger();
   if (tid == 0) {
     P.bnd_info[2 * blockIdx.x] = it0;
     P.bnd_info[2 * blockIdx.x + 1] = it1;
@@ -1126,6 +1128,8 @@ __global__ void __launch_bounds__(256) distill_tc_finish_kernel(Params P, int nc
                                                                float* __restrict__ loss_scaled) {
   __shared__ double scratch[32];
   const int k = blockIdx.x;
+  pdl_wait();
+  pdl_trigger();
   if (k == 0) {
     double s = 0.0;
     for (int i = threadIdx.x; i < ncta; i += blockDim.x) s += P.partials[i];
@@ -1296,9 +1300,10 @@ int distill_tc_launch(const void* old_att, const void* new_att, int dtype, int B
       set_error("bacs_teacher_distill: shared memory opt-in failed: %s", cudaGetErrorString(e));                   \
       return BACS_ERR_CUDA;                                                                                         \
     }                                                                                                               \
-    kern<<<cfg.grid, dtc::kThreads, cfg.smem, s>>>(maps[0], maps[1], P);                                            \
+    launch_pdl(kern, dim3(cfg.grid), dim3(dtc::kThreads), cfg.smem, s, maps[0], maps[1], P);                        \
     BACS_CHECK_LAUNCH("bacs_teacher_distill(tensor cores)");                                                        \
-    dtc::distill_tc_finish_kernel<TT><<<cfg.grid, 256, 0, s>>>(P, cfg.grid, loss_sum, loss_scaled);                 \
+    launch_pdl(dtc::distill_tc_finish_kernel<TT>, dim3(cfg.grid), dim3(256), 0, s, P, (int)cfg.grid, loss_sum,     \
+               loss_scaled);                                                                                        \
     BACS_CHECK_LAUNCH("bacs_teacher_distill(finish)");                                                              \
   } while (0)
   BACS_DISPATCH_DTYPE(dtype, TT, BACS_DTC_LAUNCH(TT));

@@ -230,8 +230,10 @@ __global__ void __launch_bounds__(1024) downsample_task_kernel(const int64_t* __
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nwarp = blockDim.x >> 5;
-  for (int i = tid; i < 256; i += blockDim.x) lut[i] = task_lut[i];
   if (tid < kMaxTasks) base[tid] = 0;
+  pdl_wait();
+  pdl_trigger();
+  for (int i = tid; i < 256; i += blockDim.x) lut[i] = task_lut[i];
   __syncthreads();
   const int hw = h * w;
   const int64_t* src = labels + (int64_t)b * H * W;
@@ -334,8 +336,8 @@ int bacs_label_downsample_task(const int64_t* labels, int B, int H, int W, int h
   BACS_REQUIRE(B > 0 && H > 0 && W > 0 && h > 0 && w > 0, "bacs_label_downsample_task: bad shape");
   BACS_REQUIRE(T > 0 && T <= kMaxTasks, "bacs_label_downsample_task: T=%d not in [1,%d]", T, kMaxTasks);
   const float sy = (float)H / (float)h, sx = (float)W / (float)w;
-  downsample_task_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(labels, H, W, h, w, sy, sx, task_lut, T, labels_down,
-                                                               task, rank, n_bt);
+  launch_pdl(downsample_task_kernel, dim3(B), dim3(1024), 0, (cudaStream_t)stream, labels, H, W, h, w, sy, sx, task_lut, T,
+             labels_down, task, rank, n_bt);
   BACS_CHECK_LAUNCH("bacs_label_downsample_task");
   return BACS_OK;
 }

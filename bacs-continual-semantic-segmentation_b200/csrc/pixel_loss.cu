@@ -683,6 +683,8 @@ __global__ void __launch_bounds__(256) pixel_reduce_kernel(const double* __restr
   // thread (g, i): accumulator i of partial rows g, g+32, ... (a partial row is 64 contiguous bytes)
   const int i = threadIdx.x & 7, g = threadIdx.x >> 3;
   double s = 0.0;
+  pdl_wait();
+  pdl_trigger();
   for (int t = t0 + g; t < t1; t += 32) s += partials[(int64_t)t * BACS_NACC + i];
   s += __shfl_xor_sync(0xffffffffu, s, 8);
   s += __shfl_xor_sync(0xffffffffu, s, 16);
@@ -1032,7 +1034,7 @@ int bacs_pixel_loss_lowres(const bacs_pixel_args* a, int32_t lh, int32_t lw, voi
   ep.focal_weight = a->focal_weight;
   ep.loss_coef = a->loss_coef;
   ep.loss_over_wsum = a->loss_over_wsum;
-  pixel_reduce_kernel<<<nblk, 256, 0, s>>>(p.partials, plan.grid, plan.groups, a->acc, a->score,
+  launch_pdl(pixel_reduce_kernel, dim3(nblk), dim3(256), 0, s, p.partials, plan.grid, plan.groups, a->acc, a->score,
                                            1.0 / ((double)a->H * (double)a->W), ep);
   BACS_CHECK_LAUNCH("bacs_pixel_loss_lowres(reduce)");
   return BACS_OK;
@@ -1120,7 +1122,7 @@ int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_
     ep.focal_weight = a->focal_weight;
     ep.loss_coef = a->loss_coef;
     ep.loss_over_wsum = a->loss_over_wsum;
-    pixel_reduce_kernel<<<nblk, 256, 0, st>>>(q.partials, sp.blocks_x * a->B, sp.blocks_x, a->acc, a->score,
+    launch_pdl(pixel_reduce_kernel, dim3(nblk), dim3(256), 0, st, q.partials, sp.blocks_x * a->B, sp.blocks_x, a->acc, a->score,
                                               1.0 / ((double)a->H * (double)a->W), ep);
     BACS_CHECK_LAUNCH("bacs_pixel_loss(reduce)");
     return BACS_OK;
@@ -1219,7 +1221,7 @@ int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_
   ep.focal_weight = a->focal_weight;
   ep.loss_coef = a->loss_coef;
   ep.loss_over_wsum = a->loss_over_wsum;
-  pixel_reduce_kernel<<<nblk, 256, 0, s>>>(p.partials, (int)n_part, p.tiles_per_image, a->acc, a->score,
+  launch_pdl(pixel_reduce_kernel, dim3(nblk), dim3(256), 0, s, p.partials, (int)n_part, p.tiles_per_image, a->acc, a->score,
                                            1.0 / (double)HW, ep);
   BACS_CHECK_LAUNCH("bacs_pixel_loss(reduce)");
   return BACS_OK;

@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(kFastThreads, 2) pixel_wce_kernel(const __grid
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();      // the seen logits, the labels and the logits come from the kernels before this one
+  pdl_trigger();
 
   const int tiles_per_row = a.W / P;
   const bool tpr1 = tiles_per_row == 1;
@@ -549,7 +551,7 @@ static int launch_wce_one(const PixelParams& p, const PixelPlan& plan, cudaStrea
       return BACS_ERR_CUDA;
     }
   }
-  kern<<<plan.grid, kFastThreads, plan.smem, s>>>(p);
+  launch_pdl(kern, dim3(plan.grid), dim3(kFastThreads), plan.smem, s, p);
   return BACS_OK;
 }
 

@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(32 * kAccWarps) proto_accumulate_kernel(const 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int c = blockIdx.x * kAccWarps + wid;
+  pdl_wait();
+  pdl_trigger();
   if (c >= D) return;
   float* acc = s_acc + (size_t)wid * Tn * 64;
   for (int i = lane; i < Tn * 64; i += 32) acc[i] = 0.f;
@@ -92,6 +94,8 @@ __global__ void __launch_bounds__(32 * kAccWarps) proto_accumulate_vec_kernel(co
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int c = blockIdx.x * kAccWarps + wid;
+  pdl_wait();
+  pdl_trigger();
   if (wid == 0 && lane < Tn && mode == 0) {  // the same for all channels of the block: computed once
     long long pre = 0, tot = 0;
     for (int bb = 0; bb < B; ++bb) {
@@ -203,6 +207,8 @@ __global__ void __launch_bounds__(kFinRows* kFinLanes) proto_finalize_kernel(con
   __shared__ double s_red[kFinLanes][kFinRows];
   const int g = blockIdx.x;
   const int tid = threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
   for (int bb = tid; bb < B; bb += blockDim.x) s_nb[bb] = n_bt[bb * Tn + g];  // parallel loads, serial scan below
   __syncthreads();
   if (tid == 0) {
@@ -269,6 +275,8 @@ __global__ void __launch_bounds__(512) proto_update_kernel(float* __restrict__ p
   __shared__ int s_upd[64];
   __shared__ int s_nonzero;
   if (threadIdx.x == 0) s_nonzero = 0;
+  pdl_wait();
+  pdl_trigger();
   __syncthreads();
   if (threadIdx.x < Tn) {
     const int g = threadIdx.x;
@@ -347,16 +355,16 @@ int bacs_proto_accumulate(const void* features, int dtype, int B, int D, int h, 
           return BACS_ERR_CUDA;
         }
       }
-      kern<<<grid, 32 * kAccWarps, vec_smem, s>>>(reinterpret_cast<const TT*>(features), B, D, hw, task, rank, n_bt, T,
-                                                  mode, partial);
+      launch_pdl(kern, grid, dim3(32 * kAccWarps), vec_smem, s, reinterpret_cast<const TT*>(features), B, D, hw, task, rank,
+                 n_bt, T, mode, partial);
     } else {
-      proto_accumulate_kernel<TT><<<grid, 32 * kAccWarps, acc_smem, s>>>(reinterpret_cast<const TT*>(features), B, D,
-                                                                         hw, task, rank, n_bt, T, mode, partial);
+      launch_pdl(proto_accumulate_kernel<TT>, grid, dim3(32 * kAccWarps), acc_smem, s,
+                 reinterpret_cast<const TT*>(features), B, D, hw, task, rank, n_bt, T, mode, partial);
     }
   });
   BACS_CHECK_LAUNCH("bacs_proto_accumulate");
-  proto_finalize_kernel<<<dim3(T, (D + kFinRows - 1) / kFinRows), kFinRows * kFinLanes, 0, s>>>(partial, B, D, n_bt, T,
-                                                                                                 mode, sums, counts);
+  launch_pdl(proto_finalize_kernel, dim3(T, (D + kFinRows - 1) / kFinRows), dim3(kFinRows * kFinLanes), 0, s, partial, B, D,
+             n_bt, T, mode, sums, counts);
   BACS_CHECK_LAUNCH("bacs_proto_accumulate(finalize)");
   return BACS_OK;
 }
@@ -365,7 +373,8 @@ int bacs_proto_update(float* proto, void* count, int count_is_int64, const doubl
                       int D, int32_t* ready, bacs_stream_t stream) {
   BACS_REQUIRE(proto && count && sums && counts, "bacs_proto_update: null pointer");
   BACS_REQUIRE(T > 0 && T <= 64 && D > 0, "bacs_proto_update: bad shape");
-  proto_update_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(proto, count, count_is_int64, sums, counts, T, D, ready);
+  launch_pdl(proto_update_kernel, dim3(1), dim3(512), 0, (cudaStream_t)stream, proto, count, count_is_int64, sums, counts, T, D,
+             ready);
   BACS_CHECK_LAUNCH("bacs_proto_update");
   return BACS_OK;
 }

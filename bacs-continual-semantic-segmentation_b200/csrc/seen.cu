@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(32 * kSeenWarps, (TMAX * PX <= 32 ? 3 : (TMAX 
   for (int i = 0; i < PX; ++i)
 #pragma unroll
     for (int t = 0; t < TMAX; ++t) acc[i][t] = 0.f;
+  pdl_wait();
+  pdl_trigger();
   const T* base = feat + (int64_t)b * D * hw + q0;
   const bool live = q0 < hw;  // hw is a multiple of PX: a lane's pixels are all inside or all outside
   for (int c0 = c_begin; c0 < c_end; c0 += chunk) {
@@ -392,13 +394,15 @@ int bacs_seen_logits(const void* features, int dtype, int B, int D, int h, int w
   cfg.blockDim = dim3(32 * kSeenWarps);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
 #define LAUNCH_Z(TT, TM, PXV)                                                                                     \
   do {                                                                                                            \
     auto kern = seen_logits_kernel<TT, TM, PXV>;                                                                  \
