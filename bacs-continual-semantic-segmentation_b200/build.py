@@ -57,7 +57,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("BACS_NVCC_EXTRA", "").split(), "-I", INCLUDE, "-I", CSRC, "-c",
+               os.path.join(CSRC, src), "-o", obj]      # BACS_NVCC_EXTRA: diagnostics builds (-DBACS_DTC_PROFILE ...)
         if src == "class_distance.cu":
             cut = _cutlass_root()
             if cut:

@@ -139,6 +139,15 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
                "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
                : "memory");
 }
+// the same with the descriptor as two words: stepping the start address is one 32-bit add on the low word
+__device__ __forceinline__ void umma_tf32_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc,
+                                              uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 d;\nmov.b64 d, {%2, %3};\nsetp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], d, %4, p;\n}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
 // K-major, no swizzle: element (n, k) at (n/8)*sbo + (n%8)*16 + (k/4)*lbo + (k%4)*4 bytes (tools/ubench/umma_probe.cu)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
@@ -1041,6 +1050,10 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
           PROF_MARK(8);
           PROF_WAIT(1, &bars[BAR_BFULL + slot], (job / kRing) & 1);
           const uint32_t sb = ring + slot * kSlotBytes;
+          // descriptor of k-step s: start address + s * 1024 bytes (the address field counts 16-byte units; the ring
+          // lies below 256 KB, so the 14-bit field never carries)
+          const uint64_t bd0 = make_desc(sb, 512, 128);
+          const uint32_t bd_lo = (uint32_t)bd0, bd_hi = (uint32_t)(bd0 >> 32);
           for (int wg = 0; wg < 2; ++wg) {
             const int buf = c & 1;
             PROF_WAIT(2, &bars[BAR_VFULL + 2 * wg + buf], (n_unit * (uint32_t)(NCH >> 1) + (uint32_t)(c >> 1)) & 1);
@@ -1051,11 +1064,10 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
               if (!(P.knock & 2))
 #pragma unroll
               for (int s = 0; s < 7; ++s) {
-                const uint64_t bd = make_desc(sb + s * 1024, 512, 128);
-                umma_tf32_ts(tw + kColDS, va + 8 * s, bd, id32, (c | s) != 0);          // Vhi * [Bhi | Blo]
+                umma_tf32_ts2(tw + kColDS, va + 8 * s, bd_lo + s * 64, bd_hi, id32, (c | s) != 0);   // Vhi * [Bhi | Blo]
                 // Vlo * Bhi joins the other small product: the main accumulator (columns 0..15) sees one addition per
                 // k-step only, which halves the bias of the tensor core's truncating fp32 accumulation
-                umma_tf32_ts(tw + kColDS + kRows, va + kPairK + 8 * s, bd, id16, 1);
+                umma_tf32_ts2(tw + kColDS + kRows, va + kPairK + 8 * s, bd_lo + s * 64, bd_hi, id16, 1);
               }
               umma_commit(&bars[BAR_VFREE + 2 * wg + buf]);
               if (c == NCH - 1) umma_commit(&bars[BAR_SFULL + wg]);
@@ -1075,6 +1087,8 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
           PROF_MARK(9);
           PROF_WAIT(3, &bars[BAR_BFULL + slot], (job / kRing) & 1);
           const uint32_t sb = ring + slot * kSlotBytes;
+          const uint64_t gd0 = make_desc(sb, kBwdLbo, 128);
+          const uint32_t gd_lo = (uint32_t)gd0, gd_hi = (uint32_t)(gd0 >> 32);
           for (int wg = 0; wg < 2; ++wg) {
             const int buf = g & 1;
             if (g == 0) PROF_WAIT(4, &bars[BAR_RFULL + wg], n_unit & 1);
@@ -1086,11 +1100,10 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
               if (!(P.knock & 2))
 #pragma unroll
               for (int t = 0; t < 2; ++t) {
-                const uint64_t bh = make_desc(sb + t * 2 * kBwdLbo, kBwdLbo, 128);
-                const uint64_t bl = make_desc(sb + kBwdHalf + t * 2 * kBwdLbo, kBwdLbo, 128);
-                umma_tf32_ts(dv, rs + 8 * t, bh, id112, t != 0);       // rs_hi * Bhi
-                umma_tf32_ts(dv, rs + 8 * t, bl, id112, 1);            // rs_hi * Blo
-                umma_tf32_ts(dv, rs + kRows + 8 * t, bh, id112, 1);    // rs_lo * Bhi
+                const uint32_t bh = gd_lo + t * (2 * kBwdLbo / 16), bl = bh + kBwdHalf / 16;
+                umma_tf32_ts2(dv, rs + 8 * t, bh, gd_hi, id112, t != 0);       // rs_hi * Bhi
+                umma_tf32_ts2(dv, rs + 8 * t, bl, gd_hi, id112, 1);            // rs_hi * Blo
+                umma_tf32_ts2(dv, rs + kRows + 8 * t, bh, gd_hi, id112, 1);    // rs_lo * Bhi
               }
               umma_commit(&bars[BAR_WREADY + 2 * wg + buf]);
             }
