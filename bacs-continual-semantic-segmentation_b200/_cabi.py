@@ -44,8 +44,11 @@ _SIGNATURES = {
     "bacs_label_downsample_task": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp]),
     "bacs_proto_workspace_bytes": (sz, [i32, i32, i32]),
     "bacs_proto_accumulate": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, sz, vp]),
+    "bacs_proto_accumulate_update": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, sz, vp, vp, i32,
+                                           vp, vp]),
     "bacs_proto_update": (i32, [vp, vp, i32, vp, vp, i32, i32, vp, vp]),
     "bacs_seen_logits": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
+    "bacs_seen_logits_heads": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
     "bacs_seen_upsample": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "bacs_seen_head_backward": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "bacs_focal_scale": (i32, [vp, vp, f32, vp, vp, vp]),
@@ -57,6 +60,7 @@ _SIGNATURES = {
     "bacs_pixel_loss_lowres": (i32, [C.POINTER(PixelArgs), i32, i32, vp, sz, vp]),
     "bacs_distill_workspace_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
     "bacs_teacher_distill": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, f32, vp, vp, vp, vp, sz, vp]),
+    "bacs_teacher_distill_add": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, f32, vp, vp, vp, vp, vp, sz, vp]),
     "bacs_distill_set_mode": (i32, [i32]),
     "bacs_distill_kernel_variant": (i32, [i32, i32, i32, i32, i32, i32, i32]),
     "bacs_der_workspace_bytes": (sz, [i32, i32, i32]),

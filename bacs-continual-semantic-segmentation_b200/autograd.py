@@ -99,7 +99,7 @@ class PixelLossFunction(torch.autograd.Function):
             focal_gamma=cfg.get("focal_gamma", 2.0), focal_alpha=cfg.get("focal_alpha"),
             lkd_threshold=cfg.get("lkd_threshold", 0.5), ignore_index=cfg.get("ignore_index", 255),
             grad_scale=cfg.get("loss_scale", 1.0), seen_scale=cfg.get("seen_scale", 16),
-            seen_max=cfg.get("seen_max"), epilogue=epilogue, lowres=lowres)
+            seen_max=cfg.get("seen_max"), epilogue=epilogue, lowres=lowres, gz=cfg.get("gz") if has_focal else None)
         acc = out["acc"]
         loss = out["loss"].reshape(())
         dweight = dbias = dfeat = None
@@ -152,19 +152,22 @@ class TeacherDistillFunction(torch.autograd.Function):
     """lkd * mean_{b,a,y} || m * (U(old)^2 - U(new)^2) ||_2 over x (bacs_loss.py:258-294)."""
 
     @staticmethod
-    def forward(ctx, new_att, old_att, mask_u8, out_hw, lkd: float):
+    def forward(ctx, new_att, old_att, mask_u8, out_hw, lkd: float, addend=None):
+        """``addend`` (optional fp32 scalar tensor, e.g. the loss terms computed before this one): the result is
+        addend + distillation term, written by the kernel's own reduction launch (no separate add)."""
         B, A, h, w = new_att.shape
         H, W = out_hw
         coef = float(lkd) / float(B * A * H)
         _, dnew, loss = ops.teacher_distill(old_att.detach(), new_att.detach(), mask_u8, (H, W), coef,
-                                            ctx.needs_input_grad[0], want_scaled=True)
+                                            ctx.needs_input_grad[0], want_scaled=True,
+                                            addend=None if addend is None else addend.detach())
         ctx.dnew = dnew
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, g):
         dnew = _take(ctx, "dnew")
-        return _scaled(dnew, g), None, None, None, None
+        return _scaled(dnew, g), None, None, None, None, (g if ctx.needs_input_grad[5] else None)
 
 
 class DerMseFunction(torch.autograd.Function):

@@ -577,14 +577,15 @@ __global__ void __launch_bounds__(32 * kDistillWarps, (CPL <= 2 ? 2 : 1)) distil
 
 __global__ void __launch_bounds__(1024) sum_partials_kernel(const double* __restrict__ partials, int n,
                                                             double* __restrict__ out, float coef,
-                                                            float* __restrict__ out_scaled) {
+                                                            float* __restrict__ out_scaled,
+                                                            const float* __restrict__ addend) {
   __shared__ double scratch[32];
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += partials[i];
   s = block_sum(s, scratch);
   if (threadIdx.x == 0) {
     out[0] = s;
-    if (out_scaled) out_scaled[0] = (float)((double)coef * s);
+    if (out_scaled) out_scaled[0] = (float)((double)coef * s) + (addend ? addend[0] : 0.f);
   }
 }
 
@@ -618,8 +619,8 @@ static DistillLayout distill_layout(int B, int A, int h, int w, int H, int W) {
 bool distill_tc_shape_ok(int dtype, int B, int A, int h, int w, int H, int W);
 size_t distill_tc_workspace_bytes(int dtype, int B, int A, int h, int w, int H, int W);
 int distill_tc_launch(const void* old_att, const void* new_att, int dtype, int B, int A, int h, int w, const uint8_t* mask, int H,
-                      int W, float grad_coef, double* loss_sum, float* loss_scaled, void* dnew, void* workspace,
-                      size_t workspace_bytes, cudaStream_t s);
+                      int W, float grad_coef, double* loss_sum, float* loss_scaled, const float* addend, void* dnew,
+                      void* workspace, size_t workspace_bytes, cudaStream_t s);
 static int g_distill_mode = 0;  // 0: tensor cores where they apply, 1: FMA kernel only, 2: tensor cores or error
 
 }  // namespace bacs
@@ -647,14 +648,15 @@ int bacs_distill_kernel_variant(int dtype, int B, int A, int h, int w, int H, in
   return (g_distill_mode != 1 && distill_tc_shape_ok(dtype, B, A, h, w, H, W)) ? 1 : 0;
 }
 
-int bacs_teacher_distill(const void* old_att, const void* new_att, int dtype, int B, int A, int h, int w,
-                         const uint8_t* mask, int H, int W, float grad_coef, double* loss_sum, float* loss_scaled, void* dnew,
-                         void* workspace, size_t workspace_bytes, bacs_stream_t stream) {
+static int teacher_distill_impl(const void* old_att, const void* new_att, int dtype, int B, int A, int h, int w,
+                                const uint8_t* mask, int H, int W, float grad_coef, double* loss_sum, float* loss_scaled,
+                                const float* addend, void* dnew, void* workspace, size_t workspace_bytes,
+                                bacs_stream_t stream) {
   BACS_REQUIRE(old_att && new_att && loss_sum && workspace, "bacs_teacher_distill: null pointer");
   BACS_REQUIRE(B > 0 && B < 65536 && A > 0 && h > 0 && w > 0, "bacs_teacher_distill: bad shape");
   BACS_REQUIRE(H >= h && W >= w, "bacs_teacher_distill: the mask must be at least as large as the attention map");
   if (g_distill_mode != 1) {
-    const int rc = distill_tc_launch(old_att, new_att, dtype, B, A, h, w, mask, H, W, grad_coef, loss_sum, loss_scaled, dnew,
+    const int rc = distill_tc_launch(old_att, new_att, dtype, B, A, h, w, mask, H, W, grad_coef, loss_sum, loss_scaled, addend, dnew,
                                      workspace, workspace_bytes, (cudaStream_t)stream);
     if (rc <= 0) return rc;  // done, or a real error
     if (g_distill_mode == 2) {
@@ -725,9 +727,25 @@ int bacs_teacher_distill(const void* old_att, const void* new_att, int dtype, in
   });
 #undef LAUNCH_DISTILL
   BACS_CHECK_LAUNCH("bacs_teacher_distill");
-  sum_partials_kernel<<<1, 1024, 0, s>>>(partials, grid, loss_sum, grad_coef, loss_scaled);
+  sum_partials_kernel<<<1, 1024, 0, s>>>(partials, grid, loss_sum, grad_coef, loss_scaled, addend);
   BACS_CHECK_LAUNCH("bacs_teacher_distill(reduce)");
   return BACS_OK;
+}
+
+int bacs_teacher_distill(const void* old_att, const void* new_att, int dtype, int B, int A, int h, int w,
+                         const uint8_t* mask, int H, int W, float grad_coef, double* loss_sum, float* loss_scaled, void* dnew,
+                         void* workspace, size_t workspace_bytes, bacs_stream_t stream) {
+  return teacher_distill_impl(old_att, new_att, dtype, B, A, h, w, mask, H, W, grad_coef, loss_sum, loss_scaled, nullptr, dnew,
+                              workspace, workspace_bytes, stream);
+}
+
+int bacs_teacher_distill_add(const void* old_att, const void* new_att, int dtype, int B, int A, int h, int w,
+                             const uint8_t* mask, int H, int W, float grad_coef, double* loss_sum, float* loss_scaled,
+                             const float* addend, void* dnew, void* workspace, size_t workspace_bytes,
+                             bacs_stream_t stream) {
+  BACS_REQUIRE(loss_scaled && addend, "bacs_teacher_distill_add: null pointer");
+  return teacher_distill_impl(old_att, new_att, dtype, B, A, h, w, mask, H, W, grad_coef, loss_sum, loss_scaled, addend, dnew,
+                              workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -1138,7 +1138,8 @@ __global__ void __launch_bounds__(kThreads, 1) distill_tc_kernel(const __grid_co
 // independent) and reduces the loss partials in a fixed order.
 template <typename T>
 __global__ void __launch_bounds__(256) distill_tc_finish_kernel(Params P, int ncta, double* __restrict__ loss_sum,
-                                                               float* __restrict__ loss_scaled) {
+                                                               float* __restrict__ loss_scaled,
+                                                               const float* __restrict__ addend) {
   __shared__ double scratch[32];
   const int k = blockIdx.x;
   pdl_wait();
@@ -1149,7 +1150,7 @@ __global__ void __launch_bounds__(256) distill_tc_finish_kernel(Params P, int nc
     s = block_sum(s, scratch);
     if (threadIdx.x == 0) {
       loss_sum[0] = s;
-      if (loss_scaled) loss_scaled[0] = (float)((double)P.grad_coef * s);
+      if (loss_scaled) loss_scaled[0] = (float)((double)P.grad_coef * s) + (addend ? addend[0] : 0.f);
     }
   }
   if (!P.want_grad) return;
@@ -1256,8 +1257,8 @@ size_t distill_tc_workspace_bytes(int dtype, int B, int A, int h, int w, int H, 
 
 // returns BACS_OK, an error, or +1 when the tensor-core path does not apply to these arguments (caller falls back)
 int distill_tc_launch(const void* old_att, const void* new_att, int dtype, int B, int A, int h, int w, const uint8_t* mask, int H,
-                      int W, float grad_coef, double* loss_sum, float* loss_scaled, void* dnew, void* workspace,
-                      size_t workspace_bytes, cudaStream_t s) {
+                      int W, float grad_coef, double* loss_sum, float* loss_scaled, const float* addend, void* dnew,
+                      void* workspace, size_t workspace_bytes, cudaStream_t s) {
   DtcConfig cfg;
   DtcEncodeTiledFn enc = dtc_encode_fn();
   if (!enc || !dtc_config(dtype, B, A, h, w, H, W, &cfg)) return 1;
@@ -1316,7 +1317,7 @@ int distill_tc_launch(const void* old_att, const void* new_att, int dtype, int B
     launch_pdl(kern, dim3(cfg.grid), dim3(dtc::kThreads), cfg.smem, s, maps[0], maps[1], P);                        \
     BACS_CHECK_LAUNCH("bacs_teacher_distill(tensor cores)");                                                        \
     launch_pdl(dtc::distill_tc_finish_kernel<TT>, dim3(cfg.grid), dim3(256), 0, s, P, (int)cfg.grid, loss_sum,     \
-               loss_scaled);                                                                                        \
+               loss_scaled, addend);                                                                                \
     BACS_CHECK_LAUNCH("bacs_teacher_distill(finish)");                                                              \
   } while (0)
   BACS_DISPATCH_DTYPE(dtype, TT, BACS_DTC_LAUNCH(TT));

@@ -21,13 +21,18 @@ __global__ void __launch_bounds__(32 * kAccWarps) proto_accumulate_kernel(const 
                                                                           const int32_t* __restrict__ rank,
                                                                           const int32_t* __restrict__ n_bt, int Tn,
                                                                           int mode,
-                                                                          float* __restrict__ partial /* [B,D,Tn,2] */) {
+                                                                          float* __restrict__ partial /* [B,D,Tn,2] */,
+                                                                          const void* __restrict__ count_raw, int count_is_int64,
+                                                                          unsigned long long* __restrict__ count_snap) {
   extern __shared__ float s_acc[];  // [warp][Tn][2][32]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int c = blockIdx.x * kAccWarps + wid;
   pdl_wait();
   pdl_trigger();
+  if (count_snap && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < Tn)
+    count_snap[threadIdx.x] = count_is_int64 ? reinterpret_cast<const unsigned long long*>(count_raw)[threadIdx.x]
+                                             : (unsigned long long)reinterpret_cast<const unsigned*>(count_raw)[threadIdx.x];
   if (c >= D) return;
   float* acc = s_acc + (size_t)wid * Tn * 64;
   for (int i = lane; i < Tn * 64; i += 32) acc[i] = 0.f;
@@ -87,7 +92,9 @@ __global__ void __launch_bounds__(32 * kAccWarps) proto_accumulate_vec_kernel(co
                                                                               int hw, const int8_t* __restrict__ task,
                                                                               const int32_t* __restrict__ rank,
                                                                               const int32_t* __restrict__ n_bt, int Tn,
-                                                                              int mode, float* __restrict__ partial) {
+                                                                              int mode, float* __restrict__ partial,
+                                                                              const void* __restrict__ count_raw, int count_is_int64,
+                                                                              unsigned long long* __restrict__ count_snap) {
   extern __shared__ float s_acc[];  // [warp][Tn*2][33] | [warp][32] split points
   __shared__ long long s_pre[32], s_tot[32];  // per task: masked pixels in the images before b / in all images
   __shared__ int s_nb[32];
@@ -96,6 +103,11 @@ __global__ void __launch_bounds__(32 * kAccWarps) proto_accumulate_vec_kernel(co
   const int c = blockIdx.x * kAccWarps + wid;
   pdl_wait();
   pdl_trigger();
+  // fused update: the finalize launch reads the counts of BEFORE the step from this snapshot while one of its blocks
+  // already writes the new ones (8 bytes per task whatever the count type; a float count sits in the low word)
+  if (count_snap && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < Tn)
+    count_snap[threadIdx.x] = count_is_int64 ? reinterpret_cast<const unsigned long long*>(count_raw)[threadIdx.x]
+                                             : (unsigned long long)reinterpret_cast<const unsigned*>(count_raw)[threadIdx.x];
   if (wid == 0 && lane < Tn && mode == 0) {  // the same for all channels of the block: computed once
     long long pre = 0, tot = 0;
     for (int bb = 0; bb < B; ++bb) {
@@ -200,7 +212,11 @@ __global__ void __launch_bounds__(kFinRows* kFinLanes) proto_finalize_kernel(con
                                                                             int D, const int32_t* __restrict__ n_bt,
                                                                             int Tn, int mode,
                                                                             double* __restrict__ sums,
-                                                                            double* __restrict__ counts) {
+                                                                            double* __restrict__ counts,
+                                                                            float* __restrict__ proto, void* __restrict__ count,
+                                                                            int count_is_int64,
+                                                                            const unsigned long long* __restrict__ count_snap,
+                                                                            int32_t* __restrict__ ready) {
   __shared__ long long s_pre[kFinMaxB];
   __shared__ int s_nb[kFinMaxB], s_lo[kFinMaxB], s_hi[kFinMaxB];
   __shared__ long long s_tot;
@@ -222,6 +238,39 @@ __global__ void __launch_bounds__(kFinRows* kFinLanes) proto_finalize_kernel(con
   }
   __syncthreads();
   const long long tot = s_tot;
+  // fused running-mean update (prototypes.py:158-163; the arithmetic of proto_update_kernel): old count from the snapshot
+  float upd_old = 0.f, upd_den = 1.f;
+  if (proto) {
+    if (count_is_int64) {
+      const long long o = (long long)count_snap[g];
+      upd_old = (float)o;
+      upd_den = (float)(o + tot);
+      if (tid == 0 && blockIdx.y == 0 && tot > 0) reinterpret_cast<long long*>(count)[g] = o + tot;
+    } else {
+      const float o = __uint_as_float((unsigned)count_snap[g]);
+      upd_old = o;
+      upd_den = __fadd_rn(o, (float)(double)tot);
+      if (tid == 0 && blockIdx.y == 0 && tot > 0) reinterpret_cast<float*>(count)[g] = upd_den;
+    }
+    if (ready && g == 0 && blockIdx.y == 0 && tid < 32) {   // all counts non-zero after the update (prototypes.py:31-40)
+      int nz = 1;
+      for (int t = tid; t < Tn; t += 32) {
+        long long n = 0;
+        for (int bb = 0; bb < B; ++bb) n += n_bt[bb * Tn + t];
+        bool nonzero;
+        if (count_is_int64) {
+          const long long o = (long long)count_snap[t];
+          nonzero = (n > 0 ? o + n : o) != 0;
+        } else {
+          const float o = __uint_as_float((unsigned)count_snap[t]);
+          nonzero = (n > 0 ? __fadd_rn(o, (float)(double)n) : o) != 0.f;
+        }
+        nz &= nonzero ? 1 : 0;
+      }
+      nz = __all_sync(0xffffffffu, nz);
+      if (tid == 0) *ready = nz;
+    }
+  }
   if (mode == 0 && tot > 0)
     for (int bb = tid; bb < B; bb += blockDim.x) {
       s_lo[bb] = (int)(((long long)D * s_pre[bb]) / tot);
@@ -262,6 +311,10 @@ __global__ void __launch_bounds__(kFinRows* kFinLanes) proto_finalize_kernel(con
 #pragma unroll
     for (int i = 0; i < kFinLanes; ++i) t += s_red[i][rl];  // fixed order: deterministic
     sums[(int64_t)g * D + r] = t;
+    if (proto && tot > 0) {
+      const int64_t i = (int64_t)g * D + r;
+      proto[i] = __fdiv_rn(__fadd_rn((float)t, __fmul_rn(upd_old, proto[i])), upd_den);
+    }
   }
 }
 
@@ -323,12 +376,13 @@ using namespace bacs;
 extern "C" {
 
 size_t bacs_proto_workspace_bytes(int B, int D, int T) {
-  return align_up((size_t)B * D * T * 2 * sizeof(float), 256);
+  return align_up((size_t)B * D * T * 2 * sizeof(float), 256) + 256;   // partial sums | snapshot of the counts
 }
 
-int bacs_proto_accumulate(const void* features, int dtype, int B, int D, int h, int w, const int8_t* task,
-                          const int32_t* rank, const int32_t* n_bt, int T, int mode, double* sums, double* counts,
-                          void* workspace, size_t workspace_bytes, bacs_stream_t stream) {
+static int proto_accumulate_impl(const void* features, int dtype, int B, int D, int h, int w, const int8_t* task,
+                                 const int32_t* rank, const int32_t* n_bt, int T, int mode, double* sums, double* counts,
+                                 void* workspace, size_t workspace_bytes, float* proto, void* count, int count_is_int64,
+                                 int32_t* ready, bacs_stream_t stream) {
   BACS_REQUIRE(features && task && rank && n_bt && sums && counts && workspace, "bacs_proto_accumulate: null pointer");
   BACS_REQUIRE(B > 0 && D > 0 && h > 0 && w > 0 && B <= kFinMaxB, "bacs_proto_accumulate: bad shape (B <= 1024)");
   BACS_REQUIRE(T > 0 && T <= 32, "bacs_proto_accumulate: T=%d not in [1,32]", T);
@@ -339,6 +393,10 @@ int bacs_proto_accumulate(const void* features, int dtype, int B, int D, int h, 
   }
   cudaStream_t s = (cudaStream_t)stream;
   float* partial = reinterpret_cast<float*>(workspace);
+  unsigned long long* snap = proto ? reinterpret_cast<unsigned long long*>(
+                                         reinterpret_cast<char*>(workspace) + align_up((size_t)B * D * T * 2 * sizeof(float), 256))
+                                   : nullptr;
+  const void* count_raw = count;
   const int hw = h * w;
   dim3 grid((D + kAccWarps - 1) / kAccWarps, B);
   const size_t acc_smem = (size_t)kAccWarps * T * 64 * sizeof(float);
@@ -356,17 +414,34 @@ int bacs_proto_accumulate(const void* features, int dtype, int B, int D, int h, 
         }
       }
       launch_pdl(kern, grid, dim3(32 * kAccWarps), vec_smem, s, reinterpret_cast<const TT*>(features), B, D, hw, task, rank,
-                 n_bt, T, mode, partial);
+                 n_bt, T, mode, partial, count_raw, count_is_int64, snap);
     } else {
       launch_pdl(proto_accumulate_kernel<TT>, grid, dim3(32 * kAccWarps), acc_smem, s,
-                 reinterpret_cast<const TT*>(features), B, D, hw, task, rank, n_bt, T, mode, partial);
+                 reinterpret_cast<const TT*>(features), B, D, hw, task, rank, n_bt, T, mode, partial, count_raw, count_is_int64, snap);
     }
   });
   BACS_CHECK_LAUNCH("bacs_proto_accumulate");
   launch_pdl(proto_finalize_kernel, dim3(T, (D + kFinRows - 1) / kFinRows), dim3(kFinRows * kFinLanes), 0, s, partial, B, D,
-             n_bt, T, mode, sums, counts);
+             n_bt, T, mode, sums, counts, proto, count, count_is_int64, (const unsigned long long*)snap, ready);
   BACS_CHECK_LAUNCH("bacs_proto_accumulate(finalize)");
   return BACS_OK;
+}
+
+int bacs_proto_accumulate(const void* features, int dtype, int B, int D, int h, int w, const int8_t* task,
+                          const int32_t* rank, const int32_t* n_bt, int T, int mode, double* sums, double* counts,
+                          void* workspace, size_t workspace_bytes, bacs_stream_t stream) {
+  return proto_accumulate_impl(features, dtype, B, D, h, w, task, rank, n_bt, T, mode, sums, counts, workspace,
+                               workspace_bytes, nullptr, nullptr, 0, nullptr, stream);
+}
+
+int bacs_proto_accumulate_update(const void* features, int dtype, int B, int D, int h, int w, const int8_t* task,
+                                 const int32_t* rank, const int32_t* n_bt, int T, int mode, double* sums, double* counts,
+                                 void* workspace, size_t workspace_bytes, float* proto, void* count, int count_is_int64,
+                                 int32_t* ready, bacs_stream_t stream) {
+  BACS_REQUIRE(proto && count, "bacs_proto_accumulate_update: null pointer");
+  BACS_REQUIRE(T <= 32, "bacs_proto_accumulate_update: T=%d not in [1,32]", T);
+  return proto_accumulate_impl(features, dtype, B, D, h, w, task, rank, n_bt, T, mode, sums, counts, workspace,
+                               workspace_bytes, proto, count, count_is_int64, ready, stream);
 }
 
 int bacs_proto_update(float* proto, void* count, int count_is_int64, const double* sums, const double* counts, int T,

@@ -49,6 +49,12 @@ __device__ __forceinline__ void load_px(const T* p, float* v) {
   }
 }
 
+// The heads as separate device arrays (the modules' own parameters: no gather launch in front of the kernel).
+struct HeadRows {
+  const float* w[32];
+  const float* b[32];
+};
+
 // A CTA covers 32*PX consecutive pixels of one image (lane -> PX adjacent pixels, one vector load per channel
 // row) and a slice of the channels; its 8 warps stride over the slice.  The CS CTAs of a thread-block cluster
 // split the channels and the leader adds their partial sums through distributed shared memory, so the grid
@@ -59,7 +65,8 @@ __global__ void __launch_bounds__(32 * kSeenWarps, (TMAX * PX <= 32 ? 3 : (TMAX 
                                                                        const float* __restrict__ proto,
                                                                        const float* __restrict__ weight,
                                                                        const float* __restrict__ bias, int Tn,
-                                                                       int chunk, int cs, float* __restrict__ z) {
+                                                                       int chunk, int cs, float* __restrict__ z,
+                                                                       const HeadRows rows, float* __restrict__ zero_out) {
   extern __shared__ __align__(16) float smem[];
   constexpr int PS = 32 * PX;            // pixels per CTA
   constexpr int stride = 2 * TMAX;       // floats per channel row: w[0..TMAX) | sigmoid(proto)[0..TMAX)
@@ -84,7 +91,7 @@ __global__ void __launch_bounds__(32 * kSeenWarps, (TMAX * PX <= 32 ? 3 : (TMAX 
     __syncthreads();
     for (int i = tid; i < TMAX * cn; i += 32 * kSeenWarps) {
       const int t = i / cn, c = i - t * cn;
-      smem[c * stride + t] = t < Tn ? weight[t * D + c0 + c] : 0.f;
+      smem[c * stride + t] = t < Tn ? (weight ? weight[t * D + c0 + c] : rows.w[t][c0 + c]) : 0.f;
       smem[c * stride + TMAX + t] = t < Tn ? sigmoid_fast(proto[t * D + c0 + c]) : 0.f;
     }
     __syncthreads();
@@ -163,12 +170,15 @@ __global__ void __launch_bounds__(32 * kSeenWarps, (TMAX * PX <= 32 ? 3 : (TMAX 
   }
   for (int e = tid; e < n_out; e += 32 * kSeenWarps) {
     const int t = e / PS, px = e - t * PS;
-    float s = bias[t];
+    float s = weight ? bias[t] : rows.b[t][0];
 #pragma unroll
     for (int g = 0; g < kSeenWarps; ++g) s += red[g * n_out + e];
     for (int r = 1; r < cs; ++r) s += xfer[(size_t)r * n_out + e];
     const int q = pb * PS + px;
-    if (q < hw) z[((int64_t)b * Tn + t) * hw + q] = s;
+    if (q < hw) {
+      z[((int64_t)b * Tn + t) * hw + q] = s;
+      if (zero_out && t == 0) zero_out[(int64_t)b * hw + q] = 0.f;   // accumulator of the following pixel kernel
+    }
   }
 }
 
@@ -364,9 +374,9 @@ using namespace bacs;
 
 extern "C" {
 
-int bacs_seen_logits(const void* features, int dtype, int B, int D, int h, int w, const float* proto,
-                     const float* weight, const float* bias, int T, float* z, bacs_stream_t stream) {
-  BACS_REQUIRE(features && proto && weight && bias && z, "bacs_seen_logits: null pointer");
+static int seen_logits_impl(const void* features, int dtype, int B, int D, int h, int w, const float* proto,
+                            const float* weight, const float* bias, const HeadRows& rows, int T, float* z,
+                            float* zero_out, bacs_stream_t stream) {
   BACS_REQUIRE(B > 0 && B < 65536 && D > 0 && h > 0 && w > 0, "bacs_seen_logits: bad shape");
   BACS_REQUIRE(T > 0 && T <= 32, "bacs_seen_logits: T=%d not in [1,32]", T);
   const int hw = h * w;
@@ -414,7 +424,7 @@ int bacs_seen_logits(const void* features, int dtype, int B, int D, int h, int w
       }                                                                                                           \
     }                                                                                                             \
     cudaError_t le = cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const TT*>(features), D, hw, proto, weight,  \
-                                        bias, T, chunk, cs, z);                                                   \
+                                        bias, T, chunk, cs, z, rows, zero_out);                                   \
     if (le != cudaSuccess) {                                                                                      \
       set_error("bacs_seen_logits: launch failed: %s", cudaGetErrorString(le));                                  \
       return BACS_ERR_CUDA;                                                                                       \
@@ -438,6 +448,27 @@ int bacs_seen_logits(const void* features, int dtype, int B, int D, int h, int w
 #undef LAUNCH_Z
   BACS_CHECK_LAUNCH("bacs_seen_logits");
   return BACS_OK;
+}
+
+int bacs_seen_logits(const void* features, int dtype, int B, int D, int h, int w, const float* proto,
+                     const float* weight, const float* bias, int T, float* z, bacs_stream_t stream) {
+  BACS_REQUIRE(features && proto && weight && bias && z, "bacs_seen_logits: null pointer");
+  HeadRows rows = {};
+  return seen_logits_impl(features, dtype, B, D, h, w, proto, weight, bias, rows, T, z, nullptr, stream);
+}
+
+int bacs_seen_logits_heads(const void* features, int dtype, int B, int D, int h, int w, const float* proto,
+                           const float* const* weight_rows_host, const float* const* bias_host, int T, float* z,
+                           float* zero_out, bacs_stream_t stream) {
+  BACS_REQUIRE(features && proto && weight_rows_host && bias_host && z, "bacs_seen_logits_heads: null pointer");
+  BACS_REQUIRE(T > 0 && T <= 32, "bacs_seen_logits_heads: T=%d not in [1,32]", T);
+  HeadRows rows = {};
+  for (int t = 0; t < T; ++t) {
+    BACS_REQUIRE(weight_rows_host[t] && bias_host[t], "bacs_seen_logits_heads: null head %d", t);
+    rows.w[t] = weight_rows_host[t];
+    rows.b[t] = bias_host[t];
+  }
+  return seen_logits_impl(features, dtype, B, D, h, w, proto, nullptr, nullptr, rows, T, z, zero_out, stream);
 }
 
 int bacs_seen_upsample(const float* z, int B, int T, int h, int w, int scale, int apply_sigmoid, float* out,

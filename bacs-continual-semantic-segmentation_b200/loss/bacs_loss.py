@@ -174,7 +174,7 @@ class BACSLoss(ExperienceReplay):
                                      return_attentions=with_distill)
         if with_distill:
             loss, preds_mask, old_attention, new_attention, seen_prob = out
-            loss = loss + self._teacher_distill(old_attention, new_attention, seen_prob, mask)
+            loss = self._teacher_distill(old_attention, new_attention, seen_prob, mask, _add_to=loss)
         else:
             loss, preds_mask = out
         preds_output = self._argmax(preds_mask)        # produced by the fused kernel, no second read
@@ -183,12 +183,13 @@ class BACSLoss(ExperienceReplay):
         join_side_stream()      # the seen-head backward forked by the pixel-loss op ran next to the distill chain
         return loss, preds_output
 
-    def _teacher_distill(self, old_attention, new_attention, seen_prob, mask):
+    def _teacher_distill(self, old_attention, new_attention, seen_prob, mask, _add_to=None):
         """bacs_loss.py:258-294.  ``seen_prob`` is the SeenMap handle produced by
         compute_base_loss (its distill mask came out of the fused pixel kernel), a plain
-        [B,T,H,W] probability tensor, or None."""
+        [B,T,H,W] probability tensor, or None.  ``_add_to`` (not in the reference): a loss tensor the term is added
+        to by the kernel's own reduction launch; the sum is returned."""
         if self.lkd == 0:
-            return 0
+            return 0 if _add_to is None else _add_to
         if isinstance(seen_prob, SeenMap) and seen_prob.distill_mask is not None:
             m = seen_prob.distill_mask
         elif seen_prob is None and self._fused_distill_mask is not None \
@@ -200,8 +201,11 @@ class BACSLoss(ExperienceReplay):
                 probs = seen_prob.materialize() if isinstance(seen_prob, SeenMap) else seen_prob
                 m = m & (probs.max(1)[0] > self.lkd_threshold)
             m = m.to(torch.uint8)
-        return TeacherDistillFunction.apply(new_attention[-1], old_attention[-1], m, tuple(mask.shape[-2:]),
-                                            float(self.lkd))
+        fuse = (_add_to is not None and torch.is_tensor(_add_to) and _add_to.is_cuda and _add_to.dtype == torch.float32
+                and _add_to.numel() == 1)
+        term = TeacherDistillFunction.apply(new_attention[-1], old_attention[-1], m, tuple(mask.shape[-2:]),
+                                            float(self.lkd), _add_to if fuse else None)
+        return term if (fuse or _add_to is None) else _add_to + term
 
     def _get_seen_detector(self, img, model, task_num=-1):
         """bacs_loss.py:296-306: full-res seen logits of one head (buffer population)."""

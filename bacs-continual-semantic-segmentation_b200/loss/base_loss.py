@@ -210,9 +210,23 @@ class BaseLoss:
         features = penultimate_output
         if wce_on or train_seen_detector:
             protos = self.prototypes
-            weight, bias = self._stack_heads(seen_net, protos.shape[0])
-            n_eval = weight.shape[0]
-            z = ops.seen_logits(penultimate_output.detach(), protos[:n_eval], weight, bias)
+            clf = seen_net.seen_not_seen_clf
+            heads = list(clf)[:protos.shape[0]] if isinstance(clf, torch.nn.ModuleList) else [clf]
+            params = [h.conv.weight for h in heads] + [h.conv.bias for h in heads]
+            if all(p.dtype == torch.float32 and p.is_cuda and p.is_contiguous() for p in params):
+                # the kernel reads the heads' own parameters (no gather launch) and clears the focal-gradient
+                # accumulator of the pixel kernel that follows (no fill launch)
+                n_eval = len(heads)
+                if train_seen_detector:
+                    cfg["gz"] = torch.empty((penultimate_output.shape[0],) + tuple(penultimate_output.shape[2:]),
+                                            dtype=torch.float32, device=penultimate_output.device)
+                z = ops.seen_logits_heads(penultimate_output.detach(), protos[:n_eval],
+                                          [p.detach() for p in params[:n_eval]], [p.detach() for p in params[n_eval:]],
+                                          zero_out=cfg.get("gz"))
+            else:
+                weight, bias = self._stack_heads(seen_net, protos.shape[0])
+                n_eval = weight.shape[0]
+                z = ops.seen_logits(penultimate_output.detach(), protos[:n_eval], weight, bias)
             cfg["z"] = z
             cfg["proto"] = protos
         if wce_on:

@@ -134,6 +134,11 @@ class Prototypes(BaseLoss):
                 self.ready_flag = reducer.allreduce(packed, self._prototypes_tensors, self._count_features, T, D)
                 return
             allreduce_packed(sums, counts)
+        elif self._count_features.is_contiguous():
+            # single process: the running-mean update rides on the finalize launch of the sums
+            self.ready_flag = ops.proto_accumulate_update(features, task, rank, n_bt, mode, self._prototypes_tensors,
+                                                          self._count_features)[2]
+            return
         else:
             sums, counts = ops.proto_accumulate(features, task, rank, n_bt, T, mode)
         self.ready_flag = ops.proto_update(self._prototypes_tensors, self._count_features, sums, counts)

@@ -123,6 +123,33 @@ def proto_accumulate(features: torch.Tensor, task: torch.Tensor, rank: torch.Ten
     return sums, counts
 
 
+def proto_accumulate_update(features: torch.Tensor, task: torch.Tensor, rank: torch.Tensor, n_bt: torch.Tensor, mode: int,
+                            proto: torch.Tensor, count: torch.Tensor,
+                            ready: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """proto_accumulate + proto_update without a launch of its own for the update (single-process step).
+    Returns (sums, counts, ready)."""
+    features = _cuda(features, "proto_accumulate_update")
+    proto = _cuda(proto, "proto_accumulate_update", torch.float32)
+    if not proto.is_contiguous() or not count.is_contiguous():
+        raise ValueError("proto_accumulate_update works in place: proto and count must be contiguous")
+    if count.dtype not in (torch.int64, torch.float32):
+        raise TypeError("proto_accumulate_update: count must be int64 or float32 (reference Q3)")
+    B, D, h, w = features.shape
+    T = proto.shape[0]
+    dev = features.device
+    packed = torch.empty(T * D + T, dtype=torch.float64, device=dev)
+    sums, counts = packed[:T * D].view(T, D), packed[T * D:T * D + T]
+    if ready is None:
+        ready = torch.empty(1, dtype=torch.int32, device=dev)
+    lib = _lib()
+    ws = _ws(lib.bacs_proto_workspace_bytes(B, D, T), dev)
+    check(lib.bacs_proto_accumulate_update(features.data_ptr(), _dt(features), B, D, h, w, task.data_ptr(), rank.data_ptr(),
+                                           n_bt.data_ptr(), T, mode, sums.data_ptr(), counts.data_ptr(), ws.data_ptr(),
+                                           ws.numel(), proto.data_ptr(), count.data_ptr(), int(count.dtype == torch.int64),
+                                           ready.data_ptr(), _stream()), "bacs_proto_accumulate_update")
+    return sums, counts, ready
+
+
 def proto_update(proto: torch.Tensor, count: torch.Tensor, sums: torch.Tensor, counts: torch.Tensor,
                  ready: Optional[torch.Tensor] = None) -> torch.Tensor:
     proto = _cuda(proto, "proto_update", torch.float32)
@@ -152,6 +179,32 @@ def seen_logits(features: torch.Tensor, proto: torch.Tensor, weight: torch.Tenso
     z = torch.empty((B, T, h, w), dtype=torch.float32, device=features.device)
     check(_lib().bacs_seen_logits(features.data_ptr(), _dt(features), B, D, h, w, proto.data_ptr(), weight.data_ptr(),
                                   bias.data_ptr(), T, z.data_ptr(), _stream()), "bacs_seen_logits")
+    return z
+
+
+def seen_logits_heads(features: torch.Tensor, proto: torch.Tensor, weights: Sequence[torch.Tensor],
+                      biases: Sequence[torch.Tensor], zero_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """seen_logits with the heads' own parameter tensors (fp32, contiguous: ``conv.weight`` [1,D,1,1] and ``conv.bias``
+    [1] of every head) instead of a stacked copy; ``zero_out`` fp32 [B,h,w] is cleared by the same launch."""
+    features = _cuda(features, "seen_logits_heads")
+    proto = _cuda(proto.float(), "seen_logits_heads")
+    B, D, h, w = features.shape
+    T = len(weights)
+    if T != len(biases) or T > proto.shape[0]:
+        raise ValueError("seen_logits_heads: %d weights, %d biases, %d prototypes" % (T, len(biases), proto.shape[0]))
+    for t in list(weights) + list(biases):
+        if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+            raise TypeError("seen_logits_heads: head parameters must be contiguous fp32 CUDA tensors")
+    if any(wt.numel() != D for wt in weights):
+        raise ValueError("seen_logits_heads: a head weight does not have D=%d entries" % D)
+    if zero_out is not None and (zero_out.dtype != torch.float32 or tuple(zero_out.shape) != (B, h, w)
+                                 or not zero_out.is_contiguous()):
+        raise ValueError("seen_logits_heads: zero_out must be a contiguous fp32 [B,h,w] tensor")
+    wp = (C.c_void_p * T)(*[wt.data_ptr() for wt in weights])
+    bp = (C.c_void_p * T)(*[bt.data_ptr() for bt in biases])
+    z = torch.empty((B, T, h, w), dtype=torch.float32, device=features.device)
+    check(_lib().bacs_seen_logits_heads(features.data_ptr(), _dt(features), B, D, h, w, proto.data_ptr(), wp, bp, T,
+                                        z.data_ptr(), _ptr(zero_out), _stream()), "bacs_seen_logits_heads")
     return z
 
 
@@ -213,13 +266,16 @@ def pixel_loss(logits: torch.Tensor, labels: torch.Tensor, mode: int, *, want_gr
                focal_alpha: Optional[float] = None, lkd_threshold: float = 0.5, ignore_index: int = 255,
                grad_scale: float = 1.0, seen_scale: int = 16, want_score: bool = False,
                seen_max: Optional[torch.Tensor] = None, epilogue: Optional[dict] = None,
-               lowres: bool = False) -> dict:
+               lowres: bool = False, gz: Optional[torch.Tensor] = None) -> dict:
     """``epilogue`` = {"ready": int32 [1] tensor or None, "focal_weight": float, "loss_coef": float,
     "over_wsum": bool}: the reduction launch also writes out["focal_scale"] and out["loss"] (fp32 [1]).
 
     ``lowres=True``: ``logits`` are the network's low-res ``sem_logits`` [B,K,lh,lw] (``return_sem_logits=True``,
     networks/deeplab_v3.py:155-156); the x16 / x8 bilinear up-sample (align_corners=False, deeplab_v3.py:157-160) and
-    its adjoint are evaluated inside the kernel, ``out["dlogits"]`` is d loss / d sem_logits."""
+    its adjoint are evaluated inside the kernel, ``out["dlogits"]`` is d loss / d sem_logits.
+
+    ``gz``: an already ZEROED fp32 [B,h,w] accumulator for the focal gradient (``seen_logits_heads(zero_out=...)`` clears
+    it in its own launch); allocated and cleared here when absent."""
     logits = _cuda(logits, "pixel_loss")
     labels = _cuda(labels, "pixel_loss", torch.int64)
     B, K = logits.shape[0], logits.shape[1]
@@ -246,7 +302,9 @@ def pixel_loss(logits: torch.Tensor, labels: torch.Tensor, mode: int, *, want_gr
         z = _cuda(z, "pixel_loss", torch.float32)
         a.T, a.h, a.w = z.shape[1], z.shape[2], z.shape[3]
         if focal_head >= 0:
-            out["gz"] = torch.zeros((B, a.h, a.w), dtype=torch.float32, device=dev)
+            if gz is not None and (gz.dtype != torch.float32 or tuple(gz.shape) != (B, a.h, a.w) or not gz.is_contiguous()):
+                raise ValueError("pixel_loss: gz must be a contiguous fp32 [B,h,w] tensor")
+            out["gz"] = gz if gz is not None else torch.zeros((B, a.h, a.w), dtype=torch.float32, device=dev)
     if seen_max is not None:
         seen_max = _cuda(seen_max.float(), "pixel_loss")
         if tuple(seen_max.shape) != (B, H, W):
@@ -307,8 +365,9 @@ def pixel_loss(logits: torch.Tensor, labels: torch.Tensor, mode: int, *, want_gr
 # teacher distillation / DER
 # --------------------------------------------------------------------------------------
 def teacher_distill(old_att: torch.Tensor, new_att: torch.Tensor, mask: Optional[torch.Tensor], out_hw,
-                    grad_coef: float, want_grad: bool, want_scaled: bool = False):
-    """-> (sum of row norms fp64 [1], grad_coef * d(sum)/d(new) or None[, grad_coef * sum as fp32 [1]])"""
+                    grad_coef: float, want_grad: bool, want_scaled: bool = False, addend: Optional[torch.Tensor] = None):
+    """-> (sum of row norms fp64 [1], grad_coef * d(sum)/d(new) or None[, grad_coef * sum as fp32 [1]])
+    ``addend`` (fp32 scalar on the device, with ``want_scaled``): the scaled output is addend + grad_coef * sum."""
     old_att = _cuda(old_att, "teacher_distill")
     new_att = _cuda(new_att, "teacher_distill")
     if old_att.dtype != new_att.dtype:
@@ -325,9 +384,17 @@ def teacher_distill(old_att: torch.Tensor, new_att: torch.Tensor, mask: Optional
     dnew = torch.empty_like(new_att) if want_grad else None
     lib = _lib()
     ws = _ws(lib.bacs_distill_workspace_bytes(B, A, h, w, H, W), dev)
-    check(lib.bacs_teacher_distill(old_att.data_ptr(), new_att.data_ptr(), _dt(new_att), B, A, h, w, _ptr(mask), H, W,
-                                   float(grad_coef), loss_sum.data_ptr(), _ptr(loss_scaled), _ptr(dnew), ws.data_ptr(),
-                                   ws.numel(), _stream()), "bacs_teacher_distill")
+    if addend is not None:
+        if not want_scaled or addend.dtype != torch.float32 or addend.numel() != 1 or not addend.is_cuda:
+            raise ValueError("teacher_distill: addend must be a CUDA fp32 scalar and needs want_scaled")
+        check(lib.bacs_teacher_distill_add(old_att.data_ptr(), new_att.data_ptr(), _dt(new_att), B, A, h, w, _ptr(mask), H,
+                                           W, float(grad_coef), loss_sum.data_ptr(), loss_scaled.data_ptr(),
+                                           addend.data_ptr(), _ptr(dnew), ws.data_ptr(), ws.numel(), _stream()),
+              "bacs_teacher_distill_add")
+    else:
+        check(lib.bacs_teacher_distill(old_att.data_ptr(), new_att.data_ptr(), _dt(new_att), B, A, h, w, _ptr(mask), H, W,
+                                       float(grad_coef), loss_sum.data_ptr(), _ptr(loss_scaled), _ptr(dnew), ws.data_ptr(),
+                                       ws.numel(), _stream()), "bacs_teacher_distill")
     if want_scaled:
         return loss_sum, dnew, loss_scaled
     return loss_sum, dnew

@@ -100,6 +100,14 @@ int bacs_proto_accumulate(const void* features, int dtype, int B, int D, int h, 
                           int mode, double* sums, double* counts, void* workspace,
                           size_t workspace_bytes, bacs_stream_t stream);
 
+/* bacs_proto_accumulate followed by bacs_proto_update in the same two launches (single-process training step: no
+ * exchange between the sums and the update; prototypes.py:127-163).  sums / counts are still written. */
+int bacs_proto_accumulate_update(const void* features, int dtype, int B, int D, int h, int w,
+                                 const int8_t* task, const int32_t* rank, const int32_t* n_bt, int T,
+                                 int mode, double* sums, double* counts, void* workspace,
+                                 size_t workspace_bytes, float* proto, void* count, int count_is_int64,
+                                 int32_t* ready, bacs_stream_t stream);
+
 /* Running-mean update proto[g] = (S[g] + cnt[g]*proto[g]) / (cnt[g] + N[g]); cnt[g] += N[g]
  * for rows with N[g] > 0 (prototypes.py:158-163), fp32 arithmetic like torch's.
  * count_is_int64: the reference keeps int64 counts at task 0 and float32 afterwards (Q3).
@@ -117,6 +125,15 @@ int bacs_proto_update(float* proto, void* count, int count_is_int64, const doubl
 int bacs_seen_logits(const void* features, int dtype, int B, int D, int h, int w,
                      const float* proto, const float* weight, const float* bias, int T,
                      float* z, bacs_stream_t stream);
+
+/* The same with the T heads given as they live in the model: HOST arrays of T device pointers (weight_rows_host[t] ->
+ * fp32[D], bias_host[t] -> fp32[1]; the nn.Conv2d parameters of bg_detector.py:17-40), so no gather launch precedes
+ * the kernel.  zero_out (optional, fp32[B,h,w]) is cleared by the same launch: it is the focal-gradient accumulator
+ * `gz` of the bacs_pixel_loss call that follows. */
+int bacs_seen_logits_heads(const void* features, int dtype, int B, int D, int h, int w,
+                           const float* proto, const float* const* weight_rows_host,
+                           const float* const* bias_host, int T, float* z, float* zero_out,
+                           bacs_stream_t stream);
 
 /* Materialised seen logits of the reference for callers that need the full-res map
  * (get_seen_map_task / get_seen_probs, bg_detector.py:100-165): out[b,t,Y,X] =
@@ -261,6 +278,12 @@ int bacs_teacher_distill(const void* old_att, const void* new_att, int dtype, in
                          int h, int w, const uint8_t* mask, int H, int W, float grad_coef,
                          double* loss_sum, float* loss_scaled, void* dnew, void* workspace,
                          size_t workspace_bytes, bacs_stream_t stream);
+/* The same with loss_scaled[0] = addend[0] + grad_coef * sum (addend: device fp32[1], e.g. the loss terms that precede
+ * the distillation term in BACSLoss.compute_loss, bacs_loss.py:250-253): the step's loss scalar without an add launch. */
+int bacs_teacher_distill_add(const void* old_att, const void* new_att, int dtype, int B, int A,
+                             int h, int w, const uint8_t* mask, int H, int W, float grad_coef,
+                             double* loss_sum, float* loss_scaled, const float* addend, void* dnew,
+                             void* workspace, size_t workspace_bytes, bacs_stream_t stream);
 
 /* ---------------------------------------------------------------------------------
  * Dark-experience-replay logit MSE with transplant (loss/bacs_loss.py:387-431)

@@ -138,6 +138,15 @@ def test_proto_accumulate_update(ops, synth, name, B, dtype):
         close(p_gpu, wp, what="proto")
         assert torch.equal(c_gpu.cpu(), wc)
         assert bool(ready.item()) == O.prototypes_ready(wc)
+        # the single-process step fuses the update into the finalize launch of the sums: identical bits
+        for mode in (0, 1):
+            s2, n2 = ops.proto_accumulate(pen.cuda(), task, rank, n_bt, cfg.T, mode)
+            p_sep, c_sep = proto.cuda(), cnt.cuda()
+            r_sep = ops.proto_update(p_sep, c_sep, s2, n2)
+            p_fus, c_fus = proto.cuda(), cnt.cuda()
+            s3, n3, r_fus = ops.proto_accumulate_update(pen.cuda(), task, rank, n_bt, mode, p_fus, c_fus)
+            assert torch.equal(s3, s2) and torch.equal(n3, n2)
+            assert torch.equal(p_fus, p_sep) and torch.equal(c_fus, c_sep) and int(r_fus.item()) == int(r_sep.item())
 
 
 def test_proto_no_foreground_is_noop(ops, synth):
@@ -152,6 +161,8 @@ def test_proto_no_foreground_is_noop(ops, synth):
     proto, cnt = inp.protos.clone().cuda(), torch.zeros(cfg.T).cuda()
     ready = ops.proto_update(proto, cnt, sums, counts)
     assert torch.equal(proto.cpu(), inp.protos) and int(ready.item()) == 0
+    _, _, ready2 = ops.proto_accumulate_update(inp.pen.cuda(), task, rank, n_bt, 0, proto, cnt)
+    assert torch.equal(proto.cpu(), inp.protos) and int(ready2.item()) == 0 and float(cnt.abs().sum()) == 0
 
 
 # --------------------------------------------------------------------------------------
@@ -166,6 +177,40 @@ def test_seen_logits_and_upsample(ops, synth, name, dtype):
     close(z, want, what="z")
     up = ops.seen_upsample(z, 16, apply_sigmoid=True)
     close(up, O.seen_probs(inp.pen.float(), inp.protos, inp.head_w, inp.head_b), what="seen probs")
+
+
+def test_seen_logits_from_head_parameters(ops, synth):
+    """bacs_seen_logits_heads: the heads as T separate parameter tensors, and the cleared accumulator"""
+    cfg = synth.CONFIGS["small"]
+    inp = synth.make_step_inputs(cfg, seed=2, dtype=torch.bfloat16)
+    pen, protos = inp.pen.cuda(), inp.protos.cuda()
+    ws = [inp.head_w[t].clone().reshape(1, -1, 1, 1).cuda() for t in range(cfg.T)]
+    bs = [inp.head_b[t].clone().reshape(1).cuda() for t in range(cfg.T)]
+    want = ops.seen_logits(pen, protos, inp.head_w.cuda(), inp.head_b.cuda())
+    gz = torch.full((cfg.B, cfg.h, cfg.w), 7.0, device="cuda")
+    got = ops.seen_logits_heads(pen, protos, ws, bs, zero_out=gz)
+    assert torch.equal(got, want) and float(gz.abs().sum()) == 0
+    got2 = ops.seen_logits_heads(pen, protos, ws[:2], bs[:2])               # fewer heads than prototypes
+    assert torch.equal(got2, want[:, :2])
+    with pytest.raises(TypeError):
+        ops.seen_logits_heads(pen, protos, [w.half() for w in ws], bs)
+
+
+def test_teacher_distill_adds_to_a_loss_scalar(ops, synth):
+    cfg = synth.CONFIGS["small"]
+    inp = synth.make_step_inputs(cfg, seed=2, dtype=torch.bfloat16)
+    old, new = inp.old_att.cuda(), inp.new_att.cuda()
+    m = (torch.rand(cfg.B, cfg.H, cfg.W, generator=torch.Generator().manual_seed(1)) > 0.4).to(torch.uint8).cuda()
+    base = torch.tensor(3.25, device="cuda")
+    for mode in (1, 0):                                                      # FMA kernel, then whatever the shape gets
+        ops.distill_set_mode(mode)
+        try:
+            _, d0, l0 = ops.teacher_distill(old, new, m, (cfg.H, cfg.W), 1e-3, True, want_scaled=True)
+            _, d1, l1 = ops.teacher_distill(old, new, m, (cfg.H, cfg.W), 1e-3, True, want_scaled=True, addend=base)
+        finally:
+            ops.distill_set_mode(0)
+        assert torch.equal(d0, d1)
+        assert float(l1) == float(torch.tensor(float(l0), dtype=torch.float32) + torch.tensor(3.25))
 
 
 def test_seen_head_backward(ops, synth):
