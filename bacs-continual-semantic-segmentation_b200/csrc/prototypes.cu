@@ -82,123 +82,140 @@ __global__ void __launch_bounds__(32 * kAccWarps) proto_accumulate_kernel(const 
   }
 }
 
-// Vectorised variant (hw a multiple of 8, 16-byte aligned rows): a lane handles 8 consecutive pixels per step.
-// The 8 task bytes are read first; feature and rank vectors are only fetched for groups that hold at least one
-// foreground pixel (labels are blocky: most groups of 8 are all background / ignore), and all of a row's
-// loads are in flight together.  The per-warp table has 33-float rows so that the final column sums are
-// conflict-free.
+// Vectorised variant (hw a multiple of 8, 16-byte aligned rows): a lane handles 8 consecutive pixels per step; task
+// bytes and features of a row's first step are requested before the split points are worked out.  The per-warp table
+// has one 32-float row per (task, low / high) entry: a lane only ever touches its own bank.
 template <typename T>
-__global__ void __launch_bounds__(32 * kAccWarps) proto_accumulate_vec_kernel(const T* __restrict__ feat, int B, int D,
-                                                                              int hw, const int8_t* __restrict__ task,
-                                                                              const int32_t* __restrict__ rank,
-                                                                              const int32_t* __restrict__ n_bt, int Tn,
-                                                                              int mode, float* __restrict__ partial,
-                                                                              const void* __restrict__ count_raw, int count_is_int64,
-                                                                              unsigned long long* __restrict__ count_snap) {
-  extern __shared__ float s_acc[];  // [warp][Tn*2][33] | [warp][32] split points
+__global__ void __launch_bounds__(32 * kAccWarps, 4) proto_accumulate_vec_kernel(const T* __restrict__ feat, int B, int D,
+                                                                                 int hw, const int8_t* __restrict__ task,
+                                                                                 const int32_t* __restrict__ rank,
+                                                                                 const int32_t* __restrict__ n_bt, int Tn,
+                                                                                 int mode, float* __restrict__ partial,
+                                                                                 const void* __restrict__ count_raw,
+                                                                                 int count_is_int64,
+                                                                                 unsigned long long* __restrict__ count_snap) {
+  extern __shared__ float s_acc[];  // [warp][Tn*2 + 2][32] | [warp][33] split points
   __shared__ long long s_pre[32], s_tot[32];  // per task: masked pixels in the images before b / in all images
   __shared__ int s_nb[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int c = blockIdx.x * kAccWarps + wid;
+  const bool live = c < D;
   pdl_wait();
   pdl_trigger();
+  // The row's first loads go out before anything else: task bytes, features and ranks of a step are all in flight
+  // together while the split points are worked out.
+  const T* row = feat + ((int64_t)b * D + (live ? c : 0)) * hw;
+  const int8_t* tk = task + (int64_t)b * hw;
+  const int32_t* rk = rank + (int64_t)b * hw;
+  const int items = hw >> 3;
+  constexpr int U = 4;
+  constexpr int NV = sizeof(T) == 4 ? 2 : 1;  // 16-byte vectors per 8 pixels
+  uint2 t8[U];
+  uint4 raw[U][NV];
+  int4 r0[U], r1[U];
+  auto load_step = [&](int it0) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int it = it0 + u * 32 + lane;
+      const bool ok = live && it < items;
+      t8[u] = ok ? *reinterpret_cast<const uint2*>(tk + it * 8) : make_uint2(0xffffffffu, 0xffffffffu);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) raw[u][k] = ok ? reinterpret_cast<const uint4*>(row + it * 8)[k] : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  auto load_ranks = [&](int it0) {   // shared by the D channel rows of the image: L2 hits, fetched after the split points
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int it = it0 + u * 32 + lane;
+      r0[u] = r1[u] = make_int4(0, 0, 0, 0);
+      if (mode == 0 && it < items) {
+        r0[u] = *reinterpret_cast<const int4*>(rk + it * 8);
+        r1[u] = *reinterpret_cast<const int4*>(rk + it * 8 + 4);
+      }
+    }
+  };
+  load_step(0);
   // fused update: the finalize launch reads the counts of BEFORE the step from this snapshot while one of its blocks
   // already writes the new ones (8 bytes per task whatever the count type; a float count sits in the low word)
   if (count_snap && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < Tn)
     count_snap[threadIdx.x] = count_is_int64 ? reinterpret_cast<const unsigned long long*>(count_raw)[threadIdx.x]
                                              : (unsigned long long)reinterpret_cast<const unsigned*>(count_raw)[threadIdx.x];
-  if (wid == 0 && lane < Tn && mode == 0) {  // the same for all channels of the block: computed once
-    long long pre = 0, tot = 0;
-    for (int bb = 0; bb < B; ++bb) {
-      const int n = n_bt[bb * Tn + lane];
-      if (bb < b) pre += n;
-      tot += n;
+  if (mode == 0) {  // the same for all channels of the block: warp w takes tasks w, w + 8, ..., its lanes the images
+    for (int t = wid; t < Tn; t += kAccWarps) {
+      long long pre = 0, tot = 0;
+      for (int bb = lane; bb < B; bb += 32) {
+        const int n = n_bt[bb * Tn + t];
+        if (bb < b) pre += n;
+        tot += n;
+      }
+      pre = warp_sum(pre);
+      tot = warp_sum(tot);
+      if (lane == 0) {
+        s_pre[t] = pre;
+        s_tot[t] = tot;
+        s_nb[t] = n_bt[b * Tn + t];
+      }
     }
-    s_pre[lane] = pre;
-    s_tot[lane] = tot;
-    s_nb[lane] = n_bt[b * Tn + lane];
   }
   __syncthreads();
-  if (c >= D) return;
+  if (!live) return;
   const int ne = Tn * 2;
-  float* acc = s_acc + (size_t)wid * ne * 33;
-  int* s_split = reinterpret_cast<int*>(s_acc + (size_t)kAccWarps * ne * 33) + wid * 32;
-  for (int i = lane; i < ne * 33; i += 32) acc[i] = 0.f;
+  float* acc = s_acc + (size_t)wid * (ne + 2) * 32;          // + the dump entry of pixels without a task
+  int* s_split = reinterpret_cast<int*>(s_acc + (size_t)kAccWarps * (ne + 2) * 32) + wid * 33;
+  for (int i = lane; i < (ne + 2) * 32; i += 32) acc[i] = 0.f;
   int split = 0x7fffffff;
   if (mode == 0 && lane < Tn) {
     const long long tot = s_tot[lane], nb = s_nb[lane];
     if (tot > 0) {
       const long long base = (long long)D * s_pre[lane] + (long long)c * nb;
-      long long r0;
-      if ((long long)D * tot < 0x7fffffffLL) r0 = (long long)((unsigned)base / (unsigned)tot);  // 32-bit division
-      else r0 = base / tot;
-      const long long sp = (r0 + 1) * tot - base;
+      long long q0;
+      if ((long long)D * tot < 0x7fffffffLL) q0 = (long long)((unsigned)base / (unsigned)tot);  // 32-bit division
+      else q0 = base / tot;
+      const long long sp = (q0 + 1) * tot - base;
       split = sp > 0x7fffffffLL ? 0x7fffffff : (int)sp;
     }
   }
-  s_split[lane] = split;
+  s_split[lane] = split;                    // lanes >= Tn hold INT_MAX: the dump entry (index Tn) never splits
+  if (lane == 0) s_split[32] = 0x7fffffff;
   __syncwarp();
-  const T* row = feat + ((int64_t)b * D + c) * hw;
-  const int8_t* tk = task + (int64_t)b * hw;
-  const int32_t* rk = rank + (int64_t)b * hw;
-  const int items = hw >> 3;
-  constexpr int U = 4;
+  // Branch-free inner loop: a pixel without a task (-1: background / ignore / later task) adds into a dump entry
+  // (table row Tn, split point INT_MAX) instead of taking a branch.
   for (int it0 = 0; it0 < items; it0 += 32 * U) {
-    uint2 t8[U];
-    bool any[U];
+    if (it0 > 0) load_step(it0);
+    load_ranks(it0);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int it = it0 + u * 32 + lane;
-      t8[u] = it < items ? *reinterpret_cast<const uint2*>(tk + it * 8) : make_uint2(0xffffffffu, 0xffffffffu);
-      any[u] = ((~t8[u].x | ~t8[u].y) & 0x80808080u) != 0u;  // some byte is >= 0
-    }
-    constexpr int NV = sizeof(T) == 4 ? 2 : 1;  // 16-byte vectors per 8 pixels
-    uint4 raw[U][NV];
-    int4 r0[U], r1[U];
+      if (((~t8[u].x | ~t8[u].y) & 0x80808080u) == 0u) continue;   // no byte >= 0 in this lane's 8 pixels
+      const int rr[8] = {r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, r1[u].z, r1[u].w};
+      const T* e8 = reinterpret_cast<const T*>(&raw[u][0]);
+      // labels are blocky: 8 pixels of ONE task whose ranks (increasing along the row) lie on one side of the split
+      // point are added in registers and cost a single table update
+      const unsigned t0 = t8[u].x & 0xffu;
+      if (t8[u].x == t0 * 0x01010101u && t8[u].y == t8[u].x) {
+        const int sp = s_split[t0];
+        if (rr[7] < sp || rr[0] >= sp) {
+          float v = 0.f;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int it = it0 + u * 32 + lane;
-      r0[u] = r1[u] = make_int4(0, 0, 0, 0);
-#pragma unroll
-      for (int k = 0; k < NV; ++k) raw[u][k] = make_uint4(0u, 0u, 0u, 0u);
-      if (any[u]) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) raw[u][k] = reinterpret_cast<const uint4*>(row + it * 8)[k];
-        if (mode == 0) {
-          r0[u] = *reinterpret_cast<const int4*>(rk + it * 8);
-          r1[u] = *reinterpret_cast<const int4*>(rk + it * 8 + 4);
+          for (int e = 0; e < 8; ++e) v += DT<T>::to_f(e8[e]);
+          acc[(int)t0 * 64 + (rr[0] < sp ? 0 : 32) + lane] += v;
+          continue;
         }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (any[u]) {
-        const int rr[8] = {r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, r1[u].z, r1[u].w};
-        const T* e8 = reinterpret_cast<const T*>(&raw[u][0]);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int t = (int)(int8_t)((e < 4 ? t8[u].x >> (8 * e) : t8[u].y >> (8 * (e - 4))) & 0xffu);
-          if (t >= 0) {
-            const int hi = rr[e] < s_split[t] ? 0 : 1;
-            acc[(t * 2 + hi) * 33 + lane] += DT<T>::to_f(e8[e]);
-          }
-        }
+      for (int e = 0; e < 8; ++e) {
+        const unsigned tb = ((e < 4 ? t8[u].x >> (8 * e) : t8[u].y >> (8 * (e - 4))) & 0xffu);
+        const int tt = (int)min(tb, (unsigned)Tn);                 // 0xff (-1) -> the dump entry
+        const int hi = rr[e] < s_split[tt] ? 0 : 32;
+        acc[tt * 64 + hi + lane] += DT<T>::to_f(e8[e]);         // bank = lane: conflict-free whatever the tasks
       }
     }
   }
   __syncwarp();
   float* out = partial + (((int64_t)b * D + c) * Tn) * 2;
-  // column sums: lane (e, half) adds 16 of the 32 lane slots of entry e
-  for (int e0 = 0; e0 < ne; e0 += 16) {
-    const int e = e0 + (lane & 15), half = lane >> 4;
-    float sacc = 0.f;
-    if (e < ne) {
-#pragma unroll
-      for (int k = 0; k < 16; ++k) sacc += acc[e * 33 + half * 16 + k];
-    }
-    sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
-    if (half == 0 && e < ne) out[e] = sacc;
+  for (int e = 0; e < ne; ++e) {
+    const float r = warp_sum(acc[e * 32 + lane]);
+    if (lane == 0) out[e] = r;
   }
 }
 
@@ -284,23 +301,42 @@ __global__ void __launch_bounds__(kFinRows* kFinLanes) proto_finalize_kernel(con
     if (mode != 0) {
       for (int bb = bl; bb < B; bb += kFinLanes) acc += (double)partial[(((int64_t)bb * D + r) * Tn + g) * 2];
     } else {
-      for (int bb = bl; bb < B; bb += kFinLanes) {
+      // the kFinLanes threads of a row walk the images together and split the CHANNELS of a contributing image
+      // (a row takes ~N_g / n_b channel runs of one or two images): four independent loads in flight per thread,
+      // never a serial chain of L2 round trips
+      auto ceil_div = [](long long a, long long d) { return a <= 0 ? 0LL : (a + d - 1) / d; };
+      auto add_range = [&](int bb, long long lo, long long hi, int part) {
+        for (long long c0 = lo + bl; c0 < hi; c0 += 4 * kFinLanes) {
+          float v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const long long c = c0 + k * kFinLanes;
+            v[k] = c < hi ? partial[(((int64_t)bb * D + c) * Tn + g) * 2 + part] : 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc += (double)v[k];
+        }
+      };
+      for (int bb = 0; bb < B; ++bb) {
         const long long nb = s_nb[bb];
         if (nb <= 0 || r < s_lo[bb] || r > s_hi[bb] + 1) continue;
         // channels c with r0(c) == r   <=>  r*tot <= D*pre + c*nb < (r+1)*tot
         const long long off = (long long)D * s_pre[bb];
-        auto ceil_div = [](long long a, long long d) { return a <= 0 ? 0LL : (a + d - 1) / d; };
-        long long c_lo = ceil_div((long long)r * tot - off, nb);
-        long long c_hi = ceil_div((long long)(r + 1) * tot - off, nb);
-        if (c_hi > D) c_hi = D;
-        for (long long c = c_lo; c < c_hi; ++c) acc += (double)partial[(((int64_t)bb * D + c) * Tn + g) * 2 + 0];
-        // channels with r0(c) == r - 1 contribute their high part
-        if (r > 0) {
-          long long d_lo = ceil_div((long long)(r - 1) * tot - off, nb);
-          long long d_hi = c_lo;
-          if (d_hi > D) d_hi = D;
-          for (long long c = d_lo; c < d_hi; ++c) acc += (double)partial[(((int64_t)bb * D + c) * Tn + g) * 2 + 1];
+        long long c_lo, c_hi, d_lo = 0;
+        if ((long long)(D + 1) * tot < 0x7fffffffLL) {   // everything fits 32 bits: cheap divisions
+          auto cd32 = [](long long a, unsigned d) { return a <= 0 ? 0LL : (long long)(((unsigned)a + d - 1u) / d); };
+          c_lo = cd32((long long)r * tot - off, (unsigned)nb);
+          c_hi = cd32((long long)(r + 1) * tot - off, (unsigned)nb);
+          if (r > 0) d_lo = cd32((long long)(r - 1) * tot - off, (unsigned)nb);
+        } else {
+          c_lo = ceil_div((long long)r * tot - off, nb);
+          c_hi = ceil_div((long long)(r + 1) * tot - off, nb);
+          if (r > 0) d_lo = ceil_div((long long)(r - 1) * tot - off, nb);
         }
+        if (c_hi > D) c_hi = D;
+        add_range(bb, c_lo, c_hi, 0);
+        // channels with r0(c) == r - 1 contribute their high part
+        if (r > 0) add_range(bb, d_lo, c_lo > D ? D : c_lo, 1);
       }
     }
   }
@@ -400,7 +436,7 @@ static int proto_accumulate_impl(const void* features, int dtype, int B, int D, 
   const int hw = h * w;
   dim3 grid((D + kAccWarps - 1) / kAccWarps, B);
   const size_t acc_smem = (size_t)kAccWarps * T * 64 * sizeof(float);
-  const size_t vec_smem = (size_t)kAccWarps * (T * 2 * 33 + 32) * sizeof(float);
+  const size_t vec_smem = (size_t)kAccWarps * ((T * 2 + 2) * 32 + 33) * sizeof(float);
   const bool vec = hw % 8 == 0 && (reinterpret_cast<uintptr_t>(features) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(task) & 7) == 0 && (reinterpret_cast<uintptr_t>(rank) & 15) == 0;
   BACS_DISPATCH_DTYPE(dtype, TT, {
