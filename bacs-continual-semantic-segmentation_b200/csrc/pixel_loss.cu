@@ -1100,6 +1100,7 @@ int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_
     q.sy = a->z ? ac_scale(a->h, a->H) : 0.f;
     q.sx = a->z ? ac_scale(a->w, a->W) : 0.f;
     cudaStream_t st = (cudaStream_t)stream;
+    const int n_part = sp.blocks_x * a->B;
     // (launching a few images at a time so that pass B re-reads them from the 126 MB L2 was measured: 1 / 2 / 4 / 8
     //  images per launch pair 2.67 / 1.69 / 1.66 / 1.48 ms against 1.33 ms for all 24 at once -- under-filled launches
     //  cost more than the second HBM read)
@@ -1122,7 +1123,7 @@ int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_
     ep.focal_weight = a->focal_weight;
     ep.loss_coef = a->loss_coef;
     ep.loss_over_wsum = a->loss_over_wsum;
-    launch_pdl(pixel_reduce_kernel, dim3(nblk), dim3(256), 0, st, q.partials, sp.blocks_x * a->B, sp.blocks_x, a->acc, a->score,
+    launch_pdl(pixel_reduce_kernel, dim3(nblk), dim3(256), 0, st, q.partials, n_part, sp.blocks_x, a->acc, a->score,
                                               1.0 / ((double)a->H * (double)a->W), ep);
     BACS_CHECK_LAUNCH("bacs_pixel_loss(reduce)");
     return BACS_OK;
