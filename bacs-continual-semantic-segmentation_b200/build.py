@@ -18,17 +18,6 @@ SOURCES = ["labels.cu", "prototypes.cu", "seen.cu", "pixel_loss.cu", "pixel_fast
            "pixel_fast_f16.cu", "distill.cu", "distill_tc.cu", "misc.cu", "peer.cu", "class_distance.cu"]
 
 
-def _cutlass_root():
-    """Header tree of CUTLASS 4 / CuTe (vendored with flashinfer in this image; BACS_CUTLASS_ROOT overrides).  Only
-    class_distance.cu needs it; without it the build FAILS (BACS_ALLOW_STUB=1 builds that entry point as a stub that
-    returns BACS_ERR_UNSUPPORTED)."""
-    cands = [os.environ.get("BACS_CUTLASS_ROOT")]
-    for sp in sys.path:
-        cands.append(os.path.join(sp, "flashinfer", "data", "cutlass"))
-    for c in cands:
-        if c and os.path.exists(os.path.join(c, "include", "cutlass", "cutlass.h")):
-            return c
-    return None
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 
@@ -59,18 +48,6 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("BACS_NVCC_EXTRA", "").split(), "-I", INCLUDE, "-I", CSRC, "-c",
                os.path.join(CSRC, src), "-o", obj]      # BACS_NVCC_EXTRA: diagnostics builds (-DBACS_DTC_PROFILE ...)
-        if src == "class_distance.cu":
-            cut = _cutlass_root()
-            if cut:
-                cmd[1:1] = ["-DBACS_HAVE_CUTLASS", "--expt-relaxed-constexpr", "-I", os.path.join(cut, "include"),
-                            "-I", os.path.join(cut, "tools", "util", "include")]
-            elif os.environ.get("BACS_ALLOW_STUB") == "1":
-                sys.stderr.write("bacs_b200.build: CUTLASS header tree not found, bacs_class_distance is a stub "
-                                 "(BACS_ALLOW_STUB=1)\n")
-            else:
-                raise RuntimeError("bacs_b200.build: CUTLASS / CuTe headers not found (flashinfer/data/cutlass or "
-                                   "BACS_CUTLASS_ROOT): bacs_class_distance cannot be built; set BACS_ALLOW_STUB=1 to "
-                                   "build the library without it")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -5,149 +5,281 @@
 //
 // The reference arithmetic has no such product (its per-task heads are a weighted L1 of sigmoids, networks/
 // bg_detector.py:17-40; SDR's per-class terms, loss/sdr.py:120-200, touch each pixel's own class only), so this is
-// the OPTIONAL per-class prototype family entry, not part of the BACS step.  The dot products are one batched GEMM
-// per call: M = h*w pixels of an image (contiguous in NCHW -> an M-major A operand, no transpose), N = classes,
-// K = D, batch = images, bf16 operands / fp32 accumulation in tensor memory: tcgen05.mma (SASS UTCHMMA) fed by TMA
-// (UTMALDG), accumulators read back with tcgen05.ld (LDTM), instantiated from the CUTLASS 4 SM100 collectives
-// (vendored header tree) inside this translation unit.  Two small kernels of ours add the norms and the arg-min.
+// the OPTIONAL per-class prototype family entry, not part of the BACS step.
+//
+// One hand-written kernel (tcgen05 / TMEM, no library GEMM):
+//   * a persistent CTA keeps ALL prototypes in shared memory as the B operand (bf16, K-major canonical no-swizzle
+//     layout: 8 x 16-byte core matrices, k-blocks Np*16 bytes apart) and their squared norms next to it;
+//   * a tile is 128 pixels of one image = the 128 TMEM lanes.  NCHW features are pixel-major, so a builder thread
+//     (= one pixel = one lane) reads its D channels with coalesced 2-byte loads, packs bf16 pairs and writes them into
+//     tensor memory as the A operand (tcgen05.st; 32 channels = 16 columns per chunk, two warpgroups alternate chunks)
+//     -- no transpose and no M-major descriptor -- and adds up |f|^2 from the same registers;
+//   * warp 8 issues tcgen05.mma.kind::f16 (A from TMEM, B by descriptor, fp32 accumulator [128 x Np] in TMEM) chunk by
+//     chunk as the builders deliver them;
+//   * epilogue in the same kernel: the builders read the accumulator back (tcgen05.ld), add the norms, clamp at zero,
+//     write dist2 [B, Kc, h, w] with coalesced rows and keep the arg-min (ties -> lowest class).
 #include <algorithm>
 
 #include "common.cuh"
 
-#ifdef BACS_HAVE_CUTLASS
-#include "cute/tensor.hpp"
-#include "cutlass/cutlass.h"
-#include "cutlass/epilogue/collective/collective_builder.hpp"
-#include "cutlass/gemm/collective/collective_builder.hpp"
-#include "cutlass/gemm/device/gemm_universal_adapter.h"
-#include "cutlass/gemm/kernel/gemm_universal.hpp"
-#include "cutlass/util/packed_stride.hpp"
-
-namespace {
-using namespace cute;
-using ElementA = cutlass::bfloat16_t;
-using ElementB = cutlass::bfloat16_t;
-using ElementC = float;
-using ElementAcc = float;
-using LayoutA = cutlass::layout::ColumnMajor;  // pixels contiguous (NCHW features)
-using LayoutB = cutlass::layout::ColumnMajor;  // D contiguous (prototype rows)
-using LayoutC = cutlass::layout::ColumnMajor;  // pixels contiguous: [B, classes, h, w]
-using ArchTag = cutlass::arch::Sm100;
-using OpClass = cutlass::arch::OpClassTensorOp;
-using TileShape = Shape<_128, _256, _64>;      // 128 pixels x up to 256 classes per CTA, one UMMA tile in N
-using ClusterShape = Shape<_1, _1, _1>;
-using CollectiveEpilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
-    ArchTag, OpClass, TileShape, ClusterShape, cutlass::epilogue::collective::EpilogueTileAuto, ElementAcc, ElementAcc,
-    ElementC, LayoutC, 4, ElementC, LayoutC, 4, cutlass::epilogue::collective::EpilogueScheduleAuto>::CollectiveOp;
-using CollectiveMainloop = typename cutlass::gemm::collective::CollectiveBuilder<
-    ArchTag, OpClass, ElementA, LayoutA, 8, ElementB, LayoutB, 8, ElementAcc, TileShape, ClusterShape,
-    cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename CollectiveEpilogue::SharedStorage))>,
-    cutlass::gemm::collective::KernelScheduleAuto>::CollectiveOp;
-using GemmKernel =
-    cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue, void>;
-using Gemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;
-
-typename Gemm::Arguments make_args(const void* A, const void* B, float* D, int M, int N, int K, int L) {
-  using StrideA = typename Gemm::GemmKernel::StrideA;
-  using StrideB = typename Gemm::GemmKernel::StrideB;
-  using StrideC = typename Gemm::GemmKernel::StrideC;
-  using StrideD = typename Gemm::GemmKernel::StrideD;
-  const StrideA sa = cutlass::make_cute_packed_stride(StrideA{}, cute::make_shape(M, K, L));
-  const StrideB sb = cutlass::make_cute_packed_stride(StrideB{}, cute::make_shape(N, K, 1));  // shared by the batch
-  const StrideC sc = cutlass::make_cute_packed_stride(StrideC{}, cute::make_shape(M, N, L));
-  const StrideD sd = cutlass::make_cute_packed_stride(StrideD{}, cute::make_shape(M, N, L));
-  return typename Gemm::Arguments{cutlass::gemm::GemmUniversalMode::kGemm,
-                                  {M, N, K, L},
-                                  {reinterpret_cast<const ElementA*>(A), sa, reinterpret_cast<const ElementB*>(B), sb},
-                                  {{1.0f, 0.0f}, D, sc, D, sd}};
-}
-}  // namespace
-#endif  // BACS_HAVE_CUTLASS
-
 namespace bacs {
+namespace cd {
 
-// cc[k] = |c_k|^2 (one warp per class)
-__global__ void __launch_bounds__(256) class_sqnorm_kernel(const __nv_bfloat16* __restrict__ protos, int Kc, int D,
-                                                           float* __restrict__ cc) {
-  const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (k >= Kc) return;
-  float s = 0.f;
-  for (int d = lane; d < D; d += 32) {
-    const float v = __bfloat162float(protos[(int64_t)k * D + d]);
-    s = fmaf(v, v, s);
-  }
-  s = warp_sum(s);
-  if (lane == 0) cc[k] = s;
+constexpr int kBuilderWarps = 8;
+constexpr int kThreads = 32 * (kBuilderWarps + 1);
+constexpr int kTileM = 128;
+constexpr int kChunkK = 32;             // channels per chunk: 16 TMEM columns, 2 MMAs of K = 16
+constexpr int kMaxChunks = 16;          // D <= 512: the A tile takes at most 256 columns
+constexpr int kColA = 256;              // accumulator in columns [0, Np), A tile in [256, 256 + Dp / 2)
+
+struct Params {
+  const __nv_bfloat16* feat;
+  const __nv_bfloat16* protos;
+  float* dist2;
+  int64_t* nearest;
+  int B, D, Dp, hw, Kc, Np, tiles_per_image, n_tiles;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t c) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(c));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(
+          smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void umma_commit(uint64_t* b) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+// D[tmem, 128 x N fp32] (+)= A[tmem, 128 lanes x 8 columns = 16 bf16] * B[smem descriptor, N x 16]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc,
+                                             uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 d;\nmov.b64 d, {%2, %3};\nsetp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], d, %4, p;\n}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// K-major, no swizzle (layouts established with tools/ubench/umma_probe.cu): element (n, k) of a 16-bit operand at
+// (n/8)*sbo + (n%8)*16 + (k/8)*lbo + (k%8)*2 bytes
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int N) {  // bf16 x bf16 -> fp32, M = 128, both operands K-major
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+#define CD_FENCE_BEFORE() asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory")
+#define CD_FENCE_AFTER() asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory")
+
+__device__ __forceinline__ void tmem_st16(uint32_t a, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(a),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t a, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(a)
+               : "memory");
 }
 
-// A block takes 64 adjacent pixels of one image with 8 thread slices: slice s sums the squares of channels s, s+8, ...
-// (every load is a 128-byte row segment), the slices meet in shared memory, then slice s turns the dot products of
-// classes s, s+8, ... into distances in place and the slices' nearest classes are merged (ties -> lowest class).
-constexpr int kCdPx = 64, kCdSlices = 8;
-__global__ void __launch_bounds__(kCdPx* kCdSlices) class_distance_finish_kernel(const __nv_bfloat16* __restrict__ feat,
-                                                                              int D, int hw, int Kc,
-                                                                              const float* __restrict__ cc,
-                                                                              float* __restrict__ dist2,
-                                                                              int64_t* __restrict__ nearest) {
-  __shared__ float s_part[kCdSlices][kCdPx];
-  __shared__ int s_arg[kCdSlices][kCdPx];
-  const int b = blockIdx.y;
-  const int px = threadIdx.x % kCdPx, sl = threadIdx.x / kCdPx;
-  const int p = blockIdx.x * kCdPx + px;
-  const bool live = p < hw;
-  float acc = 0.f;
-  if (live) {
-    const __nv_bfloat16* f = feat + (int64_t)b * D * hw + p;
-    float xa = 0.f, xb = 0.f;
-    int d = sl;
-    for (; d + kCdSlices < D; d += 2 * kCdSlices) {
-      const float v0 = __bfloat162float(f[(int64_t)d * hw]), v1 = __bfloat162float(f[(int64_t)(d + kCdSlices) * hw]);
-      xa = fmaf(v0, v0, xa);
-      xb = fmaf(v1, v1, xb);
-    }
-    if (d < D) {
-      const float v0 = __bfloat162float(f[(int64_t)d * hw]);
-      xa = fmaf(v0, v0, xa);
-    }
-    acc = xa + xb;
+// shared memory: B operand [Dp/8 k-blocks][Np + 1 rows][16 bytes] | cc[Np] | xx[2][128] | best[2][128] | arg[2][128] | barriers
+// (one spare 16-byte slot per k-block: the 32 lanes that copy one prototype row then hit different banks)
+__host__ __device__ inline size_t b_bytes(int Np, int Dp) { return (size_t)(Np + 1) * 16 * (Dp >> 3); }
+__host__ __device__ inline size_t smem_bytes(int Np, int Dp) {
+  return b_bytes(Np, Dp) + (size_t)Np * 4 + 6 * kTileM * 4 + (kMaxChunks + 2) * 8 + 16;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) class_distance_kernel(const Params P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint32_t s_tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Np = P.Np, Dp = P.Dp, KB = Dp >> 3, nchunks = (Dp + kChunkK - 1) / kChunkK;
+  const uint32_t lbo = (uint32_t)(Np + 1) * 16u;
+  unsigned char* s_b = smem;
+  float* s_cc = reinterpret_cast<float*>(smem + b_bytes(Np, Dp));
+  float* s_xx = s_cc + Np;                        // [2][128]
+  float* s_best = s_xx + 2 * kTileM;              // [2][128]
+  int* s_arg = reinterpret_cast<int*>(s_best + 2 * kTileM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_arg + 2 * kTileM) + 7) & ~(uintptr_t)7);
+  uint64_t* bar_chunk = bars;                     // [kMaxChunks]: a chunk of the A tile is in tensor memory (128 arrivals)
+  uint64_t* bar_dfull = bars + kMaxChunks;        // the accumulator is complete (commit)
+  uint64_t* bar_dfree = bars + kMaxChunks + 1;    // every builder has read the accumulator (256 arrivals)
+
+  if (tid == 0) {
+    for (int c = 0; c < kMaxChunks; ++c) mbar_init(&bar_chunk[c], 128);
+    mbar_init(bar_dfull, 1);
+    mbar_init(bar_dfree, 32 * kBuilderWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  s_part[sl][px] = acc;
+  if (warp == kBuilderWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // ---- the prototypes: B operand in the canonical layout (rows >= Kc and channels >= D are zero), squared norms ----
+  // asynchronous 16-byte copies (no registers, all in flight): consecutive threads take consecutive 16-byte pieces
+  // of a prototype row (coalesced in global memory); the padded k-block stride spreads them over the banks
+  for (int idx = tid; idx < Np * KB; idx += kThreads) {
+    const int n = idx / KB, kb = idx - n * KB;
+    const bool ok = n < P.Kc && kb * 8 < P.D;
+    const __nv_bfloat16* src = P.protos + (ok ? (size_t)n * P.D + kb * 8 : 0);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(s_b + (size_t)kb * lbo + n * 16)), "l"(src),
+                 "r"(ok ? 16 : 0)
+                 : "memory");
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
-  float xx = 0.f;
+  for (int n = tid; n < Np; n += kThreads) {
+    float s = 0.f;
+    for (int kb = 0; kb < KB; ++kb) {
+      const uint4 v = *reinterpret_cast<const uint4*>(s_b + (size_t)kb * lbo + n * 16);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-  for (int i = 0; i < kCdSlices; ++i) xx += s_part[i][px];  // same order in every slice: one value per pixel
+      for (int i = 0; i < 4; ++i) {
+        const float a = __uint_as_float(w[i] << 16), b = __uint_as_float(w[i] & 0xffff0000u);
+        s = fmaf(a, a, s);
+        s = fmaf(b, b, s);
+      }
+    }
+    s_cc[n] = s;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tensor core reads what the threads wrote
+  CD_FENCE_BEFORE();
   __syncthreads();
-  float best = INFINITY;
-  int arg = 0x7fffffff;
-  if (live) {
-    float* g = dist2 + (int64_t)b * Kc * hw + p;
-    for (int k = sl; k < Kc; k += kCdSlices) {
-      const float v = fmaxf(fmaf(-2.f, g[(int64_t)k * hw], xx + cc[k]), 0.f);
-      g[(int64_t)k * hw] = v;
-      if (v < best) {
-        best = v;
-        arg = k;
+  CD_FENCE_AFTER();
+  const uint32_t tmem = s_tmem_base;
+
+  if (warp < kBuilderWarps) {
+    // =================================================== builders: A tile -> tensor memory, epilogue
+    const int q = warp & 3, hf = warp >> 2;              // lane quarter (TMEM lanes 32q .. 32q+31), warpgroup
+    const int ml = q * 32 + lane;                        // pixel of the tile = TMEM lane
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    const int Nh = Np >> 1;                              // accumulator columns this warpgroup turns into distances
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+      const int b = tile / P.tiles_per_image, m0 = (tile - b * P.tiles_per_image) * kTileM;
+      const int m = m0 + ml;
+      const bool live = m < P.hw;
+      const unsigned short* fp = reinterpret_cast<const unsigned short*>(P.feat) + (size_t)b * P.D * P.hw + (live ? m : 0);
+      float xx = 0.f;
+      // the A columns were last read by the MMAs of the previous tile: they are complete (this thread waited for the
+      // accumulator of that tile before its epilogue)
+      auto load_chunk = [&](int c, uint32_t* r) {
+#pragma unroll
+        for (int j = 0; j < kChunkK; ++j) {
+          const int k = c * kChunkK + j;
+          r[j] = (live && k < P.D) ? (uint32_t)__ldg(fp + (size_t)k * P.hw) : 0u;
+        }
+      };
+      auto store_chunk = [&](int c, const uint32_t* r) {
+        uint32_t pk[kChunkK / 2];
+#pragma unroll
+        for (int j = 0; j < kChunkK / 2; ++j) {
+          const float a = __uint_as_float(r[2 * j] << 16), bq = __uint_as_float(r[2 * j + 1] << 16);
+          xx = fmaf(a, a, xx);
+          xx = fmaf(bq, bq, xx);
+          pk[j] = r[2 * j] | (r[2 * j + 1] << 16);       // k even in the low half, k odd in the high half
+        }
+        tmem_st16(tlane + kColA + c * (kChunkK / 2), pk);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        CD_FENCE_BEFORE();
+        mbar_arrive(&bar_chunk[c]);
+      };
+      // this warpgroup's chunks hf, hf + 2, ...: the next chunk's loads are in flight while the current one is packed
+      uint32_t ra[kChunkK], rb[kChunkK];
+      if (hf < nchunks) load_chunk(hf, ra);
+      for (int c = hf; c < nchunks; c += 4) {
+        if (c + 2 < nchunks) load_chunk(c + 2, rb);
+        store_chunk(c, ra);
+        if (c + 2 < nchunks) {
+          if (c + 4 < nchunks) load_chunk(c + 4, ra);
+          store_chunk(c + 2, rb);
+        }
+      }
+      s_xx[hf * kTileM + ml] = xx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      xx = s_xx[ml] + s_xx[kTileM + ml];
+      // ---- epilogue: distances of classes [hf*Nh, hf*Nh + Nh) for this pixel ----
+      mbar_wait(bar_dfull, it & 1);
+      CD_FENCE_AFTER();
+      float best = INFINITY;
+      int arg = 0x7fffffff;
+      float* out = P.dist2 + (size_t)b * P.Kc * P.hw + m;
+      for (int n0 = hf * Nh; n0 < (hf + 1) * Nh; n0 += 8) {
+        uint32_t d[8];
+        tmem_ld8(tlane + n0, d);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int n = n0 + j;
+          if (n < P.Kc) {
+            const float v = fmaxf(fmaf(-2.f, __uint_as_float(d[j]), xx + s_cc[n]), 0.f);
+            if (live) out[(size_t)n * P.hw] = v;
+            if (v < best) {
+              best = v;
+              arg = n;
+            }
+          }
+        }
+      }
+      CD_FENCE_BEFORE();
+      mbar_arrive(bar_dfree);
+      if (P.nearest) {
+        s_best[hf * kTileM + ml] = best;
+        s_arg[hf * kTileM + ml] = arg;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (hf == 0 && live) {
+          const float v1 = s_best[kTileM + ml];
+          if (v1 < best) arg = s_arg[kTileM + ml];         // equal distances: the lower class (first half) wins
+          P.nearest[(size_t)b * P.hw + m] = arg;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");        // s_xx / s_best are free for the next tile
+    }
+  } else {
+    // =================================================== warp 8: MMA issue
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16(Np);
+    const uint64_t d0 = make_desc(smem_u32(s_b), lbo, 128);
+    const uint32_t d_lo = (uint32_t)d0, d_hi = (uint32_t)(d0 >> 32);
+    const uint32_t kstep = (2u * lbo) >> 4;               // two k-blocks (16 channels) per MMA, in 16-byte units
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+      if (it > 0) mbar_wait(bar_dfree, (it - 1) & 1);      // the accumulator of the previous tile has been read
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(&bar_chunk[c], it & 1);
+        CD_FENCE_AFTER();
+        if (leader) {
+          const int steps = min(kChunkK, Dp - c * kChunkK) >> 4;
+          for (int s = 0; s < steps; ++s) {
+            const uint32_t ks = (uint32_t)(c * (kChunkK / 16) + s);
+            umma_bf16_ts(tmem, tmem + kColA + ks * 8, d_lo + ks * kstep, d_hi, idesc, (c | s) != 0);
+          }
+          if (c == nchunks - 1) umma_commit(bar_dfull);
+        }
+        __syncwarp();
       }
     }
   }
-  if (nearest == nullptr) return;
-  s_part[sl][px] = best;
-  s_arg[sl][px] = arg;
+  CD_FENCE_BEFORE();
   __syncthreads();
-  if (sl == 0 && live) {
-#pragma unroll
-    for (int i = 1; i < kCdSlices; ++i) {
-      const float v = s_part[i][px];
-      const int a = s_arg[i][px];
-      if (v < best || (v == best && a < arg)) {
-        best = v;
-        arg = a;
-      }
-    }
-    nearest[(int64_t)b * hw + p] = arg;
-  }
+  if (warp == kBuilderWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
+}  // namespace cd
 }  // namespace bacs
 
 using namespace bacs;
@@ -155,61 +287,48 @@ using namespace bacs;
 extern "C" {
 
 size_t bacs_class_distance_workspace_bytes(int32_t B, int32_t Kc, int32_t D, int32_t h, int32_t w) {
-#ifdef BACS_HAVE_CUTLASS
   if (B <= 0 || Kc <= 0 || D <= 0 || h <= 0 || w <= 0) return 0;
-  const size_t cc = align_up((size_t)Kc * sizeof(float), 256);
-  auto args = make_args(nullptr, nullptr, nullptr, h * w, Kc, D, B);
-  return cc + align_up(Gemm::get_workspace_size(args), 256) + 256;
-#else
-  (void)B; (void)Kc; (void)D; (void)h; (void)w;
-  return 0;
-#endif
+  return 256;   // the kernel keeps everything on chip; a non-zero size keeps callers' allocation paths uniform
 }
 
 int bacs_class_distance(const void* features, int dtype, int32_t B, int32_t D, int32_t h, int32_t w, const void* protos,
                         int32_t Kc, float* dist2, int64_t* nearest, void* workspace, size_t workspace_bytes,
                         bacs_stream_t stream) {
-#ifdef BACS_HAVE_CUTLASS
+  (void)workspace;
+  (void)workspace_bytes;
   BACS_REQUIRE(features && protos && dist2, "bacs_class_distance: null pointer");
   BACS_REQUIRE(dtype == BACS_BF16, "bacs_class_distance: bf16 features and prototypes only (tensor-core operands)");
   BACS_REQUIRE(B > 0 && D > 0 && h > 0 && w > 0 && Kc > 0 && Kc <= 256, "bacs_class_distance: bad shape (Kc <= 256)");
-  const int hw = h * w;
-  BACS_REQUIRE(hw % 8 == 0 && D % 8 == 0, "bacs_class_distance: h*w and D must be multiples of 8 (16-byte TMA rows)");
-  BACS_REQUIRE((reinterpret_cast<uintptr_t>(features) & 15) == 0 && (reinterpret_cast<uintptr_t>(protos) & 15) == 0 &&
-                   (reinterpret_cast<uintptr_t>(dist2) & 15) == 0,
-               "bacs_class_distance: pointers must be 16-byte aligned");
-  const size_t need = bacs_class_distance_workspace_bytes(B, Kc, D, h, w);
-  if (!workspace || workspace_bytes < need) {
-    set_error("bacs_class_distance: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
-    return BACS_ERR_WORKSPACE;
-  }
-  cudaStream_t s = (cudaStream_t)stream;
-  float* cc = reinterpret_cast<float*>(workspace);
-  void* gemm_ws = reinterpret_cast<unsigned char*>(workspace) + align_up((size_t)Kc * sizeof(float), 256);
-  class_sqnorm_kernel<<<(Kc + 7) / 8, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(protos), Kc, D, cc);
-  BACS_CHECK_LAUNCH("bacs_class_distance(norms)");
-  auto args = make_args(features, protos, dist2, hw, Kc, D, B);
-  Gemm gemm;
-  if (gemm.can_implement(args) != cutlass::Status::kSuccess) {
-    set_error("bacs_class_distance: the tensor-core GEMM cannot take this shape (hw=%d Kc=%d D=%d)", hw, Kc, D);
+  BACS_REQUIRE(D % 8 == 0, "bacs_class_distance: D must be a multiple of 8 (16-byte prototype rows)");
+  BACS_REQUIRE((reinterpret_cast<uintptr_t>(protos) & 15) == 0, "bacs_class_distance: prototypes must be 16-byte aligned");
+  cd::Params P;
+  P.feat = reinterpret_cast<const __nv_bfloat16*>(features);
+  P.protos = reinterpret_cast<const __nv_bfloat16*>(protos);
+  P.dist2 = dist2;
+  P.nearest = nearest;
+  P.B = B;
+  P.D = D;
+  P.Dp = (D + 15) / 16 * 16;
+  P.hw = h * w;
+  P.Kc = Kc;
+  P.Np = std::max(16, (Kc + 15) / 16 * 16);
+  P.tiles_per_image = (P.hw + cd::kTileM - 1) / cd::kTileM;
+  P.n_tiles = P.tiles_per_image * B;
+  const size_t smem = cd::smem_bytes(P.Np, P.Dp);
+  if (P.Dp > cd::kMaxChunks * cd::kChunkK || smem > (size_t)220 * 1024) {
+    set_error("bacs_class_distance: D=%d, Kc=%d do not fit one SM (D <= 512 and the bf16 prototypes, padded to %d x %d, "
+              "<= 220 KB of shared memory)", D, Kc, P.Np, P.Dp);
     return BACS_ERR_UNSUPPORTED;
   }
-  if (gemm.initialize(args, gemm_ws, s) != cutlass::Status::kSuccess || gemm.run(s) != cutlass::Status::kSuccess) {
-    set_error("bacs_class_distance: tensor-core GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  cudaError_t e = cudaFuncSetAttribute(cd::class_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("bacs_class_distance: shared memory opt-in failed: %s", cudaGetErrorString(e));
     return BACS_ERR_CUDA;
   }
-  ++g_launch_count;
-  dim3 grid((hw + kCdPx - 1) / kCdPx, B);
-  class_distance_finish_kernel<<<grid, kCdPx * kCdSlices, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(features), D, hw, Kc, cc, dist2,
-                                                    nearest);
-  BACS_CHECK_LAUNCH("bacs_class_distance(finish)");
+  const int grid = std::min(P.n_tiles, sm_count());
+  cd::class_distance_kernel<<<grid, cd::kThreads, smem, (cudaStream_t)stream>>>(P);
+  BACS_CHECK_LAUNCH("bacs_class_distance");
   return BACS_OK;
-#else
-  (void)features; (void)dtype; (void)B; (void)D; (void)h; (void)w; (void)protos; (void)Kc; (void)dist2; (void)nearest;
-  (void)workspace; (void)workspace_bytes; (void)stream;
-  set_error("bacs_class_distance: built without the CUTLASS header tree");
-  return BACS_ERR_UNSUPPORTED;
-#endif
 }
 
 }  // extern "C"
