@@ -10,14 +10,17 @@
 // One hand-written kernel (tcgen05 / TMEM, no library GEMM):
 //   * a persistent CTA keeps ALL prototypes in shared memory as the B operand (bf16, K-major canonical no-swizzle
 //     layout: 8 x 16-byte core matrices, k-blocks Np*16 bytes apart) and their squared norms next to it;
-//   * a tile is 128 pixels of one image = the 128 TMEM lanes.  NCHW features are pixel-major, so a builder thread
-//     (= one pixel = one lane) reads its D channels with coalesced 2-byte loads, packs bf16 pairs and writes them into
-//     tensor memory as the A operand (tcgen05.st; 32 channels = 16 columns per chunk, two warpgroups alternate chunks)
-//     -- no transpose and no M-major descriptor -- and adds up |f|^2 from the same registers;
-//   * warp 8 issues tcgen05.mma.kind::f16 (A from TMEM, B by descriptor, fp32 accumulator [128 x Np] in TMEM) chunk by
+//   * a tile is 128 pixels of one image = the 128 TMEM lanes.  NCHW features are pixel-major: warp 17 streams
+//     [32 channels x 128 pixels] boxes through a shared-memory ring with TMA (pixels / channels past the end arrive as
+//     zeros); a builder thread (= one pixel = one lane) reads its 32 channels of a box (conflict-free 2-byte reads),
+//     packs bf16 pairs and writes them into tensor memory as the A operand (tcgen05.st, 16 columns per chunk; the four
+//     builder warpgroups take chunks in turn) -- no transpose and no M-major descriptor -- and adds up |f|^2 on the way;
+//   * warp 16 issues tcgen05.mma.kind::f16 (A from TMEM, B by descriptor, fp32 accumulator [128 x Np] in TMEM) chunk by
 //     chunk as the builders deliver them;
 //   * epilogue in the same kernel: the builders read the accumulator back (tcgen05.ld), add the norms, clamp at zero,
 //     write dist2 [B, Kc, h, w] with coalesced rows and keep the arg-min (ties -> lowest class).
+#include <cuda.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -25,19 +28,23 @@
 namespace bacs {
 namespace cd {
 
-constexpr int kBuilderWarps = 8;
-constexpr int kThreads = 32 * (kBuilderWarps + 1);
+constexpr int kParts = 4;                            // builder warpgroups: each takes every 4th chunk and a quarter of the classes
+constexpr int kBuilderWarps = 4 * kParts;
+constexpr int kBuilders = 32 * kBuilderWarps;
+constexpr int kThreads = 32 * (kBuilderWarps + 2);   // + MMA warp + TMA warp
 constexpr int kTileM = 128;
 constexpr int kChunkK = 32;             // channels per chunk: 16 TMEM columns, 2 MMAs of K = 16
 constexpr int kMaxChunks = 16;          // D <= 512: the A tile takes at most 256 columns
 constexpr int kColA = 256;              // accumulator in columns [0, Np), A tile in [256, 256 + Dp / 2)
+constexpr int kStageBytes = kChunkK * kTileM * 2;   // one TMA box
+constexpr int kMaxStages = 8;
 
 struct Params {
   const __nv_bfloat16* feat;
   const __nv_bfloat16* protos;
   float* dist2;
   int64_t* nearest;
-  int B, D, Dp, hw, Kc, Np, tiles_per_image, n_tiles;
+  int B, D, Dp, hw, Kc, Np, tiles_per_image, n_tiles, stages;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -52,6 +59,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
       "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(
           smem_u32(b)),
       "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
@@ -96,33 +113,43 @@ __device__ __forceinline__ void tmem_ld8(uint32_t a, uint32_t* v) {
                : "memory");
 }
 
-// shared memory: B operand [Dp/8 k-blocks][Np + 1 rows][16 bytes] | cc[Np] | xx[2][128] | best[2][128] | arg[2][128] | barriers
-// (one spare 16-byte slot per k-block: the 32 lanes that copy one prototype row then hit different banks)
+// shared memory: ring of TMA boxes | B operand [Dp/8 k-blocks][Np + 1 rows][16 bytes] | cc[Np] | xx[2][128] | best[2][128] |
+// arg[2][128] | barriers   (one spare 16-byte slot per k-block: the 32 lanes that copy one prototype row then hit
+// different banks)
 __host__ __device__ inline size_t b_bytes(int Np, int Dp) { return (size_t)(Np + 1) * 16 * (Dp >> 3); }
-__host__ __device__ inline size_t smem_bytes(int Np, int Dp) {
-  return b_bytes(Np, Dp) + (size_t)Np * 4 + 6 * kTileM * 4 + (kMaxChunks + 2) * 8 + 16;
+__host__ __device__ inline size_t smem_bytes(int Np, int Dp, int stages) {
+  return (size_t)stages * kStageBytes + b_bytes(Np, Dp) + (size_t)Np * 4 + 3 * kParts * kTileM * 4 +
+         (kMaxChunks + 2 + 2 * kMaxStages) * 8 + 16;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) class_distance_kernel(const Params P) {
+__global__ void __launch_bounds__(kThreads, 1) class_distance_kernel(const __grid_constant__ CUtensorMap map_feat, const Params P) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint32_t s_tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Np = P.Np, Dp = P.Dp, KB = Dp >> 3, nchunks = (Dp + kChunkK - 1) / kChunkK;
   const uint32_t lbo = (uint32_t)(Np + 1) * 16u;
-  unsigned char* s_b = smem;
-  float* s_cc = reinterpret_cast<float*>(smem + b_bytes(Np, Dp));
-  float* s_xx = s_cc + Np;                        // [2][128]
-  float* s_best = s_xx + 2 * kTileM;              // [2][128]
-  int* s_arg = reinterpret_cast<int*>(s_best + 2 * kTileM);
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_arg + 2 * kTileM) + 7) & ~(uintptr_t)7);
+  const int S = P.stages;
+  unsigned char* s_ring = smem;
+  unsigned char* s_b = smem + (size_t)S * kStageBytes;
+  float* s_cc = reinterpret_cast<float*>(s_b + b_bytes(Np, Dp));
+  float* s_xx = s_cc + Np;                        // [kParts][128]
+  float* s_best = s_xx + kParts * kTileM;         // [kParts][128]
+  int* s_arg = reinterpret_cast<int*>(s_best + kParts * kTileM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_arg + kParts * kTileM) + 7) & ~(uintptr_t)7);
   uint64_t* bar_chunk = bars;                     // [kMaxChunks]: a chunk of the A tile is in tensor memory (128 arrivals)
   uint64_t* bar_dfull = bars + kMaxChunks;        // the accumulator is complete (commit)
-  uint64_t* bar_dfree = bars + kMaxChunks + 1;    // every builder has read the accumulator (256 arrivals)
+  uint64_t* bar_dfree = bars + kMaxChunks + 1;    // every builder has read the accumulator
+  uint64_t* bar_full = bars + kMaxChunks + 2;     // [S]: a TMA box has landed (expect-tx)
+  uint64_t* bar_empty = bar_full + kMaxStages;    // [S]: the warpgroup that owns the stage has read it (128 arrivals)
 
   if (tid == 0) {
     for (int c = 0; c < kMaxChunks; ++c) mbar_init(&bar_chunk[c], 128);
     mbar_init(bar_dfull, 1);
     mbar_init(bar_dfree, 32 * kBuilderWarps);
+    for (int k = 0; k < kMaxStages; ++k) {
+      mbar_init(&bar_full[k], 1);
+      mbar_init(&bar_empty[k], 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kBuilderWarps) {
@@ -130,9 +157,30 @@ __global__ void __launch_bounds__(kThreads, 1) class_distance_kernel(const Param
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // ---- the prototypes: B operand in the canonical layout (rows >= Kc and channels >= D are zero), squared norms ----
+  CD_FENCE_BEFORE();
+  __syncthreads();   // barriers are initialised, tensor memory is allocated
+  CD_FENCE_AFTER();
+  const uint32_t tmem = s_tmem_base;
+  constexpr int kWork = 32 * (kBuilderWarps + 1);   // threads that fill the prototypes: everyone but the TMA warp
+  if (warp == kBuilderWarps + 1) {
+    // =================================================== warp 17: feature boxes through the ring, tile after tile
+    // (it runs ahead of the prototype fill: the first boxes are in flight while the B operand is being written)
+    if (elect_one()) {
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      const int b = tile / P.tiles_per_image, m0 = (tile - b * P.tiles_per_image) * kTileM;
+      for (int c = 0; c < nchunks; ++c, ++g) {
+        const uint32_t st = g % (uint32_t)S, use = g / (uint32_t)S;
+        if (use > 0) mbar_wait(&bar_empty[st], (use - 1) & 1);
+        mbar_expect_tx(&bar_full[st], kStageBytes);
+        tma_load_3d(s_ring + (size_t)st * kStageBytes, &map_feat, m0, c * kChunkK, b, &bar_full[st]);
+      }
+    }
+    }
+  } else {
   // asynchronous 16-byte copies (no registers, all in flight): consecutive threads take consecutive 16-byte pieces
   // of a prototype row (coalesced in global memory); the padded k-block stride spreads them over the banks
-  for (int idx = tid; idx < Np * KB; idx += kThreads) {
+  for (int idx = tid; idx < Np * KB; idx += kWork) {
     const int n = idx / KB, kb = idx - n * KB;
     const bool ok = n < P.Kc && kb * 8 < P.D;
     const __nv_bfloat16* src = P.protos + (ok ? (size_t)n * P.D + kb * 8 : 0);
@@ -141,8 +189,8 @@ __global__ void __launch_bounds__(kThreads, 1) class_distance_kernel(const Param
                  : "memory");
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncthreads();
-  for (int n = tid; n < Np; n += kThreads) {
+  asm volatile("bar.sync 2, %0;" ::"n"(kWork) : "memory");
+  for (int n = tid; n < Np; n += kWork) {
     float s = 0.f;
     for (int kb = 0; kb < KB; ++kb) {
       const uint4 v = *reinterpret_cast<const uint4*>(s_b + (size_t)kb * lbo + n * 16);
@@ -157,34 +205,33 @@ __global__ void __launch_bounds__(kThreads, 1) class_distance_kernel(const Param
     s_cc[n] = s;
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tensor core reads what the threads wrote
-  CD_FENCE_BEFORE();
-  __syncthreads();
-  CD_FENCE_AFTER();
-  const uint32_t tmem = s_tmem_base;
+  asm volatile("bar.sync 2, %0;" ::"n"(kWork) : "memory");
 
   if (warp < kBuilderWarps) {
     // =================================================== builders: A tile -> tensor memory, epilogue
-    const int q = warp & 3, hf = warp >> 2;              // lane quarter (TMEM lanes 32q .. 32q+31), warpgroup
+    const int q = warp & 3, hf = warp >> 2;              // lane quarter (TMEM lanes 32q .. 32q+31), builder warpgroup
     const int ml = q * 32 + lane;                        // pixel of the tile = TMEM lane
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-    const int Nh = Np >> 1;                              // accumulator columns this warpgroup turns into distances
+    const int Nh = Np / kParts;                          // accumulator columns this warpgroup turns into distances
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
       const int b = tile / P.tiles_per_image, m0 = (tile - b * P.tiles_per_image) * kTileM;
       const int m = m0 + ml;
       const bool live = m < P.hw;
-      const unsigned short* fp = reinterpret_cast<const unsigned short*>(P.feat) + (size_t)b * P.D * P.hw + (live ? m : 0);
       float xx = 0.f;
       // the A columns were last read by the MMAs of the previous tile: they are complete (this thread waited for the
-      // accumulator of that tile before its epilogue)
-      auto load_chunk = [&](int c, uint32_t* r) {
+      // accumulator of that tile before its epilogue).  Boxes are numbered over the CTA's whole run; warpgroup p takes
+      // the boxes with number % 4 == p, so (the ring depth is a multiple of 4) a stage always belongs to one warpgroup
+      // and each of its barriers is observed phase by phase.
+      for (int c = 0; c < nchunks; ++c) {
+        const uint32_t g = it * (uint32_t)nchunks + (uint32_t)c;
+        if ((int)(g % (uint32_t)kParts) != hf) continue;
+        const uint32_t st = g % (uint32_t)S;
+        mbar_wait(&bar_full[st], (g / (uint32_t)S) & 1);
+        const unsigned short* box = reinterpret_cast<const unsigned short*>(s_ring + (size_t)st * kStageBytes) + ml;
+        uint32_t r[kChunkK];
 #pragma unroll
-        for (int j = 0; j < kChunkK; ++j) {
-          const int k = c * kChunkK + j;
-          r[j] = (live && k < P.D) ? (uint32_t)__ldg(fp + (size_t)k * P.hw) : 0u;
-        }
-      };
-      auto store_chunk = [&](int c, const uint32_t* r) {
+        for (int j = 0; j < kChunkK; ++j) r[j] = box[j * kTileM];
         uint32_t pk[kChunkK / 2];
 #pragma unroll
         for (int j = 0; j < kChunkK / 2; ++j) {
@@ -193,25 +240,17 @@ __global__ void __launch_bounds__(kThreads, 1) class_distance_kernel(const Param
           xx = fmaf(bq, bq, xx);
           pk[j] = r[2 * j] | (r[2 * j + 1] << 16);       // k even in the low half, k odd in the high half
         }
+        mbar_arrive(&bar_empty[st]);                       // the box is in registers
         tmem_st16(tlane + kColA + c * (kChunkK / 2), pk);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         CD_FENCE_BEFORE();
         mbar_arrive(&bar_chunk[c]);
-      };
-      // this warpgroup's chunks hf, hf + 2, ...: the next chunk's loads are in flight while the current one is packed
-      uint32_t ra[kChunkK], rb[kChunkK];
-      if (hf < nchunks) load_chunk(hf, ra);
-      for (int c = hf; c < nchunks; c += 4) {
-        if (c + 2 < nchunks) load_chunk(c + 2, rb);
-        store_chunk(c, ra);
-        if (c + 2 < nchunks) {
-          if (c + 4 < nchunks) load_chunk(c + 4, ra);
-          store_chunk(c + 2, rb);
-        }
       }
       s_xx[hf * kTileM + ml] = xx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      xx = s_xx[ml] + s_xx[kTileM + ml];
+      asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory");
+      xx = 0.f;
+#pragma unroll
+      for (int pt = 0; pt < kParts; ++pt) xx += s_xx[pt * kTileM + ml];   // the same order in every warpgroup
       // ---- epilogue: distances of classes [hf*Nh, hf*Nh + Nh) for this pixel ----
       mbar_wait(bar_dfull, it & 1);
       CD_FENCE_AFTER();
@@ -240,17 +279,23 @@ __global__ void __launch_bounds__(kThreads, 1) class_distance_kernel(const Param
       if (P.nearest) {
         s_best[hf * kTileM + ml] = best;
         s_arg[hf * kTileM + ml] = arg;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory");
         if (hf == 0 && live) {
-          const float v1 = s_best[kTileM + ml];
-          if (v1 < best) arg = s_arg[kTileM + ml];         // equal distances: the lower class (first half) wins
+#pragma unroll
+          for (int pt = 1; pt < kParts; ++pt) {              // equal distances: the lower class (earlier part) wins
+            const float v1 = s_best[pt * kTileM + ml];
+            if (v1 < best) {
+              best = v1;
+              arg = s_arg[pt * kTileM + ml];
+            }
+          }
           P.nearest[(size_t)b * P.hw + m] = arg;
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");        // s_xx / s_best are free for the next tile
+      asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory");   // s_xx / s_best are free for the next tile
     }
-  } else {
-    // =================================================== warp 8: MMA issue
+  } else if (warp == kBuilderWarps) {
+    // =================================================== warp 16: MMA issue
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc_bf16(Np);
     const uint64_t d0 = make_desc(smem_u32(s_b), lbo, 128);
@@ -274,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) class_distance_kernel(const Param
       }
     }
   }
+  }
   CD_FENCE_BEFORE();
   __syncthreads();
   if (warp == kBuilderWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
@@ -283,6 +329,24 @@ __global__ void __launch_bounds__(kThreads, 1) class_distance_kernel(const Param
 }  // namespace bacs
 
 using namespace bacs;
+
+typedef CUresult (*CdEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static CdEncodeFn cd_encode_fn() {
+  static CdEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<CdEncodeFn>(ptr);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
 
 extern "C" {
 
@@ -299,8 +363,9 @@ int bacs_class_distance(const void* features, int dtype, int32_t B, int32_t D, i
   BACS_REQUIRE(features && protos && dist2, "bacs_class_distance: null pointer");
   BACS_REQUIRE(dtype == BACS_BF16, "bacs_class_distance: bf16 features and prototypes only (tensor-core operands)");
   BACS_REQUIRE(B > 0 && D > 0 && h > 0 && w > 0 && Kc > 0 && Kc <= 256, "bacs_class_distance: bad shape (Kc <= 256)");
-  BACS_REQUIRE(D % 8 == 0, "bacs_class_distance: D must be a multiple of 8 (16-byte prototype rows)");
-  BACS_REQUIRE((reinterpret_cast<uintptr_t>(protos) & 15) == 0, "bacs_class_distance: prototypes must be 16-byte aligned");
+  BACS_REQUIRE(D % 8 == 0 && (h * w) % 8 == 0, "bacs_class_distance: D and h*w must be multiples of 8 (16-byte rows)");
+  BACS_REQUIRE((reinterpret_cast<uintptr_t>(protos) & 15) == 0 && (reinterpret_cast<uintptr_t>(features) & 15) == 0,
+               "bacs_class_distance: features and prototypes must be 16-byte aligned");
   cd::Params P;
   P.feat = reinterpret_cast<const __nv_bfloat16*>(features);
   P.protos = reinterpret_cast<const __nv_bfloat16*>(protos);
@@ -311,14 +376,37 @@ int bacs_class_distance(const void* features, int dtype, int32_t B, int32_t D, i
   P.Dp = (D + 15) / 16 * 16;
   P.hw = h * w;
   P.Kc = Kc;
-  P.Np = std::max(16, (Kc + 15) / 16 * 16);
+  P.Np = (Kc + 31) / 32 * 32;   // a multiple of 8 accumulator columns for each of the four builder warpgroups
   P.tiles_per_image = (P.hw + cd::kTileM - 1) / cd::kTileM;
   P.n_tiles = P.tiles_per_image * B;
-  const size_t smem = cd::smem_bytes(P.Np, P.Dp);
-  if (P.Dp > cd::kMaxChunks * cd::kChunkK || smem > (size_t)220 * 1024) {
+  // ring depth: 8 or 4 boxes (a multiple of the four builder warpgroups), whatever fits next to the prototypes
+  int stages = cd::kMaxStages;
+  if (cd::smem_bytes(P.Np, P.Dp, stages) > (size_t)224 * 1024) stages = 4;
+  const size_t smem = cd::smem_bytes(P.Np, P.Dp, stages);
+  if (P.Dp > cd::kMaxChunks * cd::kChunkK || smem > (size_t)224 * 1024) {
     set_error("bacs_class_distance: D=%d, Kc=%d do not fit one SM (D <= 512 and the bf16 prototypes, padded to %d x %d, "
-              "<= 220 KB of shared memory)", D, Kc, P.Np, P.Dp);
+              "+ 32 KB of staging <= 224 KB of shared memory)", D, Kc, P.Np, P.Dp);
     return BACS_ERR_UNSUPPORTED;
+  }
+  P.stages = stages;
+  CdEncodeFn enc = cd_encode_fn();
+  if (!enc) {
+    set_error("bacs_class_distance: cuTensorMapEncodeTiled is not available from this driver");
+    return BACS_ERR_UNSUPPORTED;
+  }
+  CUtensorMap map;
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)P.hw, (cuuint64_t)D, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)P.hw * 2, (cuuint64_t)P.hw * 2 * (cuuint64_t)D};
+    const cuuint32_t box[3] = {(cuuint32_t)cd::kTileM, (cuuint32_t)cd::kChunkK, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(features), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("bacs_class_distance: cuTensorMapEncodeTiled failed (%d)", (int)r);
+      return BACS_ERR_CUDA;
+    }
   }
   cudaError_t e = cudaFuncSetAttribute(cd::class_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
@@ -326,7 +414,7 @@ int bacs_class_distance(const void* features, int dtype, int32_t B, int32_t D, i
     return BACS_ERR_CUDA;
   }
   const int grid = std::min(P.n_tiles, sm_count());
-  cd::class_distance_kernel<<<grid, cd::kThreads, smem, (cudaStream_t)stream>>>(P);
+  cd::class_distance_kernel<<<grid, cd::kThreads, smem, (cudaStream_t)stream>>>(map, P);
   BACS_CHECK_LAUNCH("bacs_class_distance");
   return BACS_OK;
 }
