@@ -72,6 +72,8 @@ _SIGNATURES = {
     "bacs_confmat_metrics": (i32, [vp, i32, vp, vp]),
     "bacs_class_distance_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
     "bacs_class_distance": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, sz, vp]),
+    "bacs_class_sums_workspace_bytes": (sz, [i32, i32, i32]),
+    "bacs_class_sums": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, sz, vp]),
     "bacs_gather_rows": (i32, [vp, i64, i64, vp, i64, vp, vp]),
     "bacs_scale_inplace": (i32, [vp, i32, i64, vp, vp]),
     "bacs_scale_inplace_multi": (i32, [i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(i64), vp, vp]),

@@ -325,6 +325,57 @@ __global__ void __launch_bounds__(kThreads, 1) class_distance_kernel(const __gri
   if (warp == kBuilderWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
+// ---- per-class segmented sums (the segmented reduction of prototypes.cu with G = K classes instead of <= 32 tasks) ----
+// One warp per (image, channel) row; a lane keeps a private column of the warp's [K][32] shared-memory table, so the
+// update of a pixel touches only the lane's own bank (no atomics, no conflicts), then the K rows are summed over the
+// lanes.  partial[b][c][k] fp32; a second launch adds the images in fp64.
+constexpr int kSumWarps = 8;
+template <typename T>
+__global__ void __launch_bounds__(32 * kSumWarps) class_sums_kernel(const T* __restrict__ feat, int D, int hw,
+                                                                    const int64_t* __restrict__ labels, int K, int warps,
+                                                                    float* __restrict__ partial) {
+  extern __shared__ float s_tab[];   // [warps][K][32]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = blockIdx.y, c = blockIdx.x * warps + wid;
+  if (wid >= warps || c >= D) return;
+  float* acc = s_tab + (size_t)wid * K * 32;
+  for (int i = lane; i < K * 32; i += 32) acc[i] = 0.f;
+  __syncwarp();
+  const T* row = feat + ((int64_t)b * D + c) * hw;
+  const int64_t* lab = labels + (int64_t)b * hw;
+  constexpr int U = 8;   // independent loads in flight per lane
+  for (int q0 = 0; q0 < hw; q0 += 32 * U) {
+    long long l[U];
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int q = q0 + u * 32 + lane;
+      l[u] = q < hw ? __ldg(lab + q) : -1;
+      v[u] = q < hw ? DT<T>::to_f(row[q]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (l[u] >= 0 && l[u] < K) acc[(int)l[u] * 32 + lane] += v[u];
+  }
+  __syncwarp();
+  float* out = partial + ((int64_t)b * D + c) * K;
+  for (int k = 0; k < K; ++k) {
+    const float r = warp_sum(acc[k * 32 + lane]);
+    if (lane == 0) out[k] = r;
+  }
+}
+
+// sums[k][c] = sum_b partial[b][c][k] (fp64, images in order: deterministic)
+__global__ void __launch_bounds__(256) class_sums_finalize_kernel(const float* __restrict__ partial, int B, int D, int K,
+                                                                  double* __restrict__ sums) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over (c, k): consecutive threads -> consecutive k
+  if (i >= (int64_t)D * K) return;
+  const int c = (int)(i / K), k = (int)(i - (int64_t)c * K);
+  double s = 0.0;
+  for (int b = 0; b < B; ++b) s += (double)partial[((int64_t)b * D + c) * K + k];
+  sums[(int64_t)k * D + c] = s;
+}
+
 }  // namespace cd
 }  // namespace bacs
 
@@ -416,6 +467,44 @@ int bacs_class_distance(const void* features, int dtype, int32_t B, int32_t D, i
   const int grid = std::min(P.n_tiles, sm_count());
   cd::class_distance_kernel<<<grid, cd::kThreads, smem, (cudaStream_t)stream>>>(map, P);
   BACS_CHECK_LAUNCH("bacs_class_distance");
+  return BACS_OK;
+}
+
+size_t bacs_class_sums_workspace_bytes(int32_t B, int32_t D, int32_t K) {
+  if (B <= 0 || D <= 0 || K <= 0) return 0;
+  return align_up((size_t)B * D * K * sizeof(float), 256);
+}
+
+int bacs_class_sums(const void* features, int dtype, int32_t B, int32_t D, int32_t h, int32_t w, const int64_t* labels_down,
+                    int32_t K, double* sums, void* workspace, size_t workspace_bytes, bacs_stream_t stream) {
+  BACS_REQUIRE(features && labels_down && sums && workspace, "bacs_class_sums: null pointer");
+  BACS_REQUIRE(B > 0 && B < 65536 && D > 0 && h > 0 && w > 0 && K > 0 && K <= 1024, "bacs_class_sums: bad shape (K <= 1024)");
+  if (workspace_bytes < bacs_class_sums_workspace_bytes(B, D, K)) {
+    set_error("bacs_class_sums: workspace %zu < %zu", workspace_bytes, bacs_class_sums_workspace_bytes(B, D, K));
+    return BACS_ERR_WORKSPACE;
+  }
+  // warps (= channel rows) per block: as many [K][32] tables as fit 200 KB of shared memory, at most 8
+  int warps = (int)std::min<size_t>(cd::kSumWarps, (size_t)200 * 1024 / ((size_t)K * 32 * sizeof(float)));
+  BACS_REQUIRE(warps >= 1, "bacs_class_sums: K=%d does not fit a shared-memory table", K);
+  const size_t smem = (size_t)warps * K * 32 * sizeof(float);
+  float* partial = reinterpret_cast<float*>(workspace);
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((D + warps - 1) / warps, B);
+  BACS_DISPATCH_DTYPE(dtype, TT, {
+    auto kern = cd::class_sums_kernel<TT>;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) {
+        set_error("bacs_class_sums: shared memory opt-in failed: %s", cudaGetErrorString(e));
+        return BACS_ERR_CUDA;
+      }
+    }
+    kern<<<grid, 32 * cd::kSumWarps, smem, s>>>(reinterpret_cast<const TT*>(features), D, h * w, labels_down, K, warps, partial);
+  });
+  BACS_CHECK_LAUNCH("bacs_class_sums");
+  const int64_t n = (int64_t)D * K;
+  cd::class_sums_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(partial, B, D, K, sums);
+  BACS_CHECK_LAUNCH("bacs_class_sums(finalize)");
   return BACS_OK;
 }
 

@@ -536,6 +536,26 @@ def class_distance(features: torch.Tensor, class_protos: torch.Tensor, want_near
     return dist2, nearest
 
 
+def class_sums(features: torch.Tensor, labels_down: torch.Tensor, K: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-class feature sums and pixel counts (the per-class prototype family): features [B,D,h,w],
+    labels_down int64 [B,h,w] class ids (ids outside [0,K), e.g. ignore-255, are skipped) ->
+    (sums fp64 [K,D], counts int64 [K])."""
+    features = _cuda(features, "class_sums")
+    labels_down = _cuda(labels_down, "class_sums", torch.int64)
+    B, D, h, w = features.shape
+    if tuple(labels_down.shape) != (B, h, w):
+        raise ValueError("class_sums: labels %s do not match features %s" % (tuple(labels_down.shape), tuple(features.shape)))
+    if not 0 < K <= 256:
+        raise ValueError("class_sums: K must be in (0, 256] (the label histogram has 256 bins)")
+    dev = features.device
+    sums = torch.empty((K, D), dtype=torch.float64, device=dev)
+    lib = _lib()
+    ws = _ws(lib.bacs_class_sums_workspace_bytes(B, D, K), dev)
+    check(lib.bacs_class_sums(features.data_ptr(), _dt(features), B, D, h, w, labels_down.data_ptr(), K, sums.data_ptr(),
+                              ws.data_ptr(), ws.numel(), _stream()), "bacs_class_sums")
+    return sums, label_hist(labels_down)[:K]
+
+
 def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     """out[i] = src[idx[i]] along dim 0 (any dtype; rows are copied as bytes)."""
     src = _cuda(src, "gather_rows")

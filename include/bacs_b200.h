@@ -340,12 +340,26 @@ int bacs_confmat_metrics(const int64_t* confmat, int K, float* out, bacs_stream_
  * Not reference arithmetic (the reference's heads are a weighted L1 of sigmoids, networks/bg_detector.py:17-40; SDR,
  * loss/sdr.py:120-200, only ever touches a pixel's own class): the building block for nearest-class-prototype maps
  * at ADE20K sizes (150 x 512 prototypes).  features [B,D,h,w] and protos [Kc,D] are bf16 (dtype = BACS_BF16), fp32
- * accumulation; h*w and D multiples of 8, Kc <= 256; nearest may be NULL.
+ * accumulation; h*w and D multiples of 8, D <= 512, Kc <= 256 and the prototypes (padded to a multiple of 32 classes)
+ * resident in one SM's shared memory next to 32 KB of staging (<= 224 KB; 150 x 512 fits); BACS_ERR_UNSUPPORTED
+ * otherwise.  One hand-written kernel (csrc/class_distance.cu): TMA -> tensor memory (A) / shared memory (B) ->
+ * tcgen05.mma -> norms, clamp and arg-min in the epilogue.  The workspace is not used (size query kept for callers).
+ * nearest may be NULL.
  * --------------------------------------------------------------------------------- */
 size_t bacs_class_distance_workspace_bytes(int32_t B, int32_t Kc, int32_t D, int32_t h, int32_t w);
 int bacs_class_distance(const void* features, int dtype, int32_t B, int32_t D, int32_t h, int32_t w, const void* protos,
                         int32_t Kc, float* dist2, int64_t* nearest, void* workspace, size_t workspace_bytes,
                         bacs_stream_t stream);
+
+/* Per-class feature sums of the same family (SDR's per-class prototypes, loss/sdr.py:120-159; the segmented reduction
+ * of bacs_proto_accumulate with one group per CLASS instead of per task): sums[k][c] = sum over the low-res pixels of
+ * class k of features[b][c][pixel], fp64 [K, D], OVERWRITTEN.  labels_down int64 [B,h,w] holds class ids (what
+ * bacs_label_downsample_task returns as labels_down); ids outside [0, K) -- ignore-255 -- are skipped.  The per-class
+ * pixel counts are bacs_label_hist of the same labels.  workspace >= bacs_class_sums_workspace_bytes. */
+size_t bacs_class_sums_workspace_bytes(int32_t B, int32_t D, int32_t K);
+int bacs_class_sums(const void* features, int dtype, int32_t B, int32_t D, int32_t h, int32_t w,
+                    const int64_t* labels_down, int32_t K, double* sums, void* workspace,
+                    size_t workspace_bytes, bacs_stream_t stream);
 
 /* Minibatch gather of the HBM-resident replay store: dst[i] = src[idx[i]] for rows of row_bytes bytes.
  * Replaces the fancy-index read of the reference's memmapped buffer fields in Buffer.get_data

@@ -410,6 +410,20 @@ def unbiased_kd(logits, old_logits, alpha: float = 1.0, mask: Optional[torch.Ten
 # Rows 12/14 -- arg-max and confusion matrix / metrics
 #   bacs_loss.py:255; training/metrics.py:38-88 over torchmetrics 0.6.0 ConfusionMatrix/IoU
 # --------------------------------------------------------------------------------------
+def class_sums(features: torch.Tensor, labels_down: torch.Tensor, K: int):
+    """Per-class feature sums / pixel counts of the per-class prototype family (SDR, loss/sdr.py:120-159 sums the
+    features of the pixels of each class present in the down-sampled labels): features [B,D,h,w], labels_down [B,h,w]
+    -> (sums fp64 [K,D], counts int64 [K]); ids outside [0,K) are skipped."""
+    B, D, h, w = features.shape
+    f = features.double().permute(0, 2, 3, 1).reshape(-1, D)
+    l = labels_down.reshape(-1).long()
+    keep = (l >= 0) & (l < K)
+    sums = torch.zeros(K, D, dtype=torch.float64, device=features.device)
+    sums.index_add_(0, l[keep], f[keep])
+    counts = torch.bincount(l[keep], minlength=K)[:K]
+    return sums, counts
+
+
 def class_distance(features: torch.Tensor, class_protos: torch.Tensor):
     """Optional per-class prototype family (no counterpart in the reference's arithmetic): squared
     Euclidean distance of every pixel feature [B,D,h,w] to every class prototype [Kc,D], evaluated directly as

@@ -702,6 +702,36 @@ def test_class_distance_tensor_cores(ops, B, D, h, w, Kc):
     assert none is None and torch.equal(d2, got)
 
 
+def test_class_distance_limits(ops):
+    """shapes whose prototypes do not fit one SM's shared memory are refused, never computed some other way"""
+    from bacs_b200._cabi import BacsError
+    f = torch.randn(1, 1024, 4, 8).to(torch.bfloat16).cuda()
+    with pytest.raises(BacsError):
+        ops.class_distance(f, torch.randn(10, 1024).to(torch.bfloat16).cuda())
+    f = torch.randn(2, 256, 8, 8, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16)
+    c = torch.randn(200, 256, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16)
+    want, _ = O.class_distance(f.float(), c.float())
+    got, _ = ops.class_distance(f.cuda(), c.cuda())                    # 200 classes x 256 channels: fits
+    close(got, want, atol=1e-5 * float(want.max()), what="dist2 200 classes")
+
+
+@pytest.mark.parametrize("B,D,h,w,K,dtype", [(3, 64, 8, 16, 21, torch.float32), (2, 40, 5, 7, 151, torch.bfloat16),
+                                            (4, 512, 32, 32, 151, torch.bfloat16), (1, 8, 3, 3, 256, torch.float16)])
+def test_class_sums(ops, B, D, h, w, K, dtype):
+    """per-class segmented sums (G = K) and counts against index_add / bincount"""
+    g = torch.Generator().manual_seed(K + D)
+    f = torch.randn(B, D, h, w, generator=g).to(dtype)
+    lab = torch.randint(0, K, (B, h, w), generator=g)
+    lab[torch.rand(B, h, w, generator=g) < 0.2] = 255 if K <= 255 else 300      # ignore / out of range
+    lab[0, 0, 0] = 0
+    want_s, want_n = O.class_sums(f.float(), lab, K)
+    got_s, got_n = ops.class_sums(f.cuda(), lab.cuda(), K)
+    assert got_s.dtype == torch.float64 and tuple(got_s.shape) == (K, D)
+    if K <= 255:
+        assert torch.equal(got_n.cpu(), want_n)
+    close(got_s, want_s, atol=1e-5 * float(want_s.abs().max()), what="class sums")
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_pixel_modes_on_the_streaming_path(ops, dtype):
     """K >= 64 takes the two streaming passes (variant 4): plain / class-weighted CE, unbiased CE and the per-image score"""
