@@ -634,3 +634,33 @@ def unpack_state(packed: torch.Tensor, sums: Optional[torch.Tensor], counts: Opt
     K = confmat.shape[0] if confmat is not None else 0
     check(_lib().bacs_unpack_state(packed.data_ptr(), T, D, _ptr(sums), _ptr(counts), _ptr(confmat), K, _stream()),
           "bacs_unpack_state")
+
+
+# --------------------------------------------------------------------------------------
+# BACS_NVTX=1: every op of this module runs inside an NVTX range named after it (timeline tools then show the step as
+# bacs/label_downsample_task, bacs/proto_accumulate_update, bacs/seen_logits_heads, bacs/pixel_loss, bacs/teacher_distill
+# ...).  Off by default: the ranges cost a few microseconds of host time per op.
+# --------------------------------------------------------------------------------------
+def _install_nvtx_ranges():
+    import functools
+    import os
+    if os.environ.get("BACS_NVTX") != "1":
+        return
+
+    def wrap(fn):
+        @functools.wraps(fn)
+        def inner(*args, **kwargs):
+            torch.cuda.nvtx.range_push("bacs/" + fn.__name__)
+            try:
+                return fn(*args, **kwargs)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return inner
+    skip = {"check", "der_transplant_cut"}
+    for name, obj in list(globals().items()):
+        if callable(obj) and getattr(obj, "__module__", None) == __name__ and not name.startswith("_") and name not in skip \
+                and not isinstance(obj, type):
+            globals()[name] = wrap(obj)
+
+
+_install_nvtx_ranges()

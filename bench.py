@@ -213,7 +213,7 @@ def integer_rows(timed_fn, dev, peak, shape=(4, 1024, 2048), K=20):
     for name, fn, nbytes, limiter in (
             ("confmat_accumulate [%d,%d,%d] K=%d, random classes" % (B, H, W, K),
              lambda: ops.confmat_accumulate(preds, target, K, confmat), 16 * px,
-             "shared-memory atomics: 32 distinct bins per warp instruction"),
+             "HBM (one shared-memory atomic per distinct bin of a warp instruction: ballot aggregation)"),
             ("confmat_accumulate [%d,%d,%d] K=%d, blocky map with 10%% errors" % (B, H, W, K),
              lambda: ops.confmat_accumulate(noisy, blocky, K, confmat), 16 * px, "HBM"),
             ("label_remap [%d,%d,%d]" % (B, H, W), lambda: ops.label_remap(target, lut, 0, out=out), 24 * px,
@@ -225,6 +225,20 @@ def integer_rows(timed_fn, dev, peak, shape=(4, 1024, 2048), K=20):
         gbs = nbytes / (ms * 1e-3) / 1e9
         rows.append({"name": name, "us": ms * 1e3, "algorithmic_bytes": nbytes, "GB/s": gbs,
                      "frac_of_hbm_peak": gbs / peak, "limiter": limiter})
+    # the optional per-class prototype family at the ADE20K shape: tensor-core distance, per-class sums
+    Bc, Dc, hc, wc, Kc = 24, 512, 32, 32, 150
+    f = torch.randn(Bc, Dc, hc, wc, device=dev, generator=g).to(torch.bfloat16)
+    c = torch.randn(Kc, Dc, device=dev, generator=g).to(torch.bfloat16)
+    lab = torch.randint(0, Kc + 1, (Bc, hc, wc), device=dev, generator=g, dtype=torch.int64)
+    ms = timed_fn(lambda: ops.class_distance(f, c), 20, 3)
+    flop = 2.0 * Bc * hc * wc * 160 * Dc
+    rows.append({"name": "class_distance [%d,%d,%d,%d] x %d classes (tcgen05, bf16)" % (Bc, Dc, hc, wc, Kc), "us": ms * 1e3,
+                 "algorithmic_bytes": int(f.numel() * 2 + Bc * Kc * hc * wc * 4), "TFLOP/s": flop / (ms * 1e-3) / 1e12,
+                 "limiter": "prototype fill from L2 + 192 tiles on 148 SMs (a 4 GFLOP product)"})
+    ms = timed_fn(lambda: ops.class_sums(f, lab, Kc + 1), 20, 3)
+    rows.append({"name": "class_sums [%d,%d,%d,%d] into %d classes" % (Bc, Dc, hc, wc, Kc + 1), "us": ms * 1e3,
+                 "algorithmic_bytes": int(f.numel() * 2), "GB/s": f.numel() * 2 / (ms * 1e-3) / 1e9,
+                 "limiter": "shared-memory table update per pixel + per-class warp sums"})
     return rows
 
 
