@@ -736,7 +736,7 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // [B,K,H,W] as the 3-D tensor (H*W, K, B) with boxes of 256 pixels x K channels x 1 image
-static bool make_tile_map(CUtensorMap* map, const void* base, int dtype, int B, int K, int64_t HW) {
+static bool make_tile_map(CUtensorMap* map, const void* base, int dtype, int B, int K, int64_t HW, unsigned box_px = 256u) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn || K > 256) return false;
   const size_t es = dtype_size(dtype);
@@ -745,7 +745,7 @@ static bool make_tile_map(CUtensorMap* map, const void* base, int dtype, int B, 
                                                       : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)K, (cuuint64_t)B};
   const cuuint64_t strides[2] = {(cuuint64_t)HW * es, (cuuint64_t)HW * K * es};
-  const cuuint32_t box[3] = {256u, (cuuint32_t)K, 1u};
+  const cuuint32_t box[3] = {box_px, (cuuint32_t)K, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   return fn(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -864,6 +864,7 @@ static bool make_plan(const bacs_pixel_args& a, PixelPlan* plan) {
 
 #include "pixel_lowres.cuh"  // the same loss evaluated from low-res logits (up-sample + adjoint fused)
 #include "pixel_stream.cuh"  // large class counts: two streaming passes instead of shared-memory tiles
+#include "pixel_regs.cuh"    // large class counts in 16-bit storage: one pass, the channel column in registers
 
 namespace bacs {
 
@@ -889,6 +890,34 @@ static bool make_stream_plan(const bacs_pixel_args& a, StreamPlan* plan) {
   plan->blocks_x = (int)bx;
   plan->part_bytes = align_up((size_t)bx * a.B * BACS_NACC * sizeof(double), 256);
   plan->coef_bytes = a.dlogits ? align_up((size_t)6 * HW * a.B * sizeof(float), 256) : 0;
+  return true;
+}
+
+// tile shape of the register-column kernel: 256 threads x 2 CTAs per SM, or (BACS_REGS_CFG=128) 128 threads x 3
+static int regs_threads() {
+  const char* e = getenv("BACS_REGS_CFG");
+  return (e && atoi(e) == 256) ? 256 : 128;
+}
+static int regs_ctas(int nt) {
+  const char* e = getenv("BACS_REGS_CTAS");
+  return nt == 256 ? 2 : ((e && atoi(e) == 3) ? 3 : 4);
+}
+
+// 16-bit logits with 64 <= K <= kRegsKMax on whole 256-pixel tiles: one pass with the channel column of a pixel pair in
+// the registers of two lanes (pixel_regs.cuh)
+static bool make_regs_plan(const bacs_pixel_args& a, StreamPlan* plan) {
+  if (getenv("BACS_NO_REGS")) return false;
+  const int64_t HW = (int64_t)a.H * a.W;
+  auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
+  const int nt = regs_threads();
+  if (a.dtype == BACS_F32 || a.K < 64 || a.K > kRegsKMax || HW % 256 != 0 || encode_tiled_fn() == nullptr) return false;
+  if (a.mode == BACS_PIX_SCORE) return false;  // (per-image sums: streaming path)
+  if (!al(a.logits, 16) || !al(a.labels, 8) || (a.dlogits && !al(a.dlogits, 4))) return false;
+  const int64_t tiles = HW / nt * a.B;
+  if (tiles > 0x3fffffff) return false;
+  plan->blocks_x = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * regs_ctas(nt));  // persistent: one wave
+  plan->part_bytes = align_up((size_t)plan->blocks_x * BACS_NACC * sizeof(double), 256);
+  plan->coef_bytes = 0;
   return true;
 }
 
@@ -1043,6 +1072,7 @@ int bacs_pixel_loss_lowres(const bacs_pixel_args* a, int32_t lh, int32_t lw, voi
 size_t bacs_pixel_workspace_bytes(const bacs_pixel_args* a) {
   if (!a) return 0;
   StreamPlan sp;
+  if (make_regs_plan(*a, &sp)) return sp.part_bytes;
   if (make_stream_plan(*a, &sp)) return sp.part_bytes + sp.coef_bytes;
   PixelPlan plan;
   if (!make_plan(*a, &plan)) return 0;
@@ -1060,6 +1090,7 @@ static bool wce_eligible(const bacs_pixel_args& a, const PixelPlan& plan) {
 int bacs_pixel_kernel_variant(const bacs_pixel_args* a) {
   PixelPlan plan;
   StreamPlan sp;
+  if (a && make_regs_plan(*a, &sp)) return 5;
   if (a && make_stream_plan(*a, &sp)) return 4;
   if (!a || !make_plan(*a, &plan)) return -1;
   return wce_eligible(*a, plan) ? 2 : (plan.fast ? 1 : 0);
@@ -1086,6 +1117,59 @@ int bacs_pixel_loss(const bacs_pixel_args* a, void* workspace, size_t workspace_
   if (a->mode == BACS_PIX_SCORE)
     BACS_REQUIRE(a->score && !a->dlogits, "bacs_pixel_loss: SCORE mode needs score and no gradient");
   StreamPlan sp;
+  if (make_regs_plan(*a, &sp)) {  // large K, 16-bit logits: one pass, channel column in registers (pixel_regs.cuh)
+    if (!workspace || workspace_bytes < sp.part_bytes) {
+      set_error("bacs_pixel_loss: workspace too small (%zu bytes)", workspace_bytes);
+      return BACS_ERR_WORKSPACE;
+    }
+    RegsParams rq;
+    StreamParams& q = rq.s;
+    q.a = *a;
+    q.partials = reinterpret_cast<double*>(workspace);
+    q.coef = a->dlogits ? reinterpret_cast<float*>(workspace) : nullptr;  // only "a gradient is wanted" (stream_norm)
+    q.blocks_x = sp.blocks_x;
+    q.b0 = 0;
+    q.inv_n = (float)(1.0 / ((double)a->B * (double)a->H * (double)a->W));
+    q.sy = a->z ? ac_scale(a->h, a->H) : 0.f;
+    q.sx = a->z ? ac_scale(a->w, a->W) : 0.f;
+    const int64_t HWr = (int64_t)a->H * a->W;
+    const int nt = regs_threads();
+    rq.tiles_per_image = (int)(HWr / nt);
+    rq.n_tiles = rq.tiles_per_image * a->B;
+    if (!make_tile_map(&rq.tmap_in, a->logits, a->dtype, a->B, a->K, HWr, (unsigned)nt)) {
+      set_error("bacs_pixel_loss: cuTensorMapEncodeTiled failed for the logits");
+      return BACS_ERR_CUDA;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)sp.blocks_x);
+    const size_t smem = (size_t)a->K * nt * 2 + 128;
+#define LAUNCH_REGS(TT)                                                                                         \
+  do {                                                                                                          \
+    auto kern = nt == 256 ? pixel_regs_kernel<TT, kRegsKH, 256, 2>                                              \
+                          : (regs_ctas(nt) == 3 ? pixel_regs_kernel<TT, kRegsKH, 128, 3> : pixel_regs_kernel<TT, kRegsKH, 128, 4>); \
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {    \
+      set_error("bacs_pixel_loss: cannot opt in to %zu bytes of shared memory", smem);                          \
+      return BACS_ERR_CUDA;                                                                                     \
+    }                                                                                                           \
+    kern<<<grid, nt, smem, st>>>(rq);                                                                 \
+  } while (0)
+    if (a->dtype == BACS_BF16) LAUNCH_REGS(__nv_bfloat16);
+    else LAUNCH_REGS(__half);
+#undef LAUNCH_REGS
+    BACS_CHECK_LAUNCH("bacs_pixel_loss(register column)");
+    const int nblk = 1 + (a->mode == BACS_PIX_SCORE ? a->B : 0);
+    PixelEpilogue ep;
+    ep.ready = a->ready;
+    ep.focal_scale_out = a->focal_scale_out;
+    ep.loss_out = a->loss_out;
+    ep.focal_weight = a->focal_weight;
+    ep.loss_coef = a->loss_coef;
+    ep.loss_over_wsum = a->loss_over_wsum;
+    launch_pdl(pixel_reduce_kernel, dim3(nblk), dim3(256), 0, st, q.partials, sp.blocks_x, sp.blocks_x, a->acc,
+               a->score, 1.0 / ((double)a->H * (double)a->W), ep);
+    BACS_CHECK_LAUNCH("bacs_pixel_loss(reduce)");
+    return BACS_OK;
+  }
   if (make_stream_plan(*a, &sp)) {  // large K: two streaming passes (pixel_stream.cuh)
     if (!workspace || workspace_bytes < sp.part_bytes + sp.coef_bytes) {
       set_error("bacs_pixel_loss: workspace too small (%zu bytes)", workspace_bytes);

@@ -88,6 +88,140 @@ constexpr int kStreamThreads = 256;
 constexpr int kStreamStatsPx = 4;  // pixels per thread of the statistics pass (8- or 16-byte loads): its state fits 80 registers
 constexpr int kStreamChunk = 4;  // channels (16-byte loads) in flight per thread
 
+// ---- per-pixel stage (everything that follows the soft-max statistics of N adjacent pixels p0 .. p0+N-1 of image b):
+// labels, seen probability from the T head maps, pixel_terms(), distill mask, focal gradient, arg-max.  The gradient
+// coefficients of pixel j leave through emit(j, -max*log2e, coefficients, label).
+// PRE (N == 1 only): the caller has already loaded the label (pre_lab) and the label's own logit (pre_xy).
+template <typename T, int N, bool PRE = false, typename Emit>
+__device__ __forceinline__ void stream_pixel_stage(const StreamParams& p, int b, float s_norm, int old_cl, bool have_seen,
+                                                   int64_t p0, const T* base, const float (&m)[N], const float (&so)[N],
+                                                   const float (&sn)[N], const float (&x0)[N], const int (&am)[N],
+                                                   float* acc, Emit emit, long long pre_lab = 0, float pre_xy = 0.f) {
+  static_assert(!PRE || N == 1, "preloaded labels: one pixel per thread");
+  const bacs_pixel_args& a = p.a;
+  const int K = a.K;
+  const int64_t HW = (int64_t)a.H * a.W;
+  const int64_t pix0 = (int64_t)b * HW + p0;
+  long long lab[N];
+  {
+    const int64_t* lp = a.labels + pix0;
+    if constexpr (PRE) {
+      lab[0] = pre_lab;
+    } else if constexpr (N == 1) {
+      lab[0] = __ldg(lp);
+    } else {
+#pragma unroll
+      for (int j = 0; j + 1 < N; j += 2) {
+        const longlong2 t = __ldg(reinterpret_cast<const longlong2*>(lp + j));
+        lab[j] = t.x;
+        lab[j + 1] = t.y;
+      }
+    }
+  }
+  uint32_t mbits = 0;
+  // focal gradient: runs of pixels that share the low-res cell are merged before the atomics
+  int run_cell = -1, run_dx = 0, run_dy = 0;
+  float r00 = 0.f, r01 = 0.f, r10 = 0.f, r11 = 0.f;
+  float* gzb = a.gz ? a.gz + (int64_t)b * a.h * a.w : nullptr;
+  auto run_flush = [&]() {
+    if (run_cell >= 0) {
+      if (r00 != 0.f) atomicAdd(gzb + run_cell, r00);
+      if (r01 != 0.f) atomicAdd(gzb + run_cell + run_dx, r01);
+      if (r10 != 0.f) atomicAdd(gzb + run_cell + run_dy, r10);
+      if (r11 != 0.f) atomicAdd(gzb + run_cell + run_dy + run_dx, r11);
+    }
+    run_cell = -1;
+    r00 = r01 = r10 = r11 = 0.f;
+  };
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    int y = -1;
+    bool is_ign = true;
+    const long long l = lab[j];
+    if (l == a.ignore_index) {
+    } else if (l >= 0 && l < K) {
+      y = (int)l;
+      is_ign = false;
+    } else {
+      acc[BACS_ACC_INVALID] += 1.f;
+    }
+    const float nmj = -m[j] * kLog2e;
+    const float e0 = ex2_fast(fmaf(x0[j], kLog2e, nmj));
+    const float S_fg = so[j] + sn[j];
+    const float S = S_fg + e0;
+    const float S_old = so[j] + (old_cl >= 1 ? e0 : 0.f);
+    float xy;
+    if constexpr (PRE) xy = y > 0 ? pre_xy : x0[j];
+    else xy = y > 0 ? DT<T>::to_f(base[(int64_t)y * HW + j]) : x0[j];
+    float seen = 0.f, zfoc = 0.f, wx1 = 0.f, wy1 = 0.f;
+    int cell = -1, cdx = 0, cdy = 0;
+    if (a.seen_max) seen = __ldg(a.seen_max + pix0 + j);
+    if (a.z) {
+      const int64_t pix = p0 + j;
+      const int Y = (int)(pix / a.W), X = (int)(pix - (int64_t)Y * a.W);
+      const Lerp ly = lerp_align_corners(Y, a.h, p.sy), lx = lerp_align_corners(X, a.w, p.sx);
+      const float wx0 = 1.f - lx.w1, wy0 = 1.f - ly.w1;
+      const float* zb = a.z + (int64_t)b * a.T * a.h * a.w;
+      const int o00 = ly.i0 * a.w + lx.i0, o01 = ly.i0 * a.w + lx.i1;
+      const int o10 = ly.i1 * a.w + lx.i0, o11 = ly.i1 * a.w + lx.i1;
+      float zmax = -INFINITY;
+      for (int t = 0; t < a.T; ++t) {
+        const float* zt = zb + (int64_t)t * a.h * a.w;
+        const float left = __fadd_rn(__fmul_rn(wy0, __ldg(zt + o00)), __fmul_rn(ly.w1, __ldg(zt + o10)));
+        const float right = __fadd_rn(__fmul_rn(wy0, __ldg(zt + o01)), __fmul_rn(ly.w1, __ldg(zt + o11)));
+        const float v = __fadd_rn(__fmul_rn(wx0, left), __fmul_rn(lx.w1, right));
+        zmax = fmaxf(zmax, v);
+        if (t == a.focal_head) zfoc = v;
+      }
+      cell = o00;
+      cdx = lx.i1 - lx.i0;
+      cdy = (ly.i1 - ly.i0) * a.w;
+      wx1 = lx.w1;
+      wy1 = ly.w1;
+      if (!a.seen_max) seen = sigmoid_fast(zmax);
+    }
+    PixCoef pc;
+    float gfoc;
+    uint8_t dm;
+    pixel_terms(a, p.inv_n, s_norm, old_cl, y, is_ign, m[j], S, S_old, S_fg, e0, x0[j], xy, seen, have_seen, zfoc, acc,
+                pc, gfoc, dm);
+    mbits |= (uint32_t)dm << (8 * (j & 3));
+    if (N == 1) {
+      if (a.distill_mask) a.distill_mask[pix0] = dm;
+    } else if (N == 2) {
+      if (j == 1 && a.distill_mask) *reinterpret_cast<uint16_t*>(a.distill_mask + pix0) = (uint16_t)mbits;
+    } else if ((j & 3) == 3) {
+      if (a.distill_mask) *reinterpret_cast<uint32_t*>(a.distill_mask + pix0 + (j & ~3)) = mbits;
+      mbits = 0;
+    }
+    emit(j, nmj, pc, l);
+    if (a.gz) {
+      if (cell != run_cell || cdx != run_dx || cdy != run_dy) run_flush();
+      if (gfoc != 0.f) {
+        run_cell = cell;
+        run_dx = cdx;
+        run_dy = cdy;
+        const float t0 = gfoc * (1.f - wy1), t1 = gfoc * wy1;
+        r00 = fmaf(t0, 1.f - wx1, r00);
+        r01 = fmaf(t0, wx1, r01);
+        r10 = fmaf(t1, 1.f - wx1, r10);
+        r11 = fmaf(t1, wx1, r11);
+      }
+    }
+  }
+  if (a.gz) run_flush();
+  if (a.preds) {
+    int64_t* out = a.preds + pix0;
+    if constexpr (N == 1) {
+      out[0] = (long long)am[0];
+    } else {
+#pragma unroll
+      for (int j = 0; j + 1 < N; j += 2)
+        *reinterpret_cast<longlong2*>(out + j) = make_longlong2((long long)am[j], (long long)am[j + 1]);
+    }
+  }
+}
+
 // ---- pass A: statistics, loss terms, coefficients, arg-max, distill mask, focal gradient ---------------------------
 // groups of kStreamStatsPx pixels g_first, g_first + g_step, ... < g_end of image b
 template <typename T>
@@ -200,120 +334,18 @@ __device__ __forceinline__ void stream_stats_groups(const StreamParams& p, int b
       so[j] = f * ((j & 1) ? f2hi(so2[j >> 1]) : f2lo(so2[j >> 1]));
       sn[j] = f * ((j & 1) ? f2hi(sn2[j >> 1]) : f2lo(sn2[j >> 1]));
     }
-    // ---- per-pixel terms ----------------------------------------------------------------------------------------------
-    const int64_t pix0 = (int64_t)b * HW + p0;
-    long long lab[N];
-    {
-      const int64_t* lp = a.labels + pix0;
-#pragma unroll
-      for (int j = 0; j < N; j += 2) {
-        const longlong2 t = __ldg(reinterpret_cast<const longlong2*>(lp + j));
-        lab[j] = t.x;
-        lab[j + 1] = t.y;
-      }
-    }
-    uint32_t mbits = 0;
-    float* cf = p.coef ? p.coef + pix0 : nullptr;
-    // focal gradient: runs of pixels that share the low-res cell are merged before the atomics
-    int run_cell = -1, run_dx = 0, run_dy = 0;
-    float r00 = 0.f, r01 = 0.f, r10 = 0.f, r11 = 0.f;
-    float* gzb = a.gz ? a.gz + (int64_t)b * a.h * a.w : nullptr;
-    auto run_flush = [&]() {
-      if (run_cell >= 0) {
-        if (r00 != 0.f) atomicAdd(gzb + run_cell, r00);
-        if (r01 != 0.f) atomicAdd(gzb + run_cell + run_dx, r01);
-        if (r10 != 0.f) atomicAdd(gzb + run_cell + run_dy, r10);
-        if (r11 != 0.f) atomicAdd(gzb + run_cell + run_dy + run_dx, r11);
-      }
-      run_cell = -1;
-      r00 = r01 = r10 = r11 = 0.f;
-    };
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      int y = -1;
-      bool is_ign = true;
-      const long long l = lab[j];
-      if (l == a.ignore_index) {
-      } else if (l >= 0 && l < K) {
-        y = (int)l;
-        is_ign = false;
-      } else {
-        acc[BACS_ACC_INVALID] += 1.f;
-      }
-      const float nmj = -m[j] * kLog2e;
-      const float e0 = ex2_fast(fmaf(x0[j], kLog2e, nmj));
-      const float S_fg = so[j] + sn[j];
-      const float S = S_fg + e0;
-      const float S_old = so[j] + (old_cl >= 1 ? e0 : 0.f);
-      const float xy = y > 0 ? DT<T>::to_f(base[(int64_t)y * HW + j]) : x0[j];
-      float seen = 0.f, zfoc = 0.f, wx1 = 0.f, wy1 = 0.f;
-      int cell = -1, cdx = 0, cdy = 0;
-      if (a.seen_max) seen = __ldg(a.seen_max + pix0 + j);
-      if (a.z) {
-        const int64_t pix = p0 + j;
-        const int Y = (int)(pix / a.W), X = (int)(pix - (int64_t)Y * a.W);
-        const Lerp ly = lerp_align_corners(Y, a.h, p.sy), lx = lerp_align_corners(X, a.w, p.sx);
-        const float wx0 = 1.f - lx.w1, wy0 = 1.f - ly.w1;
-        const float* zb = a.z + (int64_t)b * a.T * a.h * a.w;
-        const int o00 = ly.i0 * a.w + lx.i0, o01 = ly.i0 * a.w + lx.i1;
-        const int o10 = ly.i1 * a.w + lx.i0, o11 = ly.i1 * a.w + lx.i1;
-        float zmax = -INFINITY;
-        for (int t = 0; t < a.T; ++t) {
-          const float* zt = zb + (int64_t)t * a.h * a.w;
-          const float left = __fadd_rn(__fmul_rn(wy0, __ldg(zt + o00)), __fmul_rn(ly.w1, __ldg(zt + o10)));
-          const float right = __fadd_rn(__fmul_rn(wy0, __ldg(zt + o01)), __fmul_rn(ly.w1, __ldg(zt + o11)));
-          const float v = __fadd_rn(__fmul_rn(wx0, left), __fmul_rn(lx.w1, right));
-          zmax = fmaxf(zmax, v);
-          if (t == a.focal_head) zfoc = v;
-        }
-        cell = o00;
-        cdx = lx.i1 - lx.i0;
-        cdy = (ly.i1 - ly.i0) * a.w;
-        wx1 = lx.w1;
-        wy1 = ly.w1;
-        if (!a.seen_max) seen = sigmoid_fast(zmax);
-      }
-      PixCoef pc;
-      float gfoc;
-      uint8_t dm;
-      pixel_terms(a, p.inv_n, s_norm, old_cl, y, is_ign, m[j], S, S_old, S_fg, e0, x0[j], xy, seen, have_seen, zfoc, acc,
-                  pc, gfoc, dm);
-      mbits |= (uint32_t)dm << (8 * (j & 3));
-      if (N == 2) {
-        if (j == 1 && a.distill_mask) *reinterpret_cast<uint16_t*>(a.distill_mask + pix0) = (uint16_t)mbits;
-      } else if ((j & 3) == 3) {
-        if (a.distill_mask) *reinterpret_cast<uint32_t*>(a.distill_mask + pix0 + (j & ~3)) = mbits;
-        mbits = 0;
-      }
-      if (cf) {  // (a thread's N pixels fill whole 32-byte sectors of every coefficient plane)
-        cf[0 * NPIX + j] = nmj;
-        cf[1 * NPIX + j] = pc.cg0;
-        cf[2 * NPIX + j] = pc.cg1;
-        cf[3 * NPIX + j] = pc.cg2;
-        cf[4 * NPIX + j] = pc.d0;
-        cf[5 * NPIX + j] = pc.dy;
-      }
-      if (a.gz) {
-        if (cell != run_cell || cdx != run_dx || cdy != run_dy) run_flush();
-        if (gfoc != 0.f) {
-          run_cell = cell;
-          run_dx = cdx;
-          run_dy = cdy;
-          const float t0 = gfoc * (1.f - wy1), t1 = gfoc * wy1;
-          r00 = fmaf(t0, 1.f - wx1, r00);
-          r01 = fmaf(t0, wx1, r01);
-          r10 = fmaf(t1, 1.f - wx1, r10);
-          r11 = fmaf(t1, wx1, r11);
-        }
-      }
-    }
-    if (a.gz) run_flush();
-    if (a.preds) {
-      int64_t* out = a.preds + pix0;
-#pragma unroll
-      for (int j = 0; j < N; j += 2)
-        *reinterpret_cast<longlong2*>(out + j) = make_longlong2((long long)am[j], (long long)am[j + 1]);
-    }
+    float* cf = p.coef ? p.coef + (int64_t)b * HW + p0 : nullptr;
+    stream_pixel_stage<T, N>(p, b, s_norm, old_cl, have_seen, p0, base, m, so, sn, x0, am, acc,
+                             [cf, NPIX](int j, float nmj, const PixCoef& pc, long long) {
+                               if (cf) {  // (a thread's N pixels fill whole 32-byte sectors of every coefficient plane)
+                                 cf[0 * NPIX + j] = nmj;
+                                 cf[1 * NPIX + j] = pc.cg0;
+                                 cf[2 * NPIX + j] = pc.cg1;
+                                 cf[3 * NPIX + j] = pc.cg2;
+                                 cf[4 * NPIX + j] = pc.d0;
+                                 cf[5 * NPIX + j] = pc.dy;
+                               }
+                             });
   }
 }
 
@@ -337,7 +369,7 @@ __device__ __forceinline__ float stream_norm(const StreamParams& p, float* s_nor
 
 // per-CTA partial sums -> p.partials[slot]
 __device__ __forceinline__ void stream_flush_acc(const StreamParams& p, const float* acc, float (*red_scratch)[BACS_NACC],
-                                                 int64_t slot) {
+                                                 int64_t slot, int nwarps = kStreamThreads / 32) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 #pragma unroll
   for (int i = 0; i < BACS_NACC; ++i) {
@@ -347,7 +379,7 @@ __device__ __forceinline__ void stream_flush_acc(const StreamParams& p, const fl
   __syncthreads();
   if (tid < BACS_NACC) {
     double v = 0.0;
-    for (int wv = 0; wv < kStreamThreads / 32; ++wv) v += (double)red_scratch[wv][tid];
+    for (int wv = 0; wv < nwarps; ++wv) v += (double)red_scratch[wv][tid];
     p.partials[slot * BACS_NACC + tid] = v;
   }
 }

@@ -195,8 +195,9 @@ def _device_oracle_pixel_check(cfg, B, dtype, lowres, seed=5):
 @pytest.mark.parametrize("name,B,dtype,variant", [
     ("voc10-1_der", 24, torch.bfloat16, 2),       # T = 11 seen heads: the 3-stage ring of the training-step kernel
     ("cityscapes", 12, torch.bfloat16, 2),        # 512 x 1024 crops, K = 20
-    ("ade100-50", 4, torch.bfloat16, 4),          # K = 151: two streaming passes (online soft-max, then gradient)
-    ("ade100-50", 2, torch.float32, 4)])
+    ("ade100-50", 4, torch.bfloat16, 5),          # K = 151, 16-bit: one pass, the channel column of a pixel pair in registers
+    ("ade100-50", 24, torch.bfloat16, 5),         # ... at the benchmarked batch
+    ("ade100-50", 2, torch.float32, 4)])          # K = 151, fp32: two streaming passes (online soft-max, then gradient)
 def test_pixel_kernel_other_baseline_configs(name, B, dtype, variant):
     from bacs_b200 import synth
     assert _device_oracle_pixel_check(synth.CONFIGS[name], B, dtype, lowres=False) == variant

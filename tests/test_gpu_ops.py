@@ -306,8 +306,9 @@ def test_pixel_training_step_kernel(ops, synth, name, dtype, ukd):
     out = ops.pixel_loss(inp.logits.cuda(), mask.cuda(), _cabi.PIX_WEIGHTED_CE, want_grad=True, z=z.detach().cuda(),
                          want_distill_mask=True, old_cl=cfg.old_cl, ukd=ukd, grad_scale=scale, focal_head=t,
                          focal_alpha=0.25)
-    want_variant = 2 if cfg.K <= 24 else (4 if cfg.K >= 64 else 0)
-    assert out["variant"] == want_variant, "training-step kernel (K <= 24) / tile kernel / two streaming passes (K >= 64)"
+    want_variant = 2 if cfg.K <= 24 else ((4 if dtype == torch.float32 else 5) if cfg.K >= 64 else 0)
+    assert out["variant"] == want_variant, \
+        "training-step kernel (K <= 24) / tile kernel / K >= 64: two streaming passes (fp32), register column (16-bit)"
     N = cfg.B * cfg.H * cfg.W
     acc = out["acc"].cpu()
     close(acc[_cabi.ACC_LOSS] / N, want, what="loss")
@@ -734,7 +735,8 @@ def test_class_sums(ops, B, D, h, w, K, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_pixel_modes_on_the_streaming_path(ops, dtype):
-    """K >= 64 takes the two streaming passes (variant 4): plain / class-weighted CE, unbiased CE and the per-image score"""
+    """K >= 64 takes the two streaming passes (fp32, variant 4) or the one-pass register-column kernel (16-bit, variant
+    5): plain / class-weighted CE, unbiased CE and the per-image score"""
     from bacs_b200 import _cabi
     B, K, H, W, old_cl = 3, 70, 16, 64, 41
     g = torch.Generator().manual_seed(70)
@@ -745,13 +747,14 @@ def test_pixel_modes_on_the_streaming_path(ops, dtype):
     clean = torch.where((y >= K) & (y != 255), torch.full_like(y, 255), y)
     w = torch.rand(K, generator=g)
     tol = 1e-5 if dtype == torch.float32 else 2.0 ** -7
+    variant = 4 if dtype == torch.float32 else 5
     for weight in (None, w):
         x = x0.float().clone().requires_grad_(True)
         want = O.cross_entropy(x, clean, weight)
         want.backward()
         out = ops.pixel_loss(x0.cuda(), y.cuda(), _cabi.PIX_CE, want_grad=True,
                              class_w=None if weight is None else weight.cuda())
-        assert out["variant"] == 4
+        assert out["variant"] == variant
         acc = out["acc"]
         close(acc[_cabi.ACC_LOSS] / acc[_cabi.ACC_WSUM], want, what="ce")
         wg = x.grad.to(dtype).float()
@@ -769,7 +772,7 @@ def test_pixel_modes_on_the_streaming_path(ops, dtype):
     w2[0] = 0
     out = ops.pixel_loss(x0.cuda(), y.cuda(), _cabi.PIX_SCORE, want_grad=False, class_w=w2.cuda(), want_score=True,
                          want_preds=False)
-    assert out["variant"] == 4
+    assert out["variant"] == 4, "per-image scores stay on the streaming path"
     close(out["score"], O.cross_entropy_per_image_score(x0.float(), clean, w2), what="score")
     # confident logits: the exponent reference is lifted when the running max runs ahead (|x| up to ~60)
     xb = (x0.float() * 6).to(dtype)
