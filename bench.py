@@ -239,6 +239,24 @@ def integer_rows(timed_fn, dev, peak, shape=(4, 1024, 2048), K=20):
     rows.append({"name": "class_sums [%d,%d,%d,%d] into %d classes" % (Bc, Dc, hc, wc, Kc + 1), "us": ms * 1e3,
                  "algorithmic_bytes": int(f.numel() * 2), "GB/s": f.numel() * 2 / (ms * 1e-3) / 1e9,
                  "limiter": "shared-memory table update per pixel + per-class warp sums"})
+    del f, c, lab
+    # BASELINE.json configs[3]: the per-pixel loss at the ADE20K 100-50 shape (K = 151, B = 24, 512 x 512, bf16 logits)
+    from bacs_b200 import _cabi, synth
+    cfg = synth.CONFIGS["ade100-50"]
+    logits = torch.randn(cfg.B, cfg.K, cfg.H, cfg.W, device=dev, generator=g).to(torch.bfloat16)
+    mask = synth.make_labels(cfg, torch.Generator().manual_seed(1), classes=list(range(1, cfg.K))).to(dev)
+    z = torch.randn(cfg.B, cfg.T, cfg.h, cfg.w, device=dev, generator=g)
+    kw = dict(want_grad=True, z=z, want_distill_mask=True, old_cl=cfg.old_cl, focal_head=cfg.T - 1)
+    variant = ops.pixel_loss(logits, mask, _cabi.PIX_WEIGHTED_CE, **kw)["variant"]
+    ms = timed_fn(lambda: ops.pixel_loss(logits, mask, _cabi.PIX_WEIGHTED_CE, **kw), 10, 3)
+    nbytes = cfg.B * cfg.H * cfg.W * (2 * cfg.K * 2 + 17)
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    rows.append({"name": "pixel_loss ade100-50 [%d,%d,%d,%d] bf16 (variant %d: one pass, channel column in registers)"
+                         % (cfg.B, cfg.K, cfg.H, cfg.W, variant), "us": ms * 1e3, "algorithmic_bytes": nbytes,
+                 "GB/s": gbs, "frac_of_hbm_peak": gbs / peak,
+                 "limiter": "instruction issue (about 40 instructions per channel and pixel pair, two ex2 per logit) "
+                            "at 16 warps per SM; DRAM traffic equals the algorithmic bytes"})
+    del logits, mask, z
     return rows
 
 
