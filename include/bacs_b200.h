@@ -239,7 +239,9 @@ typedef struct bacs_pixel_args {
 size_t bacs_pixel_workspace_bytes(const bacs_pixel_args* args_host);
 /* Which kernel serves these arguments: 0 = generic shared-memory tiles (any K, ragged shapes),
  * 1 = register-resident tiles (K <= 24), 2 = the training-step specialisation (WEIGHTED_CE on
- * 512-pixel row tiles), -1 = no plan.  Introspection only (tests, bench labels). */
+ * 512-pixel row tiles), 4 = two streaming passes (K >= 64: fp32 logits, per-image scores, K > 152),
+ * 5 = one pass with the channel column of a pixel pair in registers (64 <= K <= 152, 16-bit logits,
+ * H*W a multiple of 256), -1 = no plan.  Introspection only (tests, bench labels). */
 int bacs_pixel_kernel_variant(const bacs_pixel_args* args_host);
 int bacs_pixel_loss(const bacs_pixel_args* args_host, void* workspace, size_t workspace_bytes,
                     bacs_stream_t stream);
