@@ -212,10 +212,26 @@ __global__ void __launch_bounds__(32 * kAccWarps, 4) proto_accumulate_vec_kernel
     }
   }
   __syncwarp();
+  // The ne column sums of the warp as a reduce-scatter over groups of 16 entries: after the exchange with lane ^ 16 a
+  // lane keeps 8 entries, then 4, 2, 1 -- 16 shuffles per group instead of 5 per entry, and the same association
+  // ((l, l^16), then ^8, ^4, ^2, ^1) as warp_sum(), so the sums are bit-identical to the entry-by-entry form.
   float* out = partial + (((int64_t)b * D + c) * Tn) * 2;
-  for (int e = 0; e < ne; ++e) {
-    const float r = warp_sum(acc[e * 32 + lane]);
-    if (lane == 0) out[e] = r;
+  for (int e0 = 0; e0 < ne; e0 += 16) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = e0 + i < ne ? acc[(e0 + i) * 32 + lane] : 0.f;
+    float k8[8], k4[4], k2[2];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) k8[i] = (b4 ? v[i + 8] : v[i]) + __shfl_xor_sync(0xffffffffu, b4 ? v[i] : v[i + 8], 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) k4[i] = (b3 ? k8[i + 4] : k8[i]) + __shfl_xor_sync(0xffffffffu, b3 ? k8[i] : k8[i + 4], 8);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) k2[i] = (b2 ? k4[i + 2] : k4[i]) + __shfl_xor_sync(0xffffffffu, b2 ? k4[i] : k4[i + 2], 4);
+    float k1 = (b1 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? k2[0] : k2[1], 2);
+    k1 += __shfl_xor_sync(0xffffffffu, k1, 1);
+    const int e = e0 + ((lane >> 1) & 15);
+    if ((lane & 1) == 0 && e < ne) out[e] = k1;
   }
 }
 
