@@ -3,6 +3,7 @@ oracle on the same seeded inputs.  Integer work is bit-exact; floating point is 
 1e-5 relative tolerance BASELINE.json's north_star states (gradients of 16-bit tensors are
 compared after the oracle's gradient is rounded to the same storage type)."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -783,3 +784,66 @@ def test_pixel_modes_on_the_streaming_path(ops, dtype):
     close(out["acc"][_cabi.ACC_LOSS] / out["acc"][_cabi.ACC_WSUM], want, rtol=2e-5, what="ce (large logits)")
     wg = x.grad.to(dtype).float()
     close(out["dlogits"].float(), wg, atol=tol * float(wg.abs().max()), what="ce grad (large logits)")
+
+
+@pytest.mark.parametrize("K,old_cl,H,W,dtype", [
+    (151, 101, 16, 64, torch.bfloat16),    # ADE20K 100-50: the boundary falls into the upper lane's channel half
+    (151, 151, 16, 32, torch.bfloat16),    # no new classes (old_cl = K)
+    (151, 1, 16, 32, torch.float16),       # only the background is old; one tile of 256 pixels + one of 256
+    (152, 76, 16, 64, torch.bfloat16),     # every channel register used; boundary exactly between the two lanes
+    (152, 80, 16, 16, torch.bfloat16),     # a single 256-pixel tile; boundary on a block edge of the upper half
+    (101, 75, 32, 32, torch.bfloat16),     # ADE20K step 0 size: 51 of the upper lane's 76 registers hold -inf
+    (77, 5, 16, 48, torch.float16),        # one channel in the upper half; boundary inside block 0 (next to channel 0)
+    (64, 33, 16, 32, torch.bfloat16)])     # smallest K of the path: the upper lanes hold no channel at all
+def test_pixel_register_column_edges(ops, K, old_cl, H, W, dtype):
+    """the one-pass kernel for 64 <= K <= 152 in 16-bit storage (pixel_regs.cuh): channel halves of a pixel pair in two
+    lanes, block-wise old / new sums with a rolled boundary fix-up, -inf padding above K"""
+    from bacs_b200 import _cabi
+    from bacs_b200.synth import StepConfig, make_labels
+    B, T = 2, 3
+    cfg = StepConfig("edge", B=B, K=K, old_cl=old_cl, T=T, H=H, W=W)
+    g = torch.Generator().manual_seed(K * 1000 + old_cl)
+    logits = (torch.randn(B, K, H, W, generator=g) * 2).to(dtype)
+    mask = make_labels(cfg, g, classes=list(range(1, K)), border=1, block=4)
+    mask[0, 3, 5:9] = K + 1                                         # invalid, not ignore
+    clean = torch.where((mask >= K) & (mask != 255), torch.full_like(mask, 255), mask)
+    z = torch.randn(B, T, H // 16, W // 16, generator=g).requires_grad_(True)
+    up = O.bilinear_upsample(z, (H, W), True)
+    smax = torch.sigmoid(up).max(1)[0].detach()
+    x = logits.float().clone().requires_grad_(True)
+    want = O.weighted_ce(x, clean, smax, old_cl, 2.0, 0.5, True)
+    want.backward()
+    kept = int((clean != 255).sum())
+    want_f = O.focal_seen_loss(up[:, T - 1:T], clean, 2.0, None)
+    want_f.backward()
+    scale = 1024.0 if dtype == torch.float16 else 1.0
+    out = ops.pixel_loss(logits.cuda(), mask.cuda(), _cabi.PIX_WEIGHTED_CE, want_grad=True, z=z.detach().cuda(),
+                         want_distill_mask=True, old_cl=old_cl, ukd=True, grad_scale=scale, focal_head=T - 1)
+    assert out["variant"] == 5
+    acc = out["acc"].cpu()
+    close(acc[_cabi.ACC_LOSS] / (B * H * W), want, what="loss")
+    close(acc[_cabi.ACC_FOCAL] / kept, want_f, what="focal loss")
+    close(out["gz"] / kept, z.grad[:, T - 1], atol=2e-5 * float(z.grad.abs().max()), what="gz")
+    assert torch.equal(out["preds"].cpu(), O.argmax_first(logits.float()))
+    want_g = (x.grad * scale).to(dtype).float()
+    tol = 2.0 ** (-7 if dtype == torch.bfloat16 else -10)
+    close(out["dlogits"].float(), want_g, atol=tol * float(want_g.abs().max()), what="dlogits")
+    # element-wise: no entry further than one unit in the last place of the storage type from the oracle's rounding
+    ulp = torch.maximum(want_g.abs(), torch.full_like(want_g, 2.0 ** -100)) * 2.0 ** (-7 if dtype == torch.bfloat16 else -10)
+    big = want_g.abs() > 1e-3 * float(want_g.abs().max())
+    assert bool((((out["dlogits"].float().cpu() - want_g).abs() <= 1.01 * ulp) | ~big).all())
+    want_m = (clean == 0) & (smax > 0.5)
+    diff = out["distill_mask"].cpu().bool() != want_m
+    assert int((diff & ((smax - 0.5).abs() > 1e-6)).sum()) == 0 and int(diff.sum()) <= 2
+    assert int(acc[_cabi.ACC_KEPT]) == kept and int(acc[_cabi.ACC_INVALID]) == 4
+    assert int(acc[_cabi.ACC_BG]) == int((clean == 0).sum())
+    # the same inputs through the two streaming passes (BACS_NO_REGS is read per call): same loss, same arg-max
+    os.environ["BACS_NO_REGS"] = "1"
+    try:
+        ref = ops.pixel_loss(logits.cuda(), mask.cuda(), _cabi.PIX_WEIGHTED_CE, want_grad=True, z=z.detach().cuda(),
+                             want_distill_mask=True, old_cl=old_cl, ukd=True, grad_scale=scale, focal_head=T - 1)
+    finally:
+        del os.environ["BACS_NO_REGS"]
+    assert ref["variant"] == 4
+    assert torch.equal(ref["preds"], out["preds"]) and torch.equal(ref["distill_mask"], out["distill_mask"])
+    close(out["acc"][_cabi.ACC_LOSS], ref["acc"][_cabi.ACC_LOSS], what="loss against the streaming passes")
