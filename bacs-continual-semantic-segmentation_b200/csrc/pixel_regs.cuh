@@ -57,6 +57,14 @@ __device__ __forceinline__ uint32_t regs_pack(F2 v) {
 }
 
 // NT threads = NT pixels per tile (NT / 2 pixel pairs x 2 lanes) = one TMA box row; MINB CTAs per SM
+// (max, first arg-max) of two disjoint channel sets of the same pixel pair; ties -> the lower channel index
+template <typename T>
+__device__ __forceinline__ void regs_merge_max(typename Raw<T>::Max& a, const typename Raw<T>::Max& b) {
+  const uint32_t take = __hgt2_mask(b.m, a.m) | (__heq2_mask(b.m, a.m) & __vcmpltu2(b.a, a.a));
+  a.m = __hmax2(b.m, a.m);
+  a.a = (a.a & ~take) | (b.a & take);
+}
+
 template <typename T, int KH, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) pixel_regs_kernel(const __grid_constant__ RegsParams q) {
   constexpr int kRegsThreads = NT, kRegsTile = NT;
@@ -148,10 +156,16 @@ __global__ void __launch_bounds__(NT, MINB) pixel_regs_kernel(const __grid_const
     float m[2];
     int am[2];
     {
-      typename R::Max mt = R::init(w[0]);
+      // two independent running maxima (even / odd channels) halve the dependent HMNMX2 -> HSET2 chain
+      typename R::Max mt = R::init(w[0]), mu = R::init(w[1]);
       R::set_first(mt, 0);
+      R::set_first(mu, 1);
 #pragma unroll
-      for (int i = 1; i < KH; ++i) R::update(mt, w[i], i);
+      for (int i = 2; i < KH; ++i) {
+        if (i & 1) R::update(mu, w[i], i);
+        else R::update(mt, w[i], i);
+      }
+      regs_merge_max<T>(mt, mu);
       R::finish(mt, m[0], m[1], am[0], am[1]);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -178,15 +192,13 @@ __global__ void __launch_bounds__(NT, MINB) pixel_regs_kernel(const __grid_const
 #pragma unroll
       for (int c0 = 0; c0 < KH; c0 += 8) {
         const int bw = c0 + 8 <= KH ? 8 : KH - c0;
-        F2 t = f2b(0.f);
+        // the eight exponentials of a block are independent values summed as a tree: written as one running sum the
+        // compiler reuses one register pair per channel and every ex2 waits for the add before it (IPC 0.65 per scheduler)
+        F2 e[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (i < bw) {
-            const F2 e = expo(w[c0 + i]);
-            if (c0 + i == 0) t = hb ? e : t;  // the background channel is not part of the sums
-            else t = add2(t, e);
-          }
-        }
+        for (int i = 0; i < 8; ++i) e[i] = i < bw ? expo(w[c0 + i]) : f2b(0.f);
+        if (c0 == 0) e[0] = hb ? e[0] : f2b(0.f);  // the background channel is not part of the sums
+        const F2 t = add2(add2(add2(e[0], e[1]), add2(e[2], e[3])), add2(add2(e[4], e[5]), add2(e[6], e[7])));
         s2 = add2(s2, t);
         if (hb + c0 + bw <= old_cl) so2 = add2(so2, t);
       }
