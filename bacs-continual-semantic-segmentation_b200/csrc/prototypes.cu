@@ -235,6 +235,180 @@ __global__ void __launch_bounds__(32 * kAccWarps, 4) proto_accumulate_vec_kernel
   }
 }
 
+// ---- the same sums as a one-hot GEMM on the tensor cores (16-bit features, hw a multiple of 32) ------------------------
+// total[c][t] = sum_p feat[c][p] * [task(p) == t] is a [16 channels x pixels] x [pixels x 8 tasks] product per warp:
+// mma.sync.m16n8k16 with the features as the row-major A fragments straight from NCHW (a lane loads 8 consecutive
+// pixels of rows g and g + 8 with two 16-byte loads; which pixel sits in which k slot is free as long as B agrees) and
+// the one-hot B fragments made in registers from the lane's own 8 task bytes (byte compare + byte permute): no shared
+// memory, no per-pixel table update -- about 50 instructions per 1024-pixel channel row instead of 964.  The products
+// are exact (0/1 times a 16-bit value), the accumulation is fp32.  Exact mode: a (channel, task) run that crosses a row
+// boundary of the reference's D x N_g view (split point inside the image's n_bt pixels: about D / B channels per task)
+// is re-read by the whole warp with the rank test; all other entries are "everything below the split point".
+constexpr int kMmaWarps = 4;
+template <typename T> struct MmaOne;
+template <> struct MmaOne<__nv_bfloat16> { static constexpr uint32_t pair = 0x3F803F80u; };
+template <> struct MmaOne<__half> { static constexpr uint32_t pair = 0x3C003C00u; };
+template <typename T>
+__device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+  if constexpr (DT<T>::id == BACS_BF16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <typename T, int NT>  // NT = ceil(Tn / 8) task tiles
+__global__ void __launch_bounds__(32 * kMmaWarps) proto_accumulate_mma_kernel(const T* __restrict__ feat, int B, int D, int hw,
+                                                                              const int8_t* __restrict__ task,
+                                                                              const int32_t* __restrict__ rank,
+                                                                              const int32_t* __restrict__ n_bt, int Tn, int mode,
+                                                                              float* __restrict__ partial,
+                                                                              const void* __restrict__ count_raw,
+                                                                              int count_is_int64,
+                                                                              unsigned long long* __restrict__ count_snap) {
+  static_assert(sizeof(T) == 2, "16-bit tensor-core operands");
+  __shared__ long long s_pre[32], s_tot[32];
+  __shared__ int s_nb[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int cb = (blockIdx.x * kMmaWarps + wid) * 16;  // first channel of this warp
+  const int g = lane >> 2, tig = lane & 3;
+  pdl_wait();
+  pdl_trigger();
+  if (count_snap && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < Tn)
+    count_snap[threadIdx.x] = count_is_int64 ? reinterpret_cast<const unsigned long long*>(count_raw)[threadIdx.x]
+                                             : (unsigned long long)reinterpret_cast<const unsigned*>(count_raw)[threadIdx.x];
+  // the first loads go out before the split bookkeeping
+  const bool live = cb < D;
+  const T* rowA = feat + ((int64_t)b * D + (live ? cb : 0) + g) * hw + tig * 8;
+  const T* rowB = rowA + (int64_t)8 * hw;
+  const int8_t* tk = task + (int64_t)b * hw + tig * 8;
+  constexpr int U = 4;  // 32-pixel chunks in flight per lane
+  uint4 ra[U], rb[U];
+  uint2 tw[U];
+  auto load_step = [&](int q0) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int q = q0 + u * 32;
+      if (live && q < hw) {
+        ra[u] = __ldg(reinterpret_cast<const uint4*>(rowA + q));
+        rb[u] = __ldg(reinterpret_cast<const uint4*>(rowB + q));
+        tw[u] = __ldg(reinterpret_cast<const uint2*>(tk + q));
+      } else {
+        ra[u] = rb[u] = make_uint4(0u, 0u, 0u, 0u);
+        tw[u] = make_uint2(0xffffffffu, 0xffffffffu);
+      }
+    }
+  };
+  load_step(0);
+  if (mode == 0) {  // per task: masked pixels in the images before b / in all images / in this image
+    for (int t = wid; t < Tn; t += kMmaWarps) {
+      long long pre = 0, tot = 0;
+      for (int bb = lane; bb < B; bb += 32) {
+        const int n = n_bt[bb * Tn + t];
+        if (bb < b) pre += n;
+        tot += n;
+      }
+      pre = warp_sum(pre);
+      tot = warp_sum(tot);
+      if (lane == 0) {
+        s_pre[t] = pre;
+        s_tot[t] = tot;
+        s_nb[t] = n_bt[b * Tn + t];
+      }
+    }
+  }
+  __syncthreads();
+  if (!live) return;
+  float d[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) d[nt][0] = d[nt][1] = d[nt][2] = d[nt][3] = 0.f;
+  for (int q0 = 0; q0 < hw; q0 += 32 * U) {
+    if (q0 > 0) load_step(q0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        // words (x, y) / (z, w) of the two rows: pixels 4j .. 4j+3 of the lane; k slots 2 tig + {0,1} and 2 tig + 8 + {0,1}
+        const uint32_t a0 = j ? ra[u].z : ra[u].x, a1 = j ? rb[u].z : rb[u].x;
+        const uint32_t a2 = j ? ra[u].w : ra[u].y, a3 = j ? rb[u].w : rb[u].y;
+        const uint32_t tb = j ? tw[u].y : tw[u].x;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const uint32_t m = __vcmpeq4(tb, (uint32_t)(8 * nt + g) * 0x01010101u);  // 0xff where the pixel's task is this lane's n
+          mma_16816<T>(d[nt], a0, a1, a2, a3, __byte_perm(m, 0u, 0x1100) & MmaOne<T>::pair,
+                       __byte_perm(m, 0u, 0x3322) & MmaOne<T>::pair);
+        }
+      }
+    }
+  }
+  // D fragment: d[nt][0..1] = (row g, tasks 8 nt + 2 tig + {0,1}), d[nt][2..3] = (row g + 8, same tasks)
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int t = 8 * nt + 2 * tig + (e & 1), c = cb + g + (e >> 1) * 8;
+      if (t < Tn) *reinterpret_cast<float2*>(partial + (((int64_t)b * D + c) * Tn + t) * 2) = make_float2(d[nt][e], 0.f);
+    }
+  }
+  if (mode != 0) return;
+  __syncwarp();
+  // runs that cross a row boundary of the reference's view: low / high part by the rank test, the warp re-reads the row
+  for (int p0 = 0; p0 < 16 * Tn; p0 += 32) {
+    const int p = p0 + lane;
+    const int cl = p / Tn, t = p - cl * Tn;
+    int sp = 0x7fffffff;
+    bool is_split = false;
+    if (p < 16 * Tn) {
+      const long long tot = s_tot[t], nb = s_nb[t];
+      if (tot > 0 && nb > 0) {
+        const long long base = (long long)D * s_pre[t] + (long long)(cb + cl) * nb;
+        long long q;
+        if ((long long)D * tot < 0x7fffffffLL) q = (long long)((unsigned)base / (unsigned)tot);  // 32-bit division
+        else q = base / tot;
+        const long long spl = (q + 1) * tot - base;
+        is_split = spl < nb;
+        sp = is_split ? (int)spl : 0x7fffffff;
+      }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, is_split);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int scl = __shfl_sync(0xffffffffu, cl, src), st = __shfl_sync(0xffffffffu, t, src);
+      const int ssp = __shfl_sync(0xffffffffu, sp, src);
+      const T* row = feat + ((int64_t)b * D + cb + scl) * hw;
+      const int8_t* tkr = task + (int64_t)b * hw;
+      const int32_t* rkr = rank + (int64_t)b * hw;
+      float lo = 0.f, hi = 0.f;
+      for (int it = lane; it < (hw >> 3); it += 32) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(row + it * 8));
+        const uint2 t8 = __ldg(reinterpret_cast<const uint2*>(tkr + it * 8));
+        const int4 r0 = __ldg(reinterpret_cast<const int4*>(rkr + it * 8)), r1 = __ldg(reinterpret_cast<const int4*>(rkr + it * 8 + 4));
+        const int rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        const T* e8 = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const unsigned tbyte = ((e < 4 ? t8.x >> (8 * e) : t8.y >> (8 * (e - 4))) & 0xffu);
+          if ((int)tbyte == st) {
+            const float v = DT<T>::to_f(e8[e]);
+            if (rr[e] < ssp) lo += v;
+            else hi += v;
+          }
+        }
+      }
+      lo = warp_sum(lo);
+      hi = warp_sum(hi);
+      if (lane == 0)
+        *reinterpret_cast<float2*>(partial + (((int64_t)b * D + cb + scl) * Tn + st) * 2) = make_float2(lo, hi);
+    }
+  }
+}
+
 // One block per task g; thread r gathers the partial runs that land in output row r.
 // Image b's masked elements occupy flat positions [D*pre_b, D*(pre_b+n_b)), i.e. rows
 // lo_b .. hi_b of the D x N_g view; row r only looks at images with lo_b <= r <= hi_b + 1.
@@ -455,6 +629,26 @@ static int proto_accumulate_impl(const void* features, int dtype, int B, int D, 
   const size_t vec_smem = (size_t)kAccWarps * ((T * 2 + 2) * 32 + 33) * sizeof(float);
   const bool vec = hw % 8 == 0 && (reinterpret_cast<uintptr_t>(features) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(task) & 7) == 0 && (reinterpret_cast<uintptr_t>(rank) & 15) == 0;
+  // 16-bit features on 32-pixel chunks, 16-channel blocks: one-hot GEMM on the tensor cores (BACS_NO_PROTO_MMA=1: off)
+  const bool mma = vec && dtype != BACS_F32 && hw % 32 == 0 && D % 16 == 0 && getenv("BACS_NO_PROTO_MMA") == nullptr;
+  if (mma) {
+    dim3 mgrid((D / 16 + kMmaWarps - 1) / kMmaWarps, B);
+    const int nt = (T + 7) / 8;
+#define BACS_MMA_LAUNCH(TT, NTV)                                                                                        \
+  launch_pdl(proto_accumulate_mma_kernel<TT, NTV>, mgrid, dim3(32 * kMmaWarps), 0, s, reinterpret_cast<const TT*>(features), \
+             B, D, hw, task, rank, n_bt, T, mode, partial, count_raw, count_is_int64, snap)
+#define BACS_MMA_NT(TT)                                 \
+  do {                                                  \
+    if (nt == 1) BACS_MMA_LAUNCH(TT, 1);                \
+    else if (nt == 2) BACS_MMA_LAUNCH(TT, 2);           \
+    else if (nt == 3) BACS_MMA_LAUNCH(TT, 3);           \
+    else BACS_MMA_LAUNCH(TT, 4);                        \
+  } while (0)
+    if (dtype == BACS_BF16) BACS_MMA_NT(__nv_bfloat16);
+    else BACS_MMA_NT(__half);
+#undef BACS_MMA_NT
+#undef BACS_MMA_LAUNCH
+  } else
   BACS_DISPATCH_DTYPE(dtype, TT, {
     if (vec) {
       auto kern = proto_accumulate_vec_kernel<TT>;
