@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(32 * kAccWarps, 4) proto_accumulate_vec_kernel
 // are exact (0/1 times a 16-bit value), the accumulation is fp32.  Exact mode: a (channel, task) run that crosses a row
 // boundary of the reference's D x N_g view (split point inside the image's n_bt pixels: about D / B channels per task)
 // is re-read by the whole warp with the rank test; all other entries are "everything below the split point".
-constexpr int kMmaWarps = 4;
+constexpr int kMmaWarps = 2;
 template <typename T> struct MmaOne;
 template <> struct MmaOne<__nv_bfloat16> { static constexpr uint32_t pair = 0x3F803F80u; };
 template <> struct MmaOne<__half> { static constexpr uint32_t pair = 0x3C003C00u; };
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(32 * kMmaWarps) proto_accumulate_mma_kernel(co
                                                                               const int8_t* __restrict__ task,
                                                                               const int32_t* __restrict__ rank,
                                                                               const int32_t* __restrict__ n_bt, int Tn, int mode,
-                                                                              float* __restrict__ partial,
+                                                                              double* __restrict__ sums /* [Tn][D], zeroed */,
                                                                               const void* __restrict__ count_raw,
                                                                               int count_is_int64,
                                                                               unsigned long long* __restrict__ count_snap) {
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(32 * kMmaWarps) proto_accumulate_mma_kernel(co
   const T* rowA = feat + ((int64_t)b * D + (live ? cb : 0) + g) * hw + tig * 8;
   const T* rowB = rowA + (int64_t)8 * hw;
   const int8_t* tk = task + (int64_t)b * hw + tig * 8;
-  constexpr int U = 4;  // 32-pixel chunks in flight per lane
+  constexpr int U = 8;  // 32-pixel chunks in flight per lane
   uint4 ra[U], rb[U];
   uint2 tw[U];
   auto load_step = [&](int q0) {
@@ -346,67 +346,75 @@ __global__ void __launch_bounds__(32 * kMmaWarps) proto_accumulate_mma_kernel(co
       }
     }
   }
-  // D fragment: d[nt][0..1] = (row g, tasks 8 nt + 2 tig + {0,1}), d[nt][2..3] = (row g + 8, same tasks)
+  // D fragment: d[nt][0..1] = (row g, tasks 8 nt + 2 tig + {0,1}), d[nt][2..3] = (row g + 8, same tasks).
+  // The totals go straight into the [Tn][D] fp64 sums (no per-image partial buffer, no gather pass): an entry of image
+  // b, channel c, task t lands in row r0 = (D pre_bt + c n_bt) / N_t of the reference's D x N_t view (row c in
+  // per-channel mode).  The addends are fp32 values, about B per row: their fp64 sum is exact whatever the order.
+  // A run that crosses a row boundary (split point inside the image's n_bt pixels: about D / B channels per task) is
+  // re-read by the whole warp with the rank test and contributes to rows r0 and r0 + 1.
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int t = 8 * nt + 2 * tig + (e & 1), c = cb + g + (e >> 1) * 8;
-      if (t < Tn) *reinterpret_cast<float2*>(partial + (((int64_t)b * D + c) * Tn + t) * 2) = make_float2(d[nt][e], 0.f);
-    }
-  }
-  if (mode != 0) return;
-  __syncwarp();
-  // runs that cross a row boundary of the reference's view: low / high part by the rank test, the warp re-reads the row
-  for (int p0 = 0; p0 < 16 * Tn; p0 += 32) {
-    const int p = p0 + lane;
-    const int cl = p / Tn, t = p - cl * Tn;
-    int sp = 0x7fffffff;
-    bool is_split = false;
-    if (p < 16 * Tn) {
-      const long long tot = s_tot[t], nb = s_nb[t];
-      if (tot > 0 && nb > 0) {
-        const long long base = (long long)D * s_pre[t] + (long long)(cb + cl) * nb;
-        long long q;
-        if ((long long)D * tot < 0x7fffffffLL) q = (long long)((unsigned)base / (unsigned)tot);  // 32-bit division
-        else q = base / tot;
-        const long long spl = (q + 1) * tot - base;
-        is_split = spl < nb;
-        sp = is_split ? (int)spl : 0x7fffffff;
-      }
-    }
-    unsigned todo = __ballot_sync(0xffffffffu, is_split);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int scl = __shfl_sync(0xffffffffu, cl, src), st = __shfl_sync(0xffffffffu, t, src);
-      const int ssp = __shfl_sync(0xffffffffu, sp, src);
-      const T* row = feat + ((int64_t)b * D + cb + scl) * hw;
-      const int8_t* tkr = task + (int64_t)b * hw;
-      const int32_t* rkr = rank + (int64_t)b * hw;
-      float lo = 0.f, hi = 0.f;
-      for (int it = lane; it < (hw >> 3); it += 32) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(row + it * 8));
-        const uint2 t8 = __ldg(reinterpret_cast<const uint2*>(tkr + it * 8));
-        const int4 r0 = __ldg(reinterpret_cast<const int4*>(rkr + it * 8)), r1 = __ldg(reinterpret_cast<const int4*>(rkr + it * 8 + 4));
-        const int rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-        const T* e8 = reinterpret_cast<const T*>(&raw);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const unsigned tbyte = ((e < 4 ? t8.x >> (8 * e) : t8.y >> (8 * (e - 4))) & 0xffu);
-          if ((int)tbyte == st) {
-            const float v = DT<T>::to_f(e8[e]);
-            if (rr[e] < ssp) lo += v;
-            else hi += v;
-          }
+      int row = c, sp = 0x7fffffff;
+      bool is_split = false;
+      if (t < Tn && mode == 0) {
+        const long long tot = s_tot[t], nb = s_nb[t];
+        if (tot > 0 && nb > 0) {
+          const long long base = (long long)D * s_pre[t] + (long long)c * nb;
+          long long q;
+          if ((long long)D * tot < 0x7fffffffLL) q = (long long)((unsigned)base / (unsigned)tot);  // 32-bit division
+          else q = base / tot;
+          const long long spl = (q + 1) * tot - base;
+          row = (int)q;
+          is_split = spl < nb;
+          sp = is_split ? (int)spl : 0x7fffffff;
         }
       }
-      lo = warp_sum(lo);
-      hi = warp_sum(hi);
-      if (lane == 0)
-        *reinterpret_cast<float2*>(partial + (((int64_t)b * D + cb + scl) * Tn + st) * 2) = make_float2(lo, hi);
+      if (t < Tn && !is_split && d[nt][e] != 0.f) atomicAdd(sums + (int64_t)t * D + row, (double)d[nt][e]);
+      unsigned todo = __ballot_sync(0xffffffffu, is_split);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int sc = __shfl_sync(0xffffffffu, c, src), st = __shfl_sync(0xffffffffu, t, src);
+        const int ssp = __shfl_sync(0xffffffffu, sp, src), srow = __shfl_sync(0xffffffffu, row, src);
+        const T* rowp = feat + ((int64_t)b * D + sc) * hw;
+        const int8_t* tkr = task + (int64_t)b * hw;
+        const int32_t* rkr = rank + (int64_t)b * hw;
+        float lo = 0.f, hi = 0.f;
+        for (int it = lane; it < (hw >> 3); it += 32) {
+          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(rowp + it * 8));
+          const uint2 t8 = __ldg(reinterpret_cast<const uint2*>(tkr + it * 8));
+          const int4 r0 = __ldg(reinterpret_cast<const int4*>(rkr + it * 8)), r1 = __ldg(reinterpret_cast<const int4*>(rkr + it * 8 + 4));
+          const int rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          const T* e8 = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const unsigned tbyte = ((k < 4 ? t8.x >> (8 * k) : t8.y >> (8 * (k - 4))) & 0xffu);
+            if ((int)tbyte == st) {
+              const float v = DT<T>::to_f(e8[k]);
+              if (rr[k] < ssp) lo += v;
+              else hi += v;
+            }
+          }
+        }
+        lo = warp_sum(lo);
+        hi = warp_sum(hi);
+        if (lane == 0) {
+          atomicAdd(sums + (int64_t)st * D + srow, (double)lo);
+          atomicAdd(sums + (int64_t)st * D + srow + 1, (double)hi);
+        }
+      }
     }
   }
+}
+
+__global__ void __launch_bounds__(256) proto_zero_sums_kernel(double* __restrict__ sums, int n) {
+  pdl_wait();
+  pdl_trigger();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sums[i] = 0.0;
 }
 
 // One block per task g; thread r gathers the partial runs that land in output row r.
@@ -423,7 +431,7 @@ __global__ void __launch_bounds__(kFinRows* kFinLanes) proto_finalize_kernel(con
                                                                             float* __restrict__ proto, void* __restrict__ count,
                                                                             int count_is_int64,
                                                                             const unsigned long long* __restrict__ count_snap,
-                                                                            int32_t* __restrict__ ready) {
+                                                                            int32_t* __restrict__ ready, int gather) {
   __shared__ long long s_pre[kFinMaxB];
   __shared__ int s_nb[kFinMaxB], s_lo[kFinMaxB], s_hi[kFinMaxB];
   __shared__ long long s_tot;
@@ -478,7 +486,7 @@ __global__ void __launch_bounds__(kFinRows* kFinLanes) proto_finalize_kernel(con
       if (tid == 0) *ready = nz;
     }
   }
-  if (mode == 0 && tot > 0)
+  if (gather && mode == 0 && tot > 0)
     for (int bb = tid; bb < B; bb += blockDim.x) {
       s_lo[bb] = (int)(((long long)D * s_pre[bb]) / tot);
       s_hi[bb] = s_nb[bb] > 0 ? (int)(((long long)D * (s_pre[bb] + s_nb[bb]) - 1) / tot) : -2;
@@ -487,7 +495,7 @@ __global__ void __launch_bounds__(kFinRows* kFinLanes) proto_finalize_kernel(con
   const int rl = tid % kFinRows, bl = tid / kFinRows;
   const int r = blockIdx.y * kFinRows + rl;
   double acc = 0.0;
-  if (r < D && tot > 0) {
+  if (gather && r < D && tot > 0) {
     if (mode != 0) {
       for (int bb = bl; bb < B; bb += kFinLanes) acc += (double)partial[(((int64_t)bb * D + r) * Tn + g) * 2];
     } else {
@@ -534,9 +542,13 @@ __global__ void __launch_bounds__(kFinRows* kFinLanes) proto_finalize_kernel(con
   __syncthreads();
   if (bl == 0 && r < D) {
     double t = 0.0;
+    if (gather) {
 #pragma unroll
-    for (int i = 0; i < kFinLanes; ++i) t += s_red[i][rl];  // fixed order: deterministic
-    sums[(int64_t)g * D + r] = t;
+      for (int i = 0; i < kFinLanes; ++i) t += s_red[i][rl];  // fixed order: deterministic
+      sums[(int64_t)g * D + r] = t;
+    } else {
+      t = sums[(int64_t)g * D + r];  // the accumulate launch has already added every image into the row
+    }
     if (proto && tot > 0) {
       const int64_t i = (int64_t)g * D + r;
       proto[i] = __fdiv_rn(__fadd_rn((float)t, __fmul_rn(upd_old, proto[i])), upd_den);
@@ -632,11 +644,13 @@ static int proto_accumulate_impl(const void* features, int dtype, int B, int D, 
   // 16-bit features on 32-pixel chunks, 16-channel blocks: one-hot GEMM on the tensor cores (BACS_NO_PROTO_MMA=1: off)
   const bool mma = vec && dtype != BACS_F32 && hw % 32 == 0 && D % 16 == 0 && getenv("BACS_NO_PROTO_MMA") == nullptr;
   if (mma) {
+    launch_pdl(proto_zero_sums_kernel, dim3((T * D + 255) / 256), dim3(256), 0, s, sums, T * D);
+    BACS_CHECK_LAUNCH("bacs_proto_accumulate(zero)");
     dim3 mgrid((D / 16 + kMmaWarps - 1) / kMmaWarps, B);
     const int nt = (T + 7) / 8;
 #define BACS_MMA_LAUNCH(TT, NTV)                                                                                        \
   launch_pdl(proto_accumulate_mma_kernel<TT, NTV>, mgrid, dim3(32 * kMmaWarps), 0, s, reinterpret_cast<const TT*>(features), \
-             B, D, hw, task, rank, n_bt, T, mode, partial, count_raw, count_is_int64, snap)
+             B, D, hw, task, rank, n_bt, T, mode, sums, count_raw, count_is_int64, snap)
 #define BACS_MMA_NT(TT)                                 \
   do {                                                  \
     if (nt == 1) BACS_MMA_LAUNCH(TT, 1);                \
@@ -668,7 +682,7 @@ static int proto_accumulate_impl(const void* features, int dtype, int B, int D, 
   });
   BACS_CHECK_LAUNCH("bacs_proto_accumulate");
   launch_pdl(proto_finalize_kernel, dim3(T, (D + kFinRows - 1) / kFinRows), dim3(kFinRows * kFinLanes), 0, s, partial, B, D,
-             n_bt, T, mode, sums, counts, proto, count, count_is_int64, (const unsigned long long*)snap, ready);
+             n_bt, T, mode, sums, counts, proto, count, count_is_int64, (const unsigned long long*)snap, ready, mma ? 0 : 1);
   BACS_CHECK_LAUNCH("bacs_proto_accumulate(finalize)");
   return BACS_OK;
 }
