@@ -847,3 +847,34 @@ def test_pixel_register_column_edges(ops, K, old_cl, H, W, dtype):
     assert ref["variant"] == 4
     assert torch.equal(ref["preds"], out["preds"]) and torch.equal(ref["distill_mask"], out["distill_mask"])
     close(out["acc"][_cabi.ACC_LOSS], ref["acc"][_cabi.ACC_LOSS], what="loss against the streaming passes")
+
+
+@pytest.mark.parametrize("dtype,T,D,B", [(torch.bfloat16, 11, 48, 5), (torch.float16, 6, 32, 2), (torch.bfloat16, 3, 16, 1)])
+def test_proto_accumulate_tensor_core_path(ops, dtype, T, D, B):
+    """16-bit features on 32-pixel chunks take the one-hot GEMM (mma.sync) with direct fp64 sums: both modes against the
+    oracle, more than eight tasks (two task tiles), very unequal images (many runs split across rows of the reference's
+    view), and agreement with the shared-memory-table kernel"""
+    from bacs_b200.synth import StepConfig, make_labels
+    K = 21
+    initial = K - (T - 1)                                   # T tasks: classes 1..initial-1, then one class per task
+    cfg = StepConfig("mma", B=B, K=K, old_cl=K - 1, T=T, H=128, W=256, D=D, A=16, initial_classes=initial, increment=1)
+    g = torch.Generator().manual_seed(100 * T + B)
+    mask = make_labels(cfg, g, classes=list(range(1, K)), border=2, block=16)
+    if B > 1:
+        mask[0, :, : cfg.W // 2] = 255                     # image 0 contributes far fewer pixels than the others
+    pen = torch.randn(B, D, cfg.h, cfg.w, generator=g).to(dtype)
+    lut = torch.from_numpy(O.class_task_lut(cfg.initial_classes, cfg.increment)).int()
+    lut[lut >= cfg.T] = -1
+    task, rank, n_bt, _ = ops.label_downsample_task(mask.cuda(), cfg.h, cfg.w, lut.cuda(), cfg.T)
+    for mode, mname in [(0, "exact"), (1, "channel")]:
+        sums, counts = ops.proto_accumulate(pen.cuda(), task, rank, n_bt, cfg.T, mode)
+        want_s, want_n = O.proto_accumulate(pen.float(), mask, cfg.initial_classes, cfg.increment, cfg.T, mode=mname)
+        assert torch.equal(counts.cpu().long(), want_n)
+        close(sums, want_s, atol=2e-5 * float(want_s.abs().max()), what="sums " + mname)
+        os.environ["BACS_NO_PROTO_MMA"] = "1"
+        try:
+            s_tab, n_tab = ops.proto_accumulate(pen.cuda(), task, rank, n_bt, cfg.T, mode)
+        finally:
+            del os.environ["BACS_NO_PROTO_MMA"]
+        assert torch.equal(n_tab, counts)
+        close(sums, s_tab, atol=2e-6 * float(want_s.abs().max()), what="tensor-core sums against the table kernel, " + mname)
