@@ -410,6 +410,94 @@ __global__ void __launch_bounds__(32 * kSumWarps) class_sums_kernel(const T* __r
   }
 }
 
+// ---- the same sums as a one-hot GEMM on the tensor cores (16-bit features, hw % 32 == 0, D % 16 == 0, K <= 8 NT) -----
+// partial[b][c][k] = sum_p feat[b][c][p] * [label(p) == k]: per warp a [16 channels x pixels] x [pixels x 8 NT classes]
+// product with mma.sync.m16n8k16 -- features as row-major A fragments straight from NCHW (two 16-byte loads of 8
+// consecutive pixels of rows g and g + 8 per lane), one-hot B fragments made in registers from the lane's own 8 labels
+// (narrowed to bytes, 0xff = outside [0, K)), fp32 accumulators in registers: no shared-memory table, no per-class warp
+// sums.  Same construction as proto_accumulate_mma_kernel (prototypes.cu) with classes instead of tasks.
+constexpr int kSumMmaWarps = 2;
+template <typename T>
+__device__ __forceinline__ void cs_mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                             uint32_t b1) {
+  if constexpr (DT<T>::id == BACS_BF16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <typename T, int NT>
+__global__ void __launch_bounds__(32 * kSumMmaWarps) class_sums_mma_kernel(const T* __restrict__ feat, int D, int hw,
+                                                                           const int64_t* __restrict__ labels, int K,
+                                                                           float* __restrict__ partial) {
+  static_assert(sizeof(T) == 2, "16-bit tensor-core operands");
+  constexpr uint32_t kOne = DT<T>::id == BACS_BF16 ? 0x3F803F80u : 0x3C003C00u;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int cb = (blockIdx.x * kSumMmaWarps + wid) * 16;
+  if (cb >= D) return;
+  const int g = lane >> 2, tig = lane & 3;
+  const T* rowA = feat + ((int64_t)b * D + cb + g) * hw + tig * 8;
+  const T* rowB = rowA + (int64_t)8 * hw;
+  const int64_t* lab = labels + (int64_t)b * hw + tig * 8;
+  float d[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) d[nt][0] = d[nt][1] = d[nt][2] = d[nt][3] = 0.f;
+  constexpr int U = 2;  // 32-pixel chunks in flight per lane
+  for (int q0 = 0; q0 < hw; q0 += 32 * U) {
+    uint4 ra[U], rb[U];
+    longlong2 l2[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int q = q0 + u * 32;
+      if (q < hw) {
+        ra[u] = __ldg(reinterpret_cast<const uint4*>(rowA + q));
+        rb[u] = __ldg(reinterpret_cast<const uint4*>(rowB + q));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) l2[u][k] = __ldg(reinterpret_cast<const longlong2*>(lab + q) + k);
+      } else {
+        ra[u] = rb[u] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) l2[u][k] = make_longlong2(-1, -1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      // the lane's 8 labels as bytes (0xff: outside [0, K))
+      uint32_t tw[2] = {0u, 0u};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const long long l = (e & 1) ? l2[u][e >> 1].y : l2[u][e >> 1].x;
+        const uint32_t byte = (l >= 0 && l < K) ? (uint32_t)l : 0xffu;
+        tw[e >> 2] |= byte << (8 * (e & 3));
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t a0 = j ? ra[u].z : ra[u].x, a1 = j ? rb[u].z : rb[u].x;
+        const uint32_t a2 = j ? ra[u].w : ra[u].y, a3 = j ? rb[u].w : rb[u].y;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const uint32_t m = __vcmpeq4(tw[j], (uint32_t)(8 * nt + g) * 0x01010101u);
+          cs_mma_16816<T>(d[nt], a0, a1, a2, a3, __byte_perm(m, 0u, 0x1100) & kOne, __byte_perm(m, 0u, 0x3322) & kOne);
+        }
+      }
+    }
+  }
+  // D fragment: d[nt][0..1] = (row g, classes 8 nt + 2 tig + {0,1}), d[nt][2..3] = (row g + 8, same classes)
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = 8 * nt + 2 * tig + (e & 1), c = cb + g + (e >> 1) * 8;
+      if (k < K) partial[((int64_t)b * D + c) * K + k] = d[nt][e];
+    }
+  }
+}
+
 // sums[k][c] = sum_b partial[b][c][k] (fp64, images in order: deterministic)
 __global__ void __launch_bounds__(256) class_sums_finalize_kernel(const float* __restrict__ partial, int B, int D, int K,
                                                                   double* __restrict__ sums) {
@@ -535,6 +623,29 @@ int bacs_class_sums(const void* features, int dtype, int32_t B, int32_t D, int32
   float* partial = reinterpret_cast<float*>(workspace);
   cudaStream_t s = (cudaStream_t)stream;
   dim3 grid((D + warps - 1) / warps, B);
+  // 16-bit features on 32-pixel chunks, K <= 160 (ADE20K's 151): one-hot GEMM on the tensor cores (BACS_NO_SUMS_MMA=1: off)
+  const bool mma = dtype != BACS_F32 && (h * w) % 32 == 0 && D % 16 == 0 && K <= 160 &&
+                   (reinterpret_cast<uintptr_t>(features) & 15) == 0 && (reinterpret_cast<uintptr_t>(labels_down) & 15) == 0 &&
+                   getenv("BACS_NO_SUMS_MMA") == nullptr;
+  if (mma) {
+    dim3 mgrid((D / 16 + cd::kSumMmaWarps - 1) / cd::kSumMmaWarps, B);
+    const int nt = (K + 7) / 8;
+#define BACS_CS_LAUNCH(TT, NTV)                                                                                  \
+  cd::class_sums_mma_kernel<TT, NTV><<<mgrid, 32 * cd::kSumMmaWarps, 0, s>>>(reinterpret_cast<const TT*>(features), D, \
+                                                                               h * w, labels_down, K, partial)
+#define BACS_CS_NT(TT)                          \
+  do {                                          \
+    if (nt <= 4) BACS_CS_LAUNCH(TT, 4);         \
+    else if (nt <= 8) BACS_CS_LAUNCH(TT, 8);    \
+    else if (nt <= 12) BACS_CS_LAUNCH(TT, 12);  \
+    else if (nt <= 16) BACS_CS_LAUNCH(TT, 16);  \
+    else BACS_CS_LAUNCH(TT, 20);                \
+  } while (0)
+    if (dtype == BACS_BF16) BACS_CS_NT(__nv_bfloat16);
+    else BACS_CS_NT(__half);
+#undef BACS_CS_NT
+#undef BACS_CS_LAUNCH
+  } else
   BACS_DISPATCH_DTYPE(dtype, TT, {
     auto kern = cd::class_sums_kernel<TT>;
     if (smem > 48 * 1024) {

@@ -718,7 +718,8 @@ def test_class_distance_limits(ops):
 
 
 @pytest.mark.parametrize("B,D,h,w,K,dtype", [(3, 64, 8, 16, 21, torch.float32), (2, 40, 5, 7, 151, torch.bfloat16),
-                                            (4, 512, 32, 32, 151, torch.bfloat16), (1, 8, 3, 3, 256, torch.float16)])
+                                            (4, 512, 32, 32, 151, torch.bfloat16), (1, 8, 3, 3, 256, torch.float16),
+                                            (2, 32, 8, 8, 21, torch.float16), (3, 48, 4, 16, 100, torch.bfloat16)])
 def test_class_sums(ops, B, D, h, w, K, dtype):
     """per-class segmented sums (G = K) and counts against index_add / bincount"""
     g = torch.Generator().manual_seed(K + D)
