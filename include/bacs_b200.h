@@ -93,7 +93,12 @@ int bacs_label_downsample_task(const int64_t* labels, int B, int H, int W, int h
  * mode 1 = per-channel sums (what the reference computes when B == 1; decomposable
  *          across ranks).
  * sums fp64[T,D] and counts fp64[T] are OVERWRITTEN (fp64 so that the packed all-reduce
- * of sums|counts is exact for counts).  workspace >= bacs_proto_workspace_bytes. */
+ * of sums|counts is exact for counts).  workspace >= bacs_proto_workspace_bytes.
+ * 16-bit features with h*w a multiple of 32 and D a multiple of 16 run as a one-hot GEMM on the
+ * tensor cores whose per-(image, channel, task) totals are added into sums with fp64 atomics
+ * (exact, hence order-independent, unless the ~B fp32-valued addends of a row span more than
+ * 29 binary orders of magnitude); other inputs use the shared-memory-table kernel and a gather
+ * pass in a fixed order. */
 size_t bacs_proto_workspace_bytes(int B, int D, int T);
 int bacs_proto_accumulate(const void* features, int dtype, int B, int D, int h, int w,
                           const int8_t* task, const int32_t* rank, const int32_t* n_bt, int T,
