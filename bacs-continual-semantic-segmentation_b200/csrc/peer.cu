@@ -57,6 +57,8 @@ __global__ void __launch_bounds__(1024) peer_allreduce_update_kernel(PeerPtrs pp
                                                                      int count_is_int64, int Tn, int D,
                                                                      int32_t* __restrict__ ready) {
   __shared__ int s_timeout;
+  pdl_wait();     // `packed` comes from the launches before this one; the launch itself overlaps their tail
+  pdl_trigger();  // the next launch (seen heads) may become resident; it waits for this grid's completion itself
   const unsigned int step = *step_dev + 1u;
   const int slot = (int)(step & 1u);
   double* mine = pp.buf[rank] + (size_t)slot * n_max;
@@ -86,10 +88,30 @@ __global__ void __launch_bounds__(1024) peer_allreduce_update_kernel(PeerPtrs pp
     }
     return;
   }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    double s = 0.0;
-    for (int r = 0; r < world; ++r) s += ld_relaxed_sys_f64(pp.buf[r] + (size_t)slot * n_max + i);
-    packed[i] = s;
+  // every peer value of two elements of a thread is requested before the first add: one NVLink round trip per pair of
+  // elements instead of one per (element, peer) -- the loads are volatile asm and are not hoisted above the adds otherwise
+  for (int i0 = threadIdx.x; i0 < n; i0 += 2 * blockDim.x) {
+    const int i1 = i0 + blockDim.x;
+    double s0 = 0.0, s1 = 0.0;
+    for (int rg = 0; rg < world; rg += 8) {  // eight peers at a time (registers), rank order: bit-identical on every rank
+      double v0[8], v1[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v0[k] = v1[k] = 0.0;
+        if (rg + k < world) {
+          v0[k] = ld_relaxed_sys_f64(pp.buf[rg + k] + (size_t)slot * n_max + i0);
+          if (i1 < n) v1[k] = ld_relaxed_sys_f64(pp.buf[rg + k] + (size_t)slot * n_max + i1);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (rg + k < world) {
+          s0 += v0[k];
+          s1 += v1[k];
+        }
+    }
+    packed[i0] = s0;
+    if (i1 < n) packed[i1] = s1;
   }
   if (proto == nullptr) return;
   __syncthreads();  // packed[] (global, this block) is complete
@@ -163,8 +185,8 @@ int bacs_peer_allreduce(double* packed, int n, int n_max, int rank, int world, c
     pp.buf[r] = r < world ? reinterpret_cast<double*>(peer_buf_host[r]) : nullptr;
     pp.flag[r] = r < world ? reinterpret_cast<unsigned int*>(peer_flag_host[r]) : nullptr;
   }
-  peer_allreduce_update_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pp, rank, world, n, n_max, g_peer_timeout_ns, packed, step_dev, error_dev,
-                                                                    proto, count, count_is_int64, T, D, ready);
+  launch_pdl(peer_allreduce_update_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, pp, rank, world, n, n_max,
+             g_peer_timeout_ns, packed, step_dev, error_dev, proto, count, count_is_int64, T, D, ready);
   BACS_CHECK_LAUNCH("bacs_peer_allreduce");
   return BACS_OK;
 }
