@@ -645,7 +645,7 @@ int bacs_class_sums(const void* features, int dtype, int32_t B, int32_t D, int32
     else BACS_CS_NT(__half);
 #undef BACS_CS_NT
 #undef BACS_CS_LAUNCH
-  } else
+  } else {
   BACS_DISPATCH_DTYPE(dtype, TT, {
     auto kern = cd::class_sums_kernel<TT>;
     if (smem > 48 * 1024) {
@@ -660,6 +660,7 @@ int bacs_class_sums(const void* features, int dtype, int32_t B, int32_t D, int32
     kern<<<grid, 32 * cd::kSumWarps, smem, s>>>(reinterpret_cast<const TT*>(features), D, h * w, labels_down, K, warps, vec,
                                                  partial);
   });
+  }
   BACS_CHECK_LAUNCH("bacs_class_sums");
   const int64_t n = (int64_t)D * K;
   cd::class_sums_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(partial, B, D, K, sums);

@@ -662,7 +662,7 @@ static int proto_accumulate_impl(const void* features, int dtype, int B, int D, 
     else BACS_MMA_NT(__half);
 #undef BACS_MMA_NT
 #undef BACS_MMA_LAUNCH
-  } else
+  } else {
   BACS_DISPATCH_DTYPE(dtype, TT, {
     if (vec) {
       auto kern = proto_accumulate_vec_kernel<TT>;
@@ -680,6 +680,7 @@ static int proto_accumulate_impl(const void* features, int dtype, int B, int D, 
                  reinterpret_cast<const TT*>(features), B, D, hw, task, rank, n_bt, T, mode, partial, count_raw, count_is_int64, snap);
     }
   });
+  }
   BACS_CHECK_LAUNCH("bacs_proto_accumulate");
   launch_pdl(proto_finalize_kernel, dim3(T, (D + kFinRows - 1) / kFinRows), dim3(kFinRows * kFinLanes), 0, s, partial, B, D,
              n_bt, T, mode, sums, counts, proto, count, count_is_int64, (const unsigned long long*)snap, ready, mma ? 0 : 1);
